@@ -1,0 +1,164 @@
+/*
+ * stedm_b200 — C ABI of the sm_100a kernel library behind STEDM's sampling path.
+ *
+ * The reference (OettlM/STEDM) is 100 % Python and has no FFI of its own; this header is the
+ * boundary a maintainer binds with ctypes.  Each entry point names the reference call
+ * site(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library never frees or
+ *     retains memory, never allocates, never synchronises) unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and is
+ *     CUDA-graph capturable;
+ *   - return value 0 = enqueued; negative = error (STEDM_ERR_*), message via stedm_last_error() (thread local);
+ *   - activations inside the U-Net / VAE are NHWC ("channels last"), dtype tag STEDM_F32 or STEDM_BF16;
+ *     tensors crossing the reference-facing Python API are NCHW fp32, exactly as in the reference.
+ */
+#ifndef STEDM_B200_H
+#define STEDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEDM_ABI_VERSION 1
+
+#define STEDM_F32 0
+#define STEDM_BF16 1
+
+#define STEDM_ERR_ARG (-1)
+#define STEDM_ERR_CUDA (-2)
+#define STEDM_ERR_UNSUPPORTED (-3)
+
+int stedm_abi_version(void);
+const char* stedm_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM available), else 0. */
+int stedm_device_supported(void);
+
+/* ----------------------------------------------------------------------------------------------------
+ * K11  Classifier-free-guidance combine + std-rescale + DDIM update, one kernel.
+ * Replaces DDIMSampler.p_sample_ddim's elementwise tail, ldm/models/diffusion/ddim.py:177-209:
+ *   e_w = e_u + w (e_c - e_u);  e = phi * e_w * std_{C,H}(e_c)/std_{C,H}(e_w) + (1-phi) e_c   (guided != 0)
+ *   pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);  x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) e + sigma*noise
+ * The std is unbiased and taken over dims (1,2) = channels and height only (shape (B,1,1,W)) as the reference does.
+ * All tensors NCHW fp32 (B,C,H,W); e_u ignored when guided == 0; noise may be NULL (sigma*noise skipped).
+ */
+int stedm_cfg_ddim_step(const float* e_c, const float* e_u, const float* x, const float* noise, float* x_prev,
+                        float* pred_x0, int batch, int channels, int height, int width, int guided, float cfg_scale,
+                        float phi, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * K7  GroupNorm(32 groups) statistics and fused normalise + affine (+ SiLU) (+ channel concat).
+ * Replaces GroupNorm32 + nn.SiLU (ldm/modules/diffusionmodules/util.py:199-216, openaimodel.py:214-216, 239-241, 729-731),
+ * VAE Normalize + swish (ldm/modules/diffusionmodules/model.py:33-39) and the th.cat of skip tensors that
+ * precedes them (openaimodel.py:800).
+ * Input = channel concat [x0 (c0 ch) | x1 (c1 ch)] of NHWC tensors (x1 NULL when c1 == 0); x1 may have a smaller
+ * batch x1_batch that is broadcast as b % x1_batch (shared encoder skips under batched guidance).
+ * stats: double [batch][32][2] = (sum, sum of squares); stedm_gn_stats ACCUMULATES, caller zeroes it first.
+ */
+int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
+                   double* stats, void* stream);
+int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
+                   const double* stats, const float* gamma, const float* beta, float eps, int apply_silu, void* out,
+                   int out_dtype, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * K1/K2/K3/K4/K9/K10  Convolution as implicit GEMM, M = B*Ho*Wo pixels, N = Cout, K = k*k*(c0+c1).
+ * Replaces nn.Conv2d 3x3 / 1x1 and nn.Conv1d k=1 call sites: openaimodel.py:120, 164-166, 217, 243, 254, 326, 334,
+ * 542, 732; model.py:47-51, 92-119, 156-175, 487, 529; autoencoder.py:43 — with the epilogue fusing bias, the
+ * per-sample embedding add (openaimodel.py:278-287), and the residual / skip add (openaimodel.py:288, model.py:141).
+ */
+typedef struct stedm_conv_desc {
+  const void* x0;      /* NHWC source 0 [batch, in_h, in_w, c0] */
+  const void* x1;      /* NHWC source 1 [x1_batch, in_h, in_w, c1] or NULL: input is the concat [x0 | x1] */
+  const void* weight;  /* tensor-core path: bf16 [cout][k*k*(c0+c1)] (tap-major, channel-minor);
+                          SIMT path: fp32 [k*k*(c0+c1)][cout] */
+  const float* bias;   /* [cout] or NULL */
+  const float* emb;    /* per-sample additive vector emb[b*emb_stride + n], or NULL */
+  const void* residual;/* NHWC [batch, out_h, out_w, cout] added in the epilogue, or NULL */
+  void* out;           /* NHWC [batch, out_h, out_w, cout], or NCHW when out_nchw != 0 */
+  int32_t c0, c1;
+  int32_t in_dtype;    /* dtype of x0/x1 */
+  int32_t batch, in_h, in_w;
+  int32_t x1_batch;    /* 0 => batch */
+  int32_t ksize;       /* 1 or 3 (padding = ksize/2) */
+  int32_t stride;      /* 1 or 2 */
+  int32_t upsample;    /* 1 => nearest x2 upsample fused in front of the conv (F.interpolate + conv) */
+  int32_t emb_stride;
+  int32_t res_dtype;
+  int32_t out_dtype;
+  int32_t out_nchw;
+  int32_t cout;
+} stedm_conv_desc;
+
+/* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,
+ * upsample 0, c0 % 64 == 0, c1 % 64 == 0, cout % 16 == 0, out NHWC. */
+int stedm_conv_tc(const stedm_conv_desc* d, void* stream);
+/* General fp32-accumulate SIMT implicit GEMM: the fp32 parity mode and every shape the tensor-core path rejects. */
+int stedm_conv_simt(const stedm_conv_desc* d, void* stream);
+
+/* Batched GEMM C[z] = alpha * A[z] * op(B[z]) on CUDA cores (fp32 mode attention: QK^T and PV,
+ * openaimodel.py:388-393, model.py:185-197).  z = (zb, zh): pointer offset = zb*stride_b + zh*stride_h (elements).
+ * A is [m][k] row-major with leading dimension lda; B is [n][k] (b_is_nk != 0) or [k][n]; C is [m][n] with ldc. */
+int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_ab, int dtype_c, int m, int n, int k, int lda,
+                    int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb, long long a_sh, long long b_sb,
+                    long long b_sh, long long c_sb, long long c_sh, float alpha, void* stream);
+/* In-place row softmax over the last dimension of a [rows][cols] fp32 matrix (openaimodel.py:392, model.py:190). */
+int stedm_softmax_rows(float* x, long long rows, int cols, void* stream);
+
+/* K5/K6  Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online fp32 softmax).
+ * q, k, v: bf16, token-major: element (b, h, t, c) at base + b*stride_b + h*stride_h + t*stride_t + c.
+ * out: bf16 [batch][tokens][heads*head_dim].  scale multiplies q.k (= ch^-1/2 for both reference attentions).
+ * Replaces QKVAttentionLegacy.forward (openaimodel.py:378-394) and AttnBlock's bmm/softmax/bmm (model.py:178-197). */
+int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int tokens,
+                       int head_dim, long long stride_b, long long stride_h, long long stride_t, float scale,
+                       void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Data movement helpers.
+ */
+/* K9 (unfused form): nearest x2 upsample, NHWC [b,h,w,c] -> [b,2h,2w,c] (openaimodel.py:129, model.py:54). */
+int stedm_upsample_nearest2x(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
+/* K2 helper: gather the 3x3 / stride 2 / pad 1 receptive fields: NHWC [b,h,w,c] -> [b,h/2,w/2,9*c] (tap-major), so the
+ * Downsample conv (openaimodel.py:164-166) runs as a plain GEMM on the tensor-core path. */
+int stedm_im2col_3x3_s2(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
+/* DiffusionWrapper 'hybrid' input concat (ldm/models/diffusion/ddpm.py:1414-1415): NCHW fp32 sources [x0 | x1] ->
+ * NHWC `out_dtype` with channels zero-padded to c_pad.  x1 may be NULL. */
+int stedm_pack_nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* out, int out_dtype, int batch,
+                            int hw, int c_pad, void* stream);
+/* NHWC (any dtype) -> NCHW fp32 (API boundary). */
+int stedm_nhwc_to_nchw_f32(const void* x, int dtype, float* out, int batch, int hw, int c, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * K8  Embedding path.
+ * timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out[b] = [cos(t f) | sin(t f)], dim even. */
+int stedm_timestep_embedding(const long long* t, float* out, int batch, int dim, void* stream);
+/* out[b][n] = bias[n] + sum_k act(in[b][k]) * w[n][k], act = SiLU when silu_in != 0 (nn.Linear (out,in) layout).
+ * Covers time_embed (openaimodel.py:530-534) and all emb_layers (openaimodel.py:231-237) in one launch when their
+ * weights are stacked along n. */
+int stedm_linear(const float* in, const float* w, const float* bias, float* out, int batch, int k, int n,
+                 int silu_in, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * K12  VQ nearest-code lookup (taming VectorQuantizer2.forward via ldm/models/autoencoder.py:277):
+ * argmin_n |z|^2 + |e_n|^2 - 2 z.e_n over the codebook [n_codes][c] (fp32), first minimum wins (torch.argmin);
+ * z, zq NCHW fp32 [batch, c, hw]; idx int32 [batch*hw] (may be NULL).  c <= 8. */
+int stedm_vq_nearest(const float* z, const float* codebook, float* zq, int* idx, int batch, int c, int hw,
+                     int n_codes, void* stream);
+
+/* K13  SpatialRescaler (ldm/modules/encoders/modules.py:123-130): n_stages x bilinear 0.5 (= 2x2 mean each) then a
+ * bias-free 1x1 conv.  seg: NCHW fp32 [b, cin, p, p]; w: [cout][cin]; out NCHW fp32 [b, cout, p>>n_stages, ...]. */
+int stedm_spatial_rescale(const float* seg, const float* w, float* out, int batch, int cin, int cout, int p,
+                          int n_stages, void* stream);
+
+/* predict_step tail (modules/ldm_diffusion.py:94-96): clip to [-1,1], (x+1)*127.5, truncating uint8 cast,
+ * NCHW fp32 -> NHWC uint8. */
+int stedm_image_to_uint8(const float* img, uint8_t* out, int batch, int c, int hw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEDM_B200_H */

@@ -1,0 +1,341 @@
+"""CPU oracle for STEDM's sampling path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A functional (state-dict in, tensors out) fp32 restatement of what the reference executes for
+``predict_step``: conditioning -> classifier-free-guided DDIM loop over the eps U-Net -> VQ first-stage
+decode -> uint8 images.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this file; ``stedm_b200/`` never does.
+
+Parity pinning: the reference ships NO tests, golden vectors or fixtures, so this oracle is
+pinned against outputs of the reference's own code run in the build container through
+``oracle/ref_shims.py`` — see ``oracle/make_golden.py`` (which also asserts oracle == reference) and the
+committed ``tests/golden/*.npz``.  Third-party arithmetic: taming ``VectorQuantizer2`` (un-vendored, pinned
+only to @master) is restated in ``vq_quantize``; torchvision ``swin_v2_t`` (0.18.1 pinned, 0.26 here) is
+called as the library it is.
+
+All arithmetic is float32 on the CPU (no TF32), tensors are NCHW like the reference.  Every function cites
+the reference lines it restates (paths relative to /root/reference).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+UNET = "model.diffusion_model."
+VAE = "first_stage_model."
+
+
+# --------------------------------------------------------------------------------------------------
+# schedules
+# --------------------------------------------------------------------------------------------------
+def alphas_cumprod_linear(timesteps=1000, linear_start=0.0015, linear_end=0.0205):
+    """float64 betas -> cumprod -> float32, ldm/modules/diffusionmodules/util.py:21-25 and
+    ldm/models/diffusion/ddpm.py:120-140.  Returns (alphas_cumprod fp32 ndarray, float64 ndarray)."""
+    betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+    ac64 = np.cumprod(1.0 - betas, axis=0)
+    return ac64.astype(np.float32), ac64
+
+
+def ddim_timesteps(S, T=1000):
+    """uniform discretisation, util.py:46-60: c = T // S; range(0, T, c) + 1."""
+    c = T // S
+    return np.asarray(list(range(0, T, c))) + 1
+
+
+def ddim_tables(S, eta=0.0, T=1000, linear_start=0.0015, linear_end=0.0205):
+    """Per-index fp32 scalars used by p_sample_ddim (ddim.py:24-53, 195-198; util.py:63-74).
+
+    ``alphas`` is a gather from the fp32 alphas_cumprod; ``alphas_prev`` = [ac[0]] + ac[ts[:-1]];
+    sigma computed in float64 from fp32 alphas then rounded to fp32 by ``torch.full``.
+    """
+    ac32, _ = alphas_cumprod_linear(T, linear_start, linear_end)
+    ts = ddim_timesteps(S, T)
+    a = ac32[ts]                                                     # fp32
+    a_prev = np.asarray([ac32[0]] + ac32[ts[:-1]].tolist())          # float64 holding fp32 values
+    sig = eta * np.sqrt((1 - a_prev) / (1 - a.astype(np.float64)) * (1 - a.astype(np.float64) / a_prev))
+    sqrt_1m = np.sqrt(1.0 - a)                                       # fp32 (np.sqrt on the fp32 tensor)
+    return dict(timesteps=ts, a_t=a.astype(np.float32), a_prev=a_prev.astype(np.float32),
+                sigma=sig.astype(np.float32), sqrt_one_minus_a=sqrt_1m.astype(np.float32))
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    """[cos | sin] sinusoid, util.py:151-171."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+# --------------------------------------------------------------------------------------------------
+# U-Net (openaimodel.py)
+# --------------------------------------------------------------------------------------------------
+def _gn(x, sd, key, eps):
+    return F.group_norm(x.float(), 32, sd[key + ".weight"], sd[key + ".bias"], eps)
+
+
+def _conv(x, sd, key, stride=1, padding=1):
+    return F.conv2d(x, sd[key + ".weight"], sd.get(key + ".bias"), stride=stride, padding=padding)
+
+
+def resblock(x, emb, sd, p):
+    """ResBlock._forward, openaimodel.py:268-288 (use_scale_shift_norm=False, no up/down, dropout 0)."""
+    h = _conv(F.silu(_gn(x, sd, p + "in_layers.0", 1e-5)), sd, p + "in_layers.2")
+    e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
+    h = h + e[:, :, None, None]
+    h = _conv(F.silu(_gn(h, sd, p + "out_layers.0", 1e-5)), sd, p + "out_layers.3")
+    if (p + "skip_connection.weight") in sd:
+        x = _conv(x, sd, p + "skip_connection", padding=0)
+    return x + h
+
+
+def attention_block(x, sd, p, num_heads):
+    """AttentionBlock._forward + QKVAttentionLegacy, openaimodel.py:340-346, 378-394.
+    qkv channels are head-major [h0: q|k|v, h1: q|k|v, ...]; scale ch^-1/4 on q and k; fp32 softmax."""
+    b, c, hh, ww = x.shape
+    xf = x.reshape(b, c, -1)
+    n = F.group_norm(xf, 32, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    qkv = F.conv1d(n, sd[p + "qkv.weight"], sd[p + "qkv.bias"])
+    ch = c // num_heads
+    q, k, v = qkv.reshape(b * num_heads, 3 * ch, -1).split(ch, dim=1)
+    s = 1.0 / math.sqrt(math.sqrt(ch))
+    w = torch.einsum("bct,bcs->bts", q * s, k * s)
+    w = torch.softmax(w.float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", w, v).reshape(b, c, -1)
+    h = F.conv1d(a, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+    return (xf + h).reshape(b, c, hh, ww)
+
+
+def unet_structure(sd, prefix=UNET):
+    """Recover the block list from the state-dict keys (UNetModel.__init__, openaimodel.py:536-733)."""
+    n_in = 1 + max(int(k[len(prefix) + 13:].split(".")[0]) for k in sd if k.startswith(prefix + "input_blocks."))
+    n_out = 1 + max(int(k[len(prefix) + 14:].split(".")[0]) for k in sd if k.startswith(prefix + "output_blocks."))
+    return n_in, n_out
+
+
+def unet_forward(sd, x, t, context, num_heads=8, prefix=UNET):
+    """UNetModel.forward, openaimodel.py:761-806, for the shipped config (17 ResBlock + 1 ResBlockStyle +
+    1 AttentionBlock; the style vector replaces the timestep embedding in middle_block.1, :291-297)."""
+    P = prefix
+    mc = sd[P + "time_embed.0.weight"].shape[1]
+    emb = timestep_embedding(t, mc)
+    emb = F.linear(emb, sd[P + "time_embed.0.weight"], sd[P + "time_embed.0.bias"])
+    emb = F.linear(F.silu(emb), sd[P + "time_embed.2.weight"], sd[P + "time_embed.2.bias"])
+    n_in, n_out = unet_structure(sd, P)
+    hs = []
+    h = x.float()
+    for i in range(n_in):
+        p = f"{P}input_blocks.{i}."
+        if (p + "0.weight") in sd:                       # stem conv (:539-545)
+            h = _conv(h, sd, p + "0")
+        elif (p + "0.op.weight") in sd:                  # Downsample: conv3x3 stride 2 pad 1 (:164-166)
+            h = _conv(h, sd, p + "0.op", stride=2)
+        else:
+            h = resblock(h, emb, sd, p + "0.")
+        hs.append(h)
+    p = P + "middle_block."
+    h = resblock(h, emb, sd, p + "0.")
+    h = resblock(h, context.float(), sd, p + "1.block.")  # ResBlockStyle (:291-297; dispatch :93-101)
+    h = attention_block(h, sd, p + "2.", num_heads)
+    h = resblock(h, emb, sd, p + "3.")
+    for i in range(n_out):
+        p = f"{P}output_blocks.{i}."
+        h = torch.cat([h, hs.pop()], dim=1)               # (:800)
+        h = resblock(h, emb, sd, p + "0.")
+        if (p + "1.conv.weight") in sd:                   # Upsample: nearest x2 then conv3x3 (:123-132)
+            h = _conv(F.interpolate(h, scale_factor=2, mode="nearest"), sd, p + "1.conv")
+    h = F.silu(_gn(h, sd, P + "out.0", 1e-5))
+    return _conv(h, sd, P + "out.2")
+
+
+def apply_model(sd, x, t, cond, num_heads=8):
+    """LatentDiffusion.apply_model -> DiffusionWrapper.forward 'hybrid', ddpm.py:894-995, 1414-1417."""
+    xc = torch.cat([x] + list(cond["c_concat"]), dim=1)
+    cc = torch.cat(list(cond["c_crossattn"]), dim=1)
+    return unet_forward(sd, xc, t, cc, num_heads)
+
+
+# --------------------------------------------------------------------------------------------------
+# DDIM step with STEDM's rescaled classifier-free guidance (ddim.py:164-210)
+# --------------------------------------------------------------------------------------------------
+def cfg_combine(e_c, e_u, scale, phi=0.7):
+    """ddim.py:177-184.  std over dims (1, 2) = channels and HEIGHT only, unbiased, keepdim -> (B,1,1,W)."""
+    e_w = e_u + scale * (e_c - e_u)
+    dims = tuple(range(1, e_c.ndim - 1))
+    resc = e_w * (e_c.std(dim=dims, keepdim=True) / e_w.std(dim=dims, keepdim=True))
+    return resc * phi + (1.0 - phi) * e_c
+
+
+def ddim_update(x, e, a_t, a_prev, sigma, sqrt_1m_at, noise=None):
+    """ddim.py:195-209 with fp32 scalars (torch.full of python floats -> fp32 tensors)."""
+    f = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    a_t, a_prev, sigma, sqrt_1m_at = f(a_t), f(a_prev), f(sigma), f(sqrt_1m_at)
+    pred_x0 = (x - sqrt_1m_at * e) / a_t.sqrt()
+    dir_xt = (1.0 - a_prev - sigma ** 2).sqrt() * e
+    x_prev = a_prev.sqrt() * pred_x0 + dir_xt
+    if noise is not None:
+        x_prev = x_prev + sigma * noise
+    return x_prev, pred_x0
+
+
+def ddim_sample(sd, cond, uncond, x_T, S=50, eta=0.0, cfg_scale=1.5, num_heads=8, log_every_t=1000,
+                max_steps=None, noise_fn=None):
+    """DDIMSampler.sample / ddim_sampling, ddim.py:55-162.  ``max_steps`` truncates the loop (tests)."""
+    tab = ddim_tables(S, eta)
+    ts = tab["timesteps"]
+    total = ts.shape[0]
+    img = x_T
+    inter = {"x_inter": [img], "pred_x0": [img]}
+    for i, step in enumerate(np.flip(ts)):
+        if max_steps is not None and i >= max_steps:
+            break
+        index = total - i - 1
+        t = torch.full((img.shape[0],), int(step), dtype=torch.long)
+        e = apply_model(sd, img, t, cond, num_heads)
+        if uncond is not None and cfg_scale != 1.0:
+            e_u = apply_model(sd, img, t, uncond, num_heads)
+            e = cfg_combine(e, e_u, cfg_scale)
+        noise = noise_fn(img.shape) if (noise_fn is not None) else None
+        img, pred_x0 = ddim_update(img, e, tab["a_t"][index], tab["a_prev"][index], tab["sigma"][index],
+                                   tab["sqrt_one_minus_a"][index], noise)
+        if index % log_every_t == 0 or index == total - 1:
+            inter["x_inter"].append(img)
+            inter["pred_x0"].append(pred_x0)
+    return img, inter
+
+
+# --------------------------------------------------------------------------------------------------
+# conditioning: SpatialRescaler (encoders/modules.py:104-133) and Agg_Mean (networks/agg_blocks.py:57-75)
+# --------------------------------------------------------------------------------------------------
+def spatial_rescaler(sd, seg_nchw, n_stages=2):
+    x = seg_nchw
+    for _ in range(n_stages):
+        x = F.interpolate(x, scale_factor=0.5, mode="bilinear")
+    return F.conv2d(x, sd["cond_stage_model.channel_mapper.weight"])
+
+
+_SWIN_CACHE = {}
+
+
+def swin_embedder(sd, prefix="agg_block.embedder."):
+    """torchvision swin_v2_t with head = Linear(768, 512), networks/s_zss_dm.py:19-20 (library call)."""
+    import torchvision
+    key = id(sd)
+    if key not in _SWIN_CACHE:
+        m = torchvision.models.get_model("swin_v2_t")
+        m.head = torch.nn.Linear(768, 512)
+        sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+        m.load_state_dict(sub, strict=True)
+        _SWIN_CACHE.clear()
+        _SWIN_CACHE[key] = m.eval()
+    return _SWIN_CACHE[key]
+
+
+@torch.no_grad()
+def agg_mean(sd, style_bnhwc):
+    b, n = style_bnhwc.shape[:2]
+    imgs = style_bnhwc.permute(0, 1, 4, 2, 3).reshape(b * n, 3, *style_bnhwc.shape[2:4])
+    f = swin_embedder(sd)(imgs)
+    return f.reshape(b, n, -1).mean(dim=1)
+
+
+@torch.no_grad()
+def get_conditioning(sd, seg_bhwc, style_bnhwc):
+    """S_ZSS_DM.get_input, networks/s_zss_dm.py:45-60, minus the discarded VAE encode of the image."""
+    seg = seg_bhwc.permute(0, 3, 1, 2).contiguous().float()            # ddpm.py:332-338
+    return {"c_concat": [spatial_rescaler(sd, seg)], "c_crossattn": [agg_mean(sd, style_bnhwc)]}
+
+
+# --------------------------------------------------------------------------------------------------
+# first stage decode (ldm/models/autoencoder.py:274-282; ldm/modules/diffusionmodules/model.py:462-568)
+# --------------------------------------------------------------------------------------------------
+def vq_quantize(z, codebook):
+    """taming VectorQuantizer2.forward (see module docstring): nearest row of ``codebook`` per pixel."""
+    b, c, h, w = z.shape
+    zf = z.permute(0, 2, 3, 1).reshape(-1, c)
+    d = (zf ** 2).sum(1, keepdim=True) + (codebook ** 2).sum(1) - 2.0 * zf @ codebook.t()
+    idx = torch.argmin(d, dim=1)
+    zq = codebook[idx].reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+    return zq, idx
+
+
+def _vae_resblock(x, sd, p):
+    """ResnetBlock.forward with temb=None, model.py:121-141 (GroupNorm eps 1e-6, :38-39)."""
+    h = _conv(F.silu(_gn(x, sd, p + "norm1", 1e-6)), sd, p + "conv1")
+    h = _conv(F.silu(_gn(h, sd, p + "norm2", 1e-6)), sd, p + "conv2")
+    if (p + "nin_shortcut.weight") in sd:
+        x = _conv(x, sd, p + "nin_shortcut", padding=0)
+    return x + h
+
+
+def _vae_attn(x, sd, p):
+    """AttnBlock.forward, model.py:178-202: single head, d = C, scale C^-1/2."""
+    b, c, hh, ww = x.shape
+    n = _gn(x, sd, p + "norm", 1e-6)
+    q = _conv(n, sd, p + "q", padding=0).reshape(b, c, -1).permute(0, 2, 1)
+    k = _conv(n, sd, p + "k", padding=0).reshape(b, c, -1)
+    v = _conv(n, sd, p + "v", padding=0).reshape(b, c, -1)
+    w = torch.softmax(torch.bmm(q, k) * (int(c) ** -0.5), dim=2)
+    h = torch.bmm(v, w.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + _conv(h, sd, p + "proj_out", padding=0)
+
+
+def vae_decode(sd, z, force_not_quantize=False, prefix=VAE):
+    P = prefix
+    if not force_not_quantize:
+        z, _ = vq_quantize(z, sd[P + "quantize.embedding.weight"])
+    h = _conv(z, sd, P + "post_quant_conv", padding=0)
+    D = P + "decoder."
+    h = _conv(h, sd, D + "conv_in")
+    h = _vae_resblock(h, sd, D + "mid.block_1.")
+    h = _vae_attn(h, sd, D + "mid.attn_1.")
+    h = _vae_resblock(h, sd, D + "mid.block_2.")
+    n_levels = 1 + max(int(k[len(D) + 3:].split(".")[0]) for k in sd if k.startswith(D + "up."))
+    for lvl in reversed(range(n_levels)):
+        i = 0
+        while (f"{D}up.{lvl}.block.{i}.conv1.weight") in sd:
+            h = _vae_resblock(h, sd, f"{D}up.{lvl}.block.{i}.")
+            i += 1
+        if (f"{D}up.{lvl}.upsample.conv.weight") in sd:
+            h = _conv(F.interpolate(h, scale_factor=2.0, mode="nearest"), sd, f"{D}up.{lvl}.upsample.conv")
+    h = F.silu(_gn(h, sd, D + "norm_out", 1e-6))
+    return _conv(h, sd, D + "conv_out")
+
+
+def decode_first_stage(sd, z, force_not_quantize=False, scale_factor=1.0):
+    """LatentDiffusion.decode_first_stage, ddpm.py:708-766 (no split_input_params)."""
+    return vae_decode(sd, (1.0 / scale_factor) * z, force_not_quantize)
+
+
+def to_uint8(img_nchw):
+    """predict_step tail, modules/ldm_diffusion.py:94-96: clip, (x+1)*127.5, TRUNCATING uint8 cast, NHWC."""
+    x = torch.clip(img_nchw, -1, 1)
+    return ((x.permute(0, 2, 3, 1).cpu().numpy() + 1) * 127.5).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------------
+# whole path (modules/ldm_diffusion.py:76-96)
+# --------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def predict_images(sd, seg_bhwc, style_bnhwc, x_T, S=50, eta=0.0, cfg_scale=1.5, max_steps=None):
+    cond = get_conditioning(sd, seg_bhwc, style_bnhwc)
+    if cfg_scale == 1:
+        uncond = None
+    else:
+        uncond = get_conditioning(sd, seg_bhwc, torch.zeros_like(style_bnhwc) - 2)
+    z, _ = ddim_sample(sd, cond, uncond, x_T, S=S, eta=eta, cfg_scale=cfg_scale, max_steps=max_steps)
+    img = decode_first_stage(sd, z)
+    return to_uint8(img), img, z
+
+
+def synthetic_batch(B, P, n_style=1, seed=0):
+    """Synthetic predict batch: low-frequency 2-class layout, U(-1,1) style images."""
+    g = torch.Generator().manual_seed(99 + seed)
+    low = torch.rand(B, 1, 8, 8, generator=g)
+    mask = (F.interpolate(low, size=(P, P), mode="bilinear") > 0.5).float()[:, 0]
+    seg = torch.stack([1.0 - mask, mask], dim=-1)                               # (B,P,P,2) one-hot
+    g2 = torch.Generator().manual_seed(3 + seed)
+    style = torch.rand(B, n_style, P, P, 3, generator=g2) * 2 - 1
+    L = P // 4
+    x_T = torch.stack([torch.randn(3, L, L, generator=torch.Generator().manual_seed(1234 + seed * 100003 + i))
+                       for i in range(B)])
+    return seg, style, x_T

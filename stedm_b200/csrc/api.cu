@@ -1,0 +1,93 @@
+// C-ABI plumbing shared by every entry point: thread-local error string, launch checking, device probe,
+// and the cuTensorMapEncodeTiled driver entry point (resolved at run time, so the library links only cudart).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/stedm_b200.h"
+#include "common.cuh"
+
+namespace stedm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return ERR_CUDA;
+  }
+  return 0;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is unavailable (driver too old or no CUDA device)");
+    return ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor map base address must be 16-byte aligned");
+    return ERR_ARG;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) {
+      set_error("tensor map box dim %d = %u out of range", i, box[i]);
+      return ERR_ARG;
+    }
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (gstr[i] % 16 != 0) {
+      set_error("tensor map stride %d = %llu B is not a multiple of 16", i, (unsigned long long)gstr[i]);
+      return ERR_ARG;
+    }
+  }
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace stedm
+
+extern "C" int stedm_abi_version(void) { return STEDM_ABI_VERSION; }
+
+extern "C" const char* stedm_last_error(void) { return stedm::g_err; }
+
+extern "C" int stedm_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}

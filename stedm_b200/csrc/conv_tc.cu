@@ -1,0 +1,321 @@
+// K1/K3/K4/K10: convolution (3x3 pad 1 or 1x1, stride 1) and plain GEMM as an implicit GEMM on Blackwell's
+// 5th-generation tensor cores: tcgen05.mma (bf16 x bf16 -> fp32) issued by one thread, operands staged in
+// shared memory by TMA with the 128-byte swizzle, accumulator in TMEM, epilogue through tcgen05.ld.
+//
+//   M = B*H*W output pixels (tile 128 = UMMA_M), N = Cout (tile BN = UMMA_N), K = taps * Cin (slab 64).
+//
+// A operand (im2col of the NHWC activation) is never materialised: for filter tap (r, s) the producer issues a
+// 4-D TMA load of the box {64 channels, tile_w, tile_h, tile_b} at pixel offset (s-1, r-1); out-of-bounds rows
+// and columns are zero-filled by the TMA unit, which is exactly the convolution's zero padding.  The box lands
+// in shared memory as 128 rows x 128 B, i.e. the canonical K-major SWIZZLE_128B UMMA layout.  A channel concat
+// [x0 | x1] (openaimodel.py:800) is a second tensor map selected per K slab — no concatenated copy exists.
+// B operand = weights repacked once at load time to bf16 [Cout][tap][Cin] (K-major), 2-D TMA box {64, BN}.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2-5 = epilogue (TMEM lane quadrant = warp % 4).  smem ring of STAGES {A,B} slabs with
+// full/empty mbarriers; tcgen05.commit releases slabs and finally signals the epilogue.
+// Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287) + residual[m][n]
+// (skip connection, openaimodel.py:288), written as bf16 or fp32 NHWC with 16-byte stores.
+#include "../../include/stedm_b200.h"
+#include "common.cuh"
+
+using namespace stedm;
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  const float* bias;
+  const float* emb;
+  const void* residual;
+  void* out;
+  int M, H, W, HW, cout;
+  int taps, ksize;
+  int c0_blks, c_blks;  // 64-channel slabs in source 0 / in the concat
+  int x1_batch;
+  int emb_stride, res_dtype, out_dtype;
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_BLOCKS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int num_kb = p.taps * p.c_blks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
+      const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
+        int dy = 0, dx = 0;
+        if (p.ksize == 3) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+        if (cb < p.c0_blks)
+          tma_load_4d(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
+        else
+          tma_load_4d(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
+        tma_load_2d(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);  // frees the slab once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    const bool valid = m < p.M;
+    const int b = valid ? m / p.HW : 0;
+    const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
+    constexpr int CH = BN < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+      float v[CH];
+      if constexpr (CH == 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      if (!valid) continue;
+      const int n = n0 + c;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        }
+      }
+      if (emb_row) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
+          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        }
+      }
+      const size_t o = static_cast<size_t>(m) * p.cout + n;
+      if (p.residual) {
+        if (p.res_dtype == DT_BF16) {
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            const uint4 u = rp[j / 8];
+            float2 f;
+            f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
+            f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
+            f = unpack_bf16x2(u.z); v[j + 4] += f.x; v[j + 5] += f.y;
+            f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
+          }
+        } else {
+          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o);
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) {
+            const float4 t = rp[j / 4];
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+        }
+      }
+      if (p.out_dtype == DT_BF16) {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[j], v[j + 1]);
+          u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          op[j / 8] = u;
+        }
+      } else {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const TcParams& p,
+              cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;  // per-process; the attribute is per-function and idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.cout / BN);
+  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(ma0, ma1, mw, p);
+  return check_launch("conv_tc");
+}
+
+}  // namespace
+
+extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
+  STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_tc: null pointer");
+  STEDM_REQUIRE(d->in_dtype == DT_BF16, "conv_tc: operands must be bf16");
+  STEDM_REQUIRE(d->stride == 1 && d->upsample == 0 && d->out_nchw == 0,
+                "conv_tc: stride/upsample/NCHW output are handled by im2col_3x3_s2 / upsample_nearest2x / conv_simt");
+  STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
+  STEDM_REQUIRE(d->c0 > 0 && d->c0 % TC_BK == 0 && d->c1 % TC_BK == 0 && (d->c1 == 0 || d->x1),
+                "conv_tc: channel counts must be multiples of 64 (%d, %d)", d->c0, d->c1);
+  STEDM_REQUIRE(d->cout >= 16 && d->cout % 16 == 0, "conv_tc: cout %d must be a multiple of 16", d->cout);
+  const int H = d->in_h, W = d->in_w, B = d->batch;
+  STEDM_REQUIRE(B > 0 && H > 0 && W > 0, "conv_tc: bad shape");
+  // tile geometry: 128 consecutive pixels of the flattened (b, y, x) index must form a TMA box
+  int tw, th, tb;
+  if (W >= TC_BM) {
+    STEDM_REQUIRE(W % TC_BM == 0, "conv_tc: width %d must divide or be a multiple of 128", W);
+    tw = TC_BM; th = 1; tb = 1;
+  } else {
+    STEDM_REQUIRE(TC_BM % W == 0, "conv_tc: width %d must divide or be a multiple of 128", W);
+    tw = W;
+    const int rows = TC_BM / W;
+    if (H >= rows) {
+      STEDM_REQUIRE(H % rows == 0, "conv_tc: height %d incompatible with the 128-pixel tile", H);
+      th = rows; tb = 1;
+    } else {
+      STEDM_REQUIRE(rows % H == 0, "conv_tc: height %d incompatible with the 128-pixel tile", H);
+      th = H; tb = rows / H;
+    }
+  }
+  const int x1b = (d->c1 > 0 && d->x1_batch > 0 && d->x1_batch != B) ? d->x1_batch : 0;
+  if (x1b > 0)
+    STEDM_REQUIRE((static_cast<long long>(x1b) * H * W) % TC_BM == 0 || tb == 1,
+                  "conv_tc: broadcast source batch %d not tile aligned", x1b);
+  const long long M = static_cast<long long>(B) * H * W;
+  STEDM_REQUIRE(M < (1LL << 31), "conv_tc: too many pixels");
+
+  CUtensorMap ma0, ma1, mw;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->c0), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d->c0) * 2, static_cast<uint64_t>(W) * d->c0 * 2,
+                             static_cast<uint64_t>(H) * W * d->c0 * 2};
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    int rc = make_tmap_bf16(&ma0, d->x0, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  if (d->c1 > 0) {
+    const int b1 = x1b > 0 ? x1b : B;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->c1), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(b1)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d->c1) * 2, static_cast<uint64_t>(W) * d->c1 * 2,
+                             static_cast<uint64_t>(H) * W * d->c1 * 2};
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    int rc = make_tmap_bf16(&ma1, d->x1, 4, dims, str, box);
+    if (rc) return rc;
+  } else {
+    ma1 = ma0;
+  }
+  const int ctot = d->c0 + d->c1, taps = d->ksize * d->ksize;
+  const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 16));
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(d->cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(taps) * ctot * 2};
+    const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn)};
+    int rc = make_tmap_bf16(&mw, d->weight, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.bias = d->bias; p.emb = d->emb; p.residual = d->residual; p.out = d->out;
+  p.M = static_cast<int>(M); p.H = H; p.W = W; p.HW = H * W; p.cout = d->cout;
+  p.taps = taps; p.ksize = d->ksize;
+  p.c0_blks = d->c0 / TC_BK; p.c_blks = ctot / TC_BK;
+  p.x1_batch = x1b;
+  p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
+  auto s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_tc<256>(ma0, ma1, mw, p, s);
+    case 128: return launch_tc<128>(ma0, ma1, mw, p, s);
+    case 64: return launch_tc<64>(ma0, ma1, mw, p, s);
+    default: return launch_tc<16>(ma0, ma1, mw, p, s);
+  }
+}

@@ -1,0 +1,207 @@
+// K7: GroupNorm(32 groups) over NHWC tensors, with the channel concat of skip tensors and the SiLU that follow
+// it in the reference folded in.  HBM-bound: the statistics pass reads the input once, the apply pass reads it
+// once and writes the (usually bf16) operand of the consumer convolution.  fp32 statistics per thread, double
+// precision across threads/blocks (GroupNorm32 computes in fp32: ldm/modules/diffusionmodules/util.py:214-216).
+//
+// Layout: one "item" = 8 consecutive channels of one pixel (16 B of bf16 / 32 B of fp32).  A 256-thread block
+// owns one sample and a slice of its pixels; thread -> (pixel lane, channel item) so that a warp touches
+// consecutive 16 B items of the same pixel rows (fully coalesced).
+#include "../../include/stedm_b200.h"
+#include "common.cuh"
+
+using namespace stedm;
+
+namespace {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Pointer to the 8-channel item `item` of pixel `pix` of sample b in the virtual concat [x0 | x1].
+template <typename T>
+__device__ __forceinline__ const T* item_ptr(const T* x0, const T* x1, int b, int b1, size_t pix, int hw, int c0,
+                                             int c1, int item) {
+  const int c = item * 8;
+  if (c < c0) return x0 + (static_cast<size_t>(b) * hw + pix) * c0 + c;
+  return x1 + (static_cast<size_t>(b1) * hw + pix) * c1 + (c - c0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x0, const T* __restrict__ x1,
+                                                              int x1_batch, int hw, int c0, int c1, int pix_per_block,
+                                                              double* __restrict__ stats) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int C = c0 + c1, items = C / 8;
+  const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int tpi = min(items, GN_THREADS);       // threads along the item axis
+  const int lanes = GN_THREADS / tpi;           // pixel lanes
+  const int lane = threadIdx.x / tpi, it0 = threadIdx.x % tpi;
+  const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
+  if (lane < lanes) {
+    for (int item = it0; item < items; item += tpi) {
+      float s[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+      for (int p = p_begin + lane; p < p_end; p += lanes) {
+        float v[8];
+        load8<T>(item_ptr<T>(x0, x1, b, b1, p, hw, c0, c1, item), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] += v[j] * v[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_acc[item * 8 + j], s[j]);
+        atomicAdd(&s_acc[C + item * 8 + j], q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
+    const int cpg = C / GN_GROUPS;
+    double acc = 0.0;
+    for (int c = 0; c < cpg; ++c) acc += static_cast<double>(s_acc[which * C + g * cpg + c]);
+    atomicAdd(&stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which], acc);
+  }
+}
+
+template <typename TI, typename TO, bool kPrecise>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restrict__ x0, const TI* __restrict__ x1,
+                                                              int x1_batch, int hw, int c0, int c1, int pix_per_block,
+                                                              const double* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int apply_silu,
+                                                              TO* __restrict__ out) {
+  extern __shared__ float s_ab[];  // scale[C], shift[C]
+  const int C = c0 + c1, items = C / 8, cpg = C / GN_GROUPS;
+  const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
+  const double n = static_cast<double>(hw) * cpg;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const double sum = stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + 0];
+    const double sq = stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + 1];
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float a = rstd * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - static_cast<float>(mean) * a;
+  }
+  __syncthreads();
+  const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
+  const size_t total = static_cast<size_t>(p_end - p_begin) * items;
+  for (size_t i = threadIdx.x; i < total; i += GN_THREADS) {
+    const int item = static_cast<int>(i % items);
+    const size_t p = p_begin + i / items;
+    float v[8];
+    load8<TI>(item_ptr<TI>(x0, x1, b, b1, p, hw, c0, c1, item), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = v[j] * s_ab[item * 8 + j] + s_ab[C + item * 8 + j];
+      if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
+      v[j] = y;
+    }
+    store8<TO>(out + (static_cast<size_t>(b) * hw + p) * C + item * 8, v);
+  }
+}
+
+int pick_pix_per_block(int batch, int hw, int C) {
+  // aim for >= ~4 waves of 148 SMs x 4 resident blocks while keeping >= 16 KB of input per block
+  const int min_pix = max(1, (16 * 1024) / (C * 2));
+  int blocks_per_sample = max(1, (148 * 16 + batch - 1) / batch);
+  int ppb = (hw + blocks_per_sample - 1) / blocks_per_sample;
+  ppb = max(ppb, min_pix);
+  return min(ppb, hw);
+}
+
+}  // namespace
+
+extern "C" int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0,
+                              int c1, double* stats, void* stream) {
+  const int C = c0 + c1;
+  STEDM_REQUIRE(x0 && stats && (c1 == 0 || x1), "gn_stats: null pointer");
+  STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0,
+                "gn_stats: channels (%d + %d) must be multiples of 8 and sum to a multiple of 32", c0, c1);
+  STEDM_REQUIRE(C <= 4096, "gn_stats: too many channels");
+  const int ppb = pick_pix_per_block(batch, hw, C);
+  dim3 grid((hw + ppb - 1) / ppb, batch);
+  const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (in_dtype == DT_BF16)
+    gn_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(x0),
+                                                                 static_cast<const __nv_bfloat16*>(x1), x1_batch, hw,
+                                                                 c0, c1, ppb, stats);
+  else
+    gn_stats_kernel<float><<<grid, GN_THREADS, smem, s>>>(static_cast<const float*>(x0), static_cast<const float*>(x1),
+                                                         x1_batch, hw, c0, c1, ppb, stats);
+  return check_launch("gn_stats");
+}
+
+extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0,
+                              int c1, const double* stats, const float* gamma, const float* beta, float eps,
+                              int apply_silu, void* out, int out_dtype, void* stream) {
+  const int C = c0 + c1;
+  STEDM_REQUIRE(x0 && stats && gamma && beta && out && (c1 == 0 || x1), "gn_apply: null pointer");
+  STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0 && C <= 4096,
+                "gn_apply: bad channel counts (%d + %d)", c0, c1);
+  const int ppb = pick_pix_per_block(batch, hw, C);
+  dim3 grid((hw + ppb - 1) / ppb, batch);
+  const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  auto s = static_cast<cudaStream_t>(stream);
+#define LAUNCH(TI, TO, PREC)                                                                                       \
+  gn_apply_kernel<TI, TO, PREC><<<grid, GN_THREADS, smem, s>>>(static_cast<const TI*>(x0), static_cast<const TI*>(x1), \
+                                                              x1_batch, hw, c0, c1, ppb, stats, gamma, beta, eps,  \
+                                                              apply_silu, static_cast<TO*>(out))
+  if (in_dtype == DT_BF16 && out_dtype == DT_BF16)
+    LAUNCH(__nv_bfloat16, __nv_bfloat16, false);
+  else if (in_dtype == DT_F32 && out_dtype == DT_BF16)
+    LAUNCH(float, __nv_bfloat16, false);
+  else if (in_dtype == DT_F32 && out_dtype == DT_F32)
+    LAUNCH(float, float, true);
+  else if (in_dtype == DT_BF16 && out_dtype == DT_F32)
+    LAUNCH(__nv_bfloat16, float, true);
+  else {
+    set_error("gn_apply: unsupported dtype combination");
+    return ERR_UNSUPPORTED;
+  }
+#undef LAUNCH
+  return check_launch("gn_apply");
+}
