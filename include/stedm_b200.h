@@ -57,12 +57,15 @@ int stedm_cfg_ddim_step(const float* e_c, const float* e_u, const float* x, cons
  * precedes them (openaimodel.py:800).
  * Input = channel concat [x0 (c0 ch) | x1 (c1 ch)] of NHWC tensors (x1 NULL when c1 == 0); x1 may have a smaller
  * batch x1_batch that is broadcast as b % x1_batch (shared encoder skips under batched guidance).
- * stats: double [batch][32][2] = (sum, sum of squares); stedm_gn_stats ACCUMULATES, caller zeroes it first.
+ * partials: double [batch][n_chunks][32][2] = per-chunk (sum, sum of squares), n_chunks = stedm_gn_num_chunks(hw,
+ * c0 + c1) <= 128 (a function of the per-sample shape only).  No atomics and no zero-initialisation: the result
+ * for a sample is bit-identical whatever batch it is launched in (rank-shard invariance).
  */
+int stedm_gn_num_chunks(int hw, int channels);
 int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
-                   double* stats, void* stream);
+                   double* partials, void* stream);
 int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
-                   const double* stats, const float* gamma, const float* beta, float eps, int apply_silu, void* out,
+                   const double* partials, const float* gamma, const float* beta, float eps, int apply_silu, void* out,
                    int out_dtype, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
@@ -103,19 +106,12 @@ int stedm_conv_simt(const stedm_conv_desc* d, void* stream);
 /* Batched GEMM C[z] = alpha * A[z] * op(B[z]) on CUDA cores (fp32 mode attention: QK^T and PV,
  * openaimodel.py:388-393, model.py:185-197).  z = (zb, zh): pointer offset = zb*stride_b + zh*stride_h (elements).
  * A is [m][k] row-major with leading dimension lda; B is [n][k] (b_is_nk != 0) or [k][n]; C is [m][n] with ldc. */
-int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_ab, int dtype_c, int m, int n, int k, int lda,
-                    int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb, long long a_sh, long long b_sb,
-                    long long b_sh, long long c_sb, long long c_sh, float alpha, void* stream);
+int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_a, int dtype_b, int dtype_c, int m, int n, int k,
+                    int lda, int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb, long long a_sh,
+                    long long b_sb, long long b_sh, long long c_sb, long long c_sh, float alpha, void* stream);
 /* In-place row softmax over the last dimension of a [rows][cols] fp32 matrix (openaimodel.py:392, model.py:190). */
 int stedm_softmax_rows(float* x, long long rows, int cols, void* stream);
 
-/* K5/K6  Fused flash-style attention on tcgen05 (S and O accumulators in TMEM, online fp32 softmax).
- * q, k, v: bf16, token-major: element (b, h, t, c) at base + b*stride_b + h*stride_h + t*stride_t + c.
- * out: bf16 [batch][tokens][heads*head_dim].  scale multiplies q.k (= ch^-1/2 for both reference attentions).
- * Replaces QKVAttentionLegacy.forward (openaimodel.py:378-394) and AttnBlock's bmm/softmax/bmm (model.py:178-197). */
-int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int tokens,
-                       int head_dim, long long stride_b, long long stride_h, long long stride_t, float scale,
-                       void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * Data movement helpers.

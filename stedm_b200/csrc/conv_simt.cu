@@ -179,14 +179,14 @@ struct SimtGemmParams {
   int dtype_c;
 };
 
-template <typename T>
+template <typename TA, typename TB>
 __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(const SimtGemmParams p) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int zb = blockIdx.z / p.nh, zh = blockIdx.z % p.nh;
-  const T* A = static_cast<const T*>(p.a) + zb * p.a_sb + zh * p.a_sh;
-  const T* B = static_cast<const T*>(p.b) + zb * p.b_sb + zh * p.b_sh;
+  const TA* A = static_cast<const TA*>(p.a) + zb * p.a_sb + zh * p.a_sh;
+  const TB* B = static_cast<const TB*>(p.b) + zb * p.b_sb + zh * p.b_sh;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int ty = tid >> 4, tx = tid & 15;
   float acc[4][4];
@@ -199,19 +199,19 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(const SimtGemmParams
     for (int e = tid; e < BM * BK; e += THREADS) {
       const int r = e / BK, kk = e % BK;
       const int m = m0 + r, k = k0 + kk;
-      As[kk][r] = (m < p.m && k < p.k) ? to_f32<T>(A[static_cast<size_t>(m) * p.lda + k]) : 0.f;
+      As[kk][r] = (m < p.m && k < p.k) ? to_f32<TA>(A[static_cast<size_t>(m) * p.lda + k]) : 0.f;
     }
     if (p.b_is_nk) {
       for (int e = tid; e < BN * BK; e += THREADS) {
         const int r = e / BK, kk = e % BK;
         const int n = n0 + r, k = k0 + kk;
-        Bs[kk][r] = (n < p.n && k < p.k) ? to_f32<T>(B[static_cast<size_t>(n) * p.ldb + k]) : 0.f;
+        Bs[kk][r] = (n < p.n && k < p.k) ? to_f32<TB>(B[static_cast<size_t>(n) * p.ldb + k]) : 0.f;
       }
     } else {
       for (int e = tid; e < BN * BK; e += THREADS) {
         const int kk = e / BN, r = e % BN;
         const int n = n0 + r, k = k0 + kk;
-        Bs[kk][r] = (n < p.n && k < p.k) ? to_f32<T>(B[static_cast<size_t>(k) * p.ldb + n]) : 0.f;
+        Bs[kk][r] = (n < p.n && k < p.k) ? to_f32<TB>(B[static_cast<size_t>(k) * p.ldb + n]) : 0.f;
       }
     }
     __syncthreads();
@@ -280,18 +280,22 @@ extern "C" int stedm_conv_simt(const stedm_conv_desc* d, void* stream) {
   return check_launch("conv_simt");
 }
 
-extern "C" int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_ab, int dtype_c, int m, int n, int k,
-                               int lda, int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb, long long a_sh,
-                               long long b_sb, long long b_sh, long long c_sb, long long c_sh, float alpha,
-                               void* stream) {
+extern "C" int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_a, int dtype_b, int dtype_c, int m, int n,
+                               int k, int lda, int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb,
+                               long long a_sh, long long b_sb, long long b_sh, long long c_sb, long long c_sh,
+                               float alpha, void* stream) {
   STEDM_REQUIRE(a && b && c && m > 0 && n > 0 && k > 0 && nb > 0 && nh > 0, "gemm_simt: bad argument");
   STEDM_REQUIRE(static_cast<long long>(nb) * nh <= 65535, "gemm_simt: too many batches");
   SimtGemmParams p{a, b, c, m, n, k, lda, ldb, ldc, b_is_nk, nh, a_sb, a_sh, b_sb, b_sh, c_sb, c_sh, alpha, dtype_c};
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, nb * nh);
   auto s = static_cast<cudaStream_t>(stream);
-  if (dtype_ab == DT_BF16)
-    gemm_simt_kernel<__nv_bfloat16><<<grid, THREADS, 0, s>>>(p);
+  if (dtype_a == DT_BF16 && dtype_b == DT_BF16)
+    gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, THREADS, 0, s>>>(p);
+  else if (dtype_a == DT_F32 && dtype_b == DT_BF16)
+    gemm_simt_kernel<float, __nv_bfloat16><<<grid, THREADS, 0, s>>>(p);
+  else if (dtype_a == DT_BF16 && dtype_b == DT_F32)
+    gemm_simt_kernel<__nv_bfloat16, float><<<grid, THREADS, 0, s>>>(p);
   else
-    gemm_simt_kernel<float><<<grid, THREADS, 0, s>>>(p);
+    gemm_simt_kernel<float, float><<<grid, THREADS, 0, s>>>(p);
   return check_launch("gemm_simt");
 }

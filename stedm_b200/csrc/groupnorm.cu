@@ -1,7 +1,8 @@
 // K7: GroupNorm(32 groups) over NHWC tensors, with the channel concat of skip tensors and the SiLU that follow
 // it in the reference folded in.  HBM-bound: the statistics pass reads the input once, the apply pass reads it
 // once and writes the (usually bf16) operand of the consumer convolution.  fp32 statistics per thread, double
-// precision across threads/blocks (GroupNorm32 computes in fp32: ldm/modules/diffusionmodules/util.py:214-216).
+// precision across threads/blocks (GroupNorm32 computes in fp32: ldm/modules/diffusionmodules/util.py:214-216);
+// no atomics anywhere, so results are deterministic and independent of the batch a sample is launched in.
 //
 // Layout: one "item" = 8 consecutive channels of one pixel (16 B of bf16 / 32 B of fp32).  A 256-thread block
 // owns one sample and a slice of its pixels; thread -> (pixel lane, channel item) so that a warp touches
@@ -58,19 +59,24 @@ __device__ __forceinline__ const T* item_ptr(const T* x0, const T* x1, int b, in
   return x1 + (static_cast<size_t>(b1) * hw + pix) * c1 + (c - c0);
 }
 
+// Deterministic, batch-size-independent reduction: block (chunk, b) reduces a fixed pixel range; per-thread fp32
+// partials go to shared memory WITHOUT atomics ([lane][channel]), are folded over lanes and the group's channels
+// in a fixed order in double precision, and written to partials[b][chunk][group][{sum, sumsq}].  The apply kernel
+// folds the chunks in index order.  Hence a sample's statistics do not depend on which other samples share the
+// launch (a rank-sharded run is bit-identical to the single-GPU run) nor on scheduling.
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x0, const T* __restrict__ x1,
                                                               int x1_batch, int hw, int c0, int c1, int pix_per_block,
-                                                              double* __restrict__ stats) {
-  extern __shared__ float s_acc[];  // [2][C]
+                                                              double* __restrict__ partials) {
+  extern __shared__ float s_acc[];  // [2][lanes][C]
   const int C = c0 + c1, items = C / 8;
   const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) s_acc[i] = 0.f;
-  __syncthreads();
   const int tpi = min(items, GN_THREADS);       // threads along the item axis
   const int lanes = GN_THREADS / tpi;           // pixel lanes
   const int lane = threadIdx.x / tpi, it0 = threadIdx.x % tpi;
   const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
+  float* s_sum = s_acc;
+  float* s_sq = s_acc + static_cast<size_t>(lanes) * C;
   if (lane < lanes) {
     for (int item = it0; item < items; item += tpi) {
       float s[8], q[8];
@@ -87,8 +93,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_acc[item * 8 + j], s[j]);
-        atomicAdd(&s_acc[C + item * 8 + j], q[j]);
+        s_sum[lane * C + item * 8 + j] = s[j];
+        s_sq[lane * C + item * 8 + j] = q[j];
       }
     }
   }
@@ -96,29 +102,37 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
   if (threadIdx.x < 2 * GN_GROUPS) {
     const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
     const int cpg = C / GN_GROUPS;
+    const float* src = which ? s_sq : s_sum;
     double acc = 0.0;
-    for (int c = 0; c < cpg; ++c) acc += static_cast<double>(s_acc[which * C + g * cpg + c]);
-    atomicAdd(&stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which], acc);
+    for (int l = 0; l < lanes; ++l)
+      for (int c = 0; c < cpg; ++c) acc += static_cast<double>(src[l * C + g * cpg + c]);
+    partials[((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * GN_GROUPS + g) * 2 + which] = acc;
   }
 }
 
 template <typename TI, typename TO, bool kPrecise>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restrict__ x0, const TI* __restrict__ x1,
                                                               int x1_batch, int hw, int c0, int c1, int pix_per_block,
-                                                              const double* __restrict__ stats,
+                                                              const double* __restrict__ partials, int n_chunks,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int apply_silu,
                                                               TO* __restrict__ out) {
   extern __shared__ float s_ab[];  // scale[C], shift[C]
+  __shared__ double s_tot[2 * GN_GROUPS];
   const int C = c0 + c1, items = C / 8, cpg = C / GN_GROUPS;
   const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    const double* src = partials + static_cast<size_t>(b) * n_chunks * GN_GROUPS * 2 + threadIdx.x;
+    double acc = 0.0;
+    for (int k = 0; k < n_chunks; ++k) acc += src[static_cast<size_t>(k) * GN_GROUPS * 2];
+    s_tot[threadIdx.x] = acc;  // index = g*2 + which
+  }
+  __syncthreads();
   const double n = static_cast<double>(hw) * cpg;
   for (int c = threadIdx.x; c < C; c += GN_THREADS) {
     const int g = c / cpg;
-    const double sum = stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + 0];
-    const double sq = stats[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + 1];
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
+    const double mean = s_tot[g * 2] / n;
+    double var = s_tot[g * 2 + 1] / n - mean * mean;
     var = var < 0.0 ? 0.0 : var;
     const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     const float a = rstd * gamma[c];
@@ -143,10 +157,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
   }
 }
 
-int pick_pix_per_block(int batch, int hw, int C) {
-  // aim for >= ~4 waves of 148 SMs x 4 resident blocks while keeping >= 16 KB of input per block
+// Pixel range per statistics block: a function of (hw, C) ONLY (never of the batch), at most 128 chunks per sample.
+int stats_pix_per_block(int hw, int C) {
+  const int by_bytes = max(4, 8192 / C);
+  const int by_count = (hw + 127) / 128;
+  return min(hw, max(by_bytes, by_count));
+}
+
+int apply_pix_per_block(int batch, int hw, int C) {
   const int min_pix = max(1, (16 * 1024) / (C * 2));
-  int blocks_per_sample = max(1, (148 * 16 + batch - 1) / batch);
+  const int blocks_per_sample = max(1, (148 * 16 + batch - 1) / batch);
   int ppb = (hw + blocks_per_sample - 1) / blocks_per_sample;
   ppb = max(ppb, min_pix);
   return min(ppb, hw);
@@ -154,42 +174,51 @@ int pick_pix_per_block(int batch, int hw, int C) {
 
 }  // namespace
 
+extern "C" int stedm_gn_num_chunks(int hw, int channels) {
+  if (hw <= 0 || channels <= 0) return ERR_ARG;
+  const int ppb = stats_pix_per_block(hw, channels);
+  return (hw + ppb - 1) / ppb;
+}
+
 extern "C" int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0,
-                              int c1, double* stats, void* stream) {
+                              int c1, double* partials, void* stream) {
   const int C = c0 + c1;
-  STEDM_REQUIRE(x0 && stats && (c1 == 0 || x1), "gn_stats: null pointer");
+  STEDM_REQUIRE(x0 && partials && (c1 == 0 || x1), "gn_stats: null pointer");
   STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0,
                 "gn_stats: channels (%d + %d) must be multiples of 8 and sum to a multiple of 32", c0, c1);
   STEDM_REQUIRE(C <= 4096, "gn_stats: too many channels");
-  const int ppb = pick_pix_per_block(batch, hw, C);
+  const int ppb = stats_pix_per_block(hw, C);
   dim3 grid((hw + ppb - 1) / ppb, batch);
-  const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  const int items = C / 8, tpi = items < GN_THREADS ? items : GN_THREADS, lanes = GN_THREADS / tpi;
+  const size_t smem = static_cast<size_t>(2) * lanes * C * sizeof(float);
   auto s = static_cast<cudaStream_t>(stream);
   if (in_dtype == DT_BF16)
     gn_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(x0),
                                                                  static_cast<const __nv_bfloat16*>(x1), x1_batch, hw,
-                                                                 c0, c1, ppb, stats);
+                                                                 c0, c1, ppb, partials);
   else
     gn_stats_kernel<float><<<grid, GN_THREADS, smem, s>>>(static_cast<const float*>(x0), static_cast<const float*>(x1),
-                                                         x1_batch, hw, c0, c1, ppb, stats);
+                                                         x1_batch, hw, c0, c1, ppb, partials);
   return check_launch("gn_stats");
 }
 
 extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0,
-                              int c1, const double* stats, const float* gamma, const float* beta, float eps,
+                              int c1, const double* partials, const float* gamma, const float* beta, float eps,
                               int apply_silu, void* out, int out_dtype, void* stream) {
   const int C = c0 + c1;
-  STEDM_REQUIRE(x0 && stats && gamma && beta && out && (c1 == 0 || x1), "gn_apply: null pointer");
+  STEDM_REQUIRE(x0 && partials && gamma && beta && out && (c1 == 0 || x1), "gn_apply: null pointer");
   STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0 && C <= 4096,
                 "gn_apply: bad channel counts (%d + %d)", c0, c1);
-  const int ppb = pick_pix_per_block(batch, hw, C);
+  const int sppb = stats_pix_per_block(hw, C);
+  const int n_chunks = (hw + sppb - 1) / sppb;
+  const int ppb = apply_pix_per_block(batch, hw, C);
   dim3 grid((hw + ppb - 1) / ppb, batch);
   const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
   auto s = static_cast<cudaStream_t>(stream);
 #define LAUNCH(TI, TO, PREC)                                                                                       \
   gn_apply_kernel<TI, TO, PREC><<<grid, GN_THREADS, smem, s>>>(static_cast<const TI*>(x0), static_cast<const TI*>(x1), \
-                                                              x1_batch, hw, c0, c1, ppb, stats, gamma, beta, eps,  \
-                                                              apply_silu, static_cast<TO*>(out))
+                                                              x1_batch, hw, c0, c1, ppb, partials, n_chunks, gamma, \
+                                                              beta, eps, apply_silu, static_cast<TO*>(out))
   if (in_dtype == DT_BF16 && out_dtype == DT_BF16)
     LAUNCH(__nv_bfloat16, __nv_bfloat16, false);
   else if (in_dtype == DT_F32 && out_dtype == DT_BF16)

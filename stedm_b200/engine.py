@@ -1,0 +1,374 @@
+"""Native execution engine: walks a parameter-holding module tree once, repacks the reference-named weights into
+kernel layouts, and runs the eps U-Net / VQ decoder as a sequence of C-ABI kernel launches (stedm_b200.ops).
+
+Two precisions (north_star):
+  * ``bf16`` — throughput mode: NHWC bf16 activations, tcgen05/TMEM/TMA implicit-GEMM convolutions
+    (stedm_conv_tc), fp32 accumulation, fp32 GroupNorm statistics / softmax / embeddings, fp32 eps output.
+  * ``fp32`` — parity mode (1e-4 max-abs eps bar): NHWC fp32 activations, every contraction on the FFMA
+    implicit-GEMM kernel (stedm_conv_simt).
+Weights stay visible as nn.Parameters under the reference's names; the packed copies here are derived, private,
+and rebuilt whenever the owner invalidates them (load_state_dict / .to()).
+"""
+import math
+
+import torch
+
+from . import ops
+
+PAD_TC = 64   # channel padding granularity of the tensor-core path (one 128-byte K slab of bf16)
+PAD_SIMT = 4
+
+
+class Precision:
+    def __init__(self, name):
+        if name not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {name!r}")
+        self.name = name
+        self.tc = name == "bf16"
+        self.act = torch.bfloat16 if self.tc else torch.float32
+        self.cpad = PAD_TC if self.tc else PAD_SIMT
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class PackedConv:
+    """One convolution (nn.Conv2d 3x3/1x1 or nn.Conv1d k=1) repacked for the selected kernel.
+
+    OIHW fp32 (reference layout) ->
+      tensor-core: bf16 [Cout_pad][kh*kw*Cin_pad]   (K-major: tap-major, channel-minor)
+      SIMT:        fp32 [kh*kw*Cin_pad][Cout]
+    ``cin_split`` = (c0, c1) when the input is a two-source concat (each part padded separately)."""
+
+    def __init__(self, weight, bias, prec, *, stride=1, force_simt=False, cin_split=None, cout_pad=None):
+        w = weight.detach()
+        if w.dim() == 3:  # Conv1d k=1
+            w = w[:, :, :, None]
+        cout, cin, kh, kw = w.shape
+        assert kh == kw and kh in (1, 3)
+        self.ksize, self.stride = kh, stride
+        self.tc = prec.tc and not force_simt
+        pad = PAD_TC if self.tc else PAD_SIMT
+        parts = cin_split or (cin,)
+        assert sum(parts) == cin
+        w = w.permute(0, 2, 3, 1).float()                      # [Cout, kh, kw, Cin]
+        chunks, o = [], 0
+        for c in parts:
+            part = w[..., o:o + c]
+            cp = _round_up(c, pad)
+            if cp != c:
+                part = torch.nn.functional.pad(part, (0, cp - c))
+            chunks.append(part)
+            o += c
+        w = torch.cat(chunks, dim=-1) if len(chunks) > 1 else chunks[0]
+        self.cin_pad = w.shape[-1]
+        self.cout_real = cout
+        self.cout = cout
+        b = None if bias is None else bias.detach().float()
+        if self.tc:
+            cp = cout_pad or _round_up(cout, 16)
+            if cp != cout:
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, cp - cout))
+                if b is not None:
+                    b = torch.nn.functional.pad(b, (0, cp - cout))
+                self.cout = cp
+            self.weight = w.reshape(self.cout, -1).to(torch.bfloat16).contiguous()
+        else:
+            if cout_pad and cout_pad != cout:
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, cout_pad - cout))
+                if b is not None:
+                    b = torch.nn.functional.pad(b, (0, cout_pad - cout))
+                self.cout = cout_pad
+            self.weight = w.reshape(self.cout, -1).t().contiguous()   # [K][Cout]
+        self.bias = None if b is None else b.contiguous()
+        self.prec = prec
+
+    def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False):
+        out_dtype = out_dtype or self.prec.act
+        if self.tc:
+            if self.stride == 2:
+                assert x1 is None and self.ksize == 3
+                cols = ops.im2col_3x3_s2(x0)            # [B, H/2, W/2, 9*C]: Downsample as a plain GEMM
+                return ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
+                                out_dtype=out_dtype, tensor_core=True)
+            if upsample:
+                assert x1 is None
+                x0 = ops.upsample_nearest2x(x0)
+            return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
+                            out_dtype=out_dtype, tensor_core=True)
+        return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
+                        out_dtype=out_dtype, stride=self.stride, upsample=upsample, out_nchw=out_nchw,
+                        tensor_core=False)
+
+
+class PackedNorm:
+    def __init__(self, gn, eps):
+        self.gamma = gn.weight.detach().float().contiguous()
+        self.beta = gn.bias.detach().float().contiguous()
+        self.eps = eps
+
+    def __call__(self, x0, x1, silu, out_dtype, stats):
+        stats = ops.gn_stats(x0, x1, stats)
+        return ops.gn_apply(x0, x1, stats, self.gamma, self.beta, self.eps, silu, out_dtype)
+
+
+class StatsPool:
+    """Scratch for the per-chunk GroupNorm statistics: one reusable double buffer, sized for the largest site
+    (128 chunks x 32 groups x 2), since each site's statistics are consumed by the very next launch."""
+
+    def __init__(self, n_sites, batch, device):
+        self.buf = torch.empty((batch, 128, 32, 2), device=device, dtype=torch.float64)
+
+    def next(self):
+        return self.buf
+
+
+class PackedResBlock:
+    """GN-SiLU-conv3x3 (+emb) -> GN-SiLU-conv3x3 -> + skip(x)   (openaimodel.py:268-288, model.py:121-141)."""
+
+    def __init__(self, norm1, conv1, norm2, conv2, skip, eps, prec, cin_split=None):
+        self.n1, self.n2 = PackedNorm(norm1, eps), PackedNorm(norm2, eps)
+        self.c1 = PackedConv(conv1.weight, conv1.bias, prec, cin_split=cin_split)
+        self.c2 = PackedConv(conv2.weight, conv2.bias, prec)
+        self.skip = None if skip is None else PackedConv(skip.weight, skip.bias, prec, cin_split=cin_split)
+        self.prec = prec
+
+    def __call__(self, x0, x1, emb, pool):
+        a = self.n1(x0, x1, True, self.prec.act, pool.next())
+        h = self.c1(a, emb=emb)
+        a = self.n2(h, None, True, self.prec.act, pool.next())
+        if self.skip is not None:
+            xs = self.skip(x0, x1)
+        else:
+            assert x1 is None
+            xs = x0
+        return self.c2(a, residual=xs)
+
+
+class UNetRunner:
+    """Executes UNetModel.forward (openaimodel.py:761-806) for the module tree built by
+    stedm_b200.ldm.modules.diffusionmodules.openaimodel.UNetModel."""
+
+    def __init__(self, unet, precision):
+        self.prec = prec = Precision(precision)
+        self.mc = unet.model_channels
+        self.in_ch = unet.in_channels
+        self.out_ch = unet.out_channels
+        self.heads = unet.num_heads
+        te = unet.time_embed
+        self.te0 = (te[0].weight.detach().float().contiguous(), te[0].bias.detach().float().contiguous())
+        self.te2 = (te[2].weight.detach().float().contiguous(), te[2].bias.detach().float().contiguous())
+        emb_w, emb_b, self.emb_off = [], [], {}
+        off = 0
+        self.n_norms = 0
+
+        def add_emb(lin, key):
+            nonlocal off
+            emb_w.append(lin.weight.detach().float())
+            emb_b.append(lin.bias.detach().float())
+            self.emb_off[key] = (off, lin.weight.shape[0])
+            off += lin.weight.shape[0]
+
+        def pack_res(rb, key, cin_split=None, style=False):
+            skip = rb.skip_connection if isinstance(rb.skip_connection, torch.nn.Conv2d) else None
+            blk = PackedResBlock(rb.in_layers[0], rb.in_layers[2], rb.out_layers[0], rb.out_layers[3], skip, 1e-5,
+                                 prec, cin_split)
+            self.n_norms += 2
+            if style:
+                self.style_emb = (rb.emb_layers[1].weight.detach().float().contiguous(),
+                                  rb.emb_layers[1].bias.detach().float().contiguous())
+            else:
+                add_emb(rb.emb_layers[1], key)
+            return blk
+
+        # ---- encoder
+        self.enc = []
+        chans = []
+        for i, blk in enumerate(unet.input_blocks):
+            kind = blk.kind
+            if kind == "stem":
+                conv = blk[0]
+                self.stem = PackedConv(conv.weight, conv.bias, prec)
+                self.enc.append(("stem", None))
+                chans.append(conv.weight.shape[0])
+            elif kind == "down":
+                conv = blk[0].op
+                self.enc.append(("down", PackedConv(conv.weight, conv.bias, prec, stride=2)))
+                chans.append(conv.weight.shape[0])
+            else:
+                self.enc.append(("res", pack_res(blk[0], ("in", i)), ("in", i)))
+                chans.append(blk[0].out_channels)
+        # ---- middle: ResBlock, ResBlockStyle, AttentionBlock, ResBlock
+        mb = unet.middle_block
+        self.mid0 = pack_res(mb[0], ("mid", 0))
+        self.mid1 = pack_res(mb[1].block, None, style=True)
+        att = mb[2]
+        self.att_norm = PackedNorm(att.norm, 1e-5)
+        self.n_norms += 1
+        self.att_qkv = PackedConv(att.qkv.weight, att.qkv.bias, prec)
+        self.att_proj = PackedConv(att.proj_out.weight, att.proj_out.bias, prec)
+        self.mid3 = pack_res(mb[3], ("mid", 3))
+        # ---- decoder
+        self.dec = []
+        ch = mb[3].out_channels
+        for i, blk in enumerate(unet.output_blocks):
+            skip_ch = chans.pop()
+            rb = pack_res(blk[0], ("out", i), cin_split=(ch, skip_ch))
+            ch = blk[0].out_channels
+            up = None
+            if len(blk) > 1:
+                conv = blk[1].conv
+                up = PackedConv(conv.weight, conv.bias, prec)
+            self.dec.append((rb, ("out", i), up))
+        self.out_norm = PackedNorm(unet.out[0], 1e-5)
+        self.n_norms += 1
+        oc = unet.out[2]
+        # head: N = 3 -> CUDA-core kernel writing NCHW fp32 eps directly (fp32 for the CFG std)
+        self.head = PackedConv(oc.weight, oc.bias, prec, force_simt=True)
+        self.emb_w = torch.cat(emb_w, 0).contiguous()
+        self.emb_b = torch.cat(emb_b, 0).contiguous()
+
+    # -- embedding path (K8): sinusoid -> time_embed MLP -> all 17 emb_layers in one stacked linear
+    def embeddings(self, t, context):
+        temb = ops.timestep_embedding(t, self.mc)
+        e = ops.linear(temb, *self.te0)
+        e = ops.linear(e, *self.te2, silu_in=True)
+        emb_all = ops.linear(e, self.emb_w, self.emb_b, silu_in=True)
+        emb_style = ops.linear(context.float().contiguous(), *self.style_emb, silu_in=True)
+        return emb_all, emb_style
+
+    def __call__(self, x, c_concat, t, context):
+        """x (B,3,L,L) and c_concat (B,3,L,L) NCHW fp32 (the 'hybrid' concat of ddpm.py:1414 is fused into the
+        packing kernel), t (B,) int64, context (B,512) -> eps (B,3,L,L) NCHW fp32."""
+        prec = self.prec
+        B = x.shape[0]
+        emb_all, emb_style = self.embeddings(t, context)
+        pool = StatsPool(self.n_norms, B, x.device)
+        h = ops.pack_nchw_to_nhwc(x.contiguous(), c_concat, self.stem.cin_pad, prec.act)
+        hs = []
+        for entry in self.enc:
+            if entry[0] == "stem":
+                h = self.stem(h)
+            elif entry[0] == "down":
+                h = entry[1](h)
+            else:
+                h = entry[1](h, None, self._emb_view(emb_all, entry[2]), pool)
+            hs.append(h)
+        h = self.mid0(h, None, self._emb_view(emb_all, ("mid", 0)), pool)
+        h = self.mid1(h, None, emb_style, pool)
+        h = self._attention(h, pool)
+        h = self.mid3(h, None, self._emb_view(emb_all, ("mid", 3)), pool)
+        for rb, key, up in self.dec:
+            h = rb(h, hs.pop(), self._emb_view(emb_all, key), pool)
+            if up is not None:
+                h = up(h, upsample=True)
+        a = self.out_norm(h, None, True, prec.act, pool.next())
+        return self.head(a, out_dtype=torch.float32, out_nchw=True)
+
+    def _emb_view(self, emb_all, key):
+        off, n = self.emb_off[key]
+        return emb_all[:, off:off + n]
+
+    def _attention(self, x, pool):
+        """AttentionBlock (openaimodel.py:340-346) with QKVAttentionLegacy's head-major qkv split (:378-394)."""
+        prec = self.prec
+        B, H, W, Cc = x.shape
+        T, ch = H * W, Cc // self.heads
+        a = self.att_norm(x, None, False, prec.act, pool.next())
+        qkv = self.att_qkv(a)                                   # [B, H, W, 3C], channels [head][q|k|v][ch]
+        scale = 1.0 / math.sqrt(ch)                             # (q*ch^-1/4).(k*ch^-1/4)
+        if prec.tc and ops.attention_tc_supported(ch, T):
+            o = ops.attention_tc(qkv, qkv, qkv, self.heads, ch, T, (T * 3 * Cc, 3 * ch, 3 * Cc), scale,
+                                 q_off=0, k_off=ch, v_off=2 * ch)
+        else:
+            o = ops.attention_simt(qkv, qkv, qkv, self.heads, ch, T, 0, ch, 2 * ch, 3 * Cc, 3 * ch, scale, prec.act)
+        return self.att_proj(o.view(B, H, W, Cc), residual=x)
+
+
+class DecoderRunner:
+    """VQModelInterface.decode (autoencoder.py:274-282): VQ nearest code -> post_quant_conv -> Decoder
+    (model.py:535-568).  Input z NCHW fp32, output image NCHW fp32."""
+
+    def __init__(self, vq, precision):
+        self.prec = prec = Precision(precision)
+        self.codebook = vq.quantize.embedding.weight.detach().float().contiguous()
+        d = vq.decoder
+        pq = vq.post_quant_conv
+        zc = pq.weight.shape[0]
+        self.n_norms = 0
+        self.conv_in = PackedConv(d.conv_in.weight, d.conv_in.bias, prec)
+        # post_quant_conv: 1x1, 3 -> 3; output channel-padded with zero weights so it feeds conv_in directly
+        self.post_quant = PackedConv(pq.weight, pq.bias, prec, force_simt=True, cout_pad=self.conv_in.cin_pad)
+        self.zc = zc
+
+        def res(rb):
+            self.n_norms += 2
+            skip = getattr(rb, "nin_shortcut", None)
+            return PackedResBlock(rb.norm1, rb.conv1, rb.norm2, rb.conv2, skip, 1e-6, prec)
+
+        self.mid1 = res(d.mid.block_1)
+        at = d.mid.attn_1
+        self.att_norm = PackedNorm(at.norm, 1e-6)
+        self.n_norms += 1
+        # q, k, v 1x1 convs stacked into one GEMM: output channels [q | k | v]
+        wq = torch.cat([at.q.weight, at.k.weight, at.v.weight], 0)
+        bq = torch.cat([at.q.bias, at.k.bias, at.v.bias], 0)
+        self.att_qkv = PackedConv(wq, bq, prec)
+        self.att_proj = PackedConv(at.proj_out.weight, at.proj_out.bias, prec)
+        self.att_c = at.q.weight.shape[0]
+        self.mid2 = res(d.mid.block_2)
+        self.levels = []
+        for lvl in reversed(range(len(d.up))):
+            up = d.up[lvl]
+            blocks = [res(b) for b in up.block]
+            upc = None
+            if hasattr(up, "upsample"):
+                upc = PackedConv(up.upsample.conv.weight, up.upsample.conv.bias, prec)
+            self.levels.append((blocks, upc))
+        self.norm_out = PackedNorm(d.norm_out, 1e-6)
+        self.n_norms += 1
+        self.conv_out = PackedConv(d.conv_out.weight, d.conv_out.bias, prec, force_simt=True)
+
+    def __call__(self, z, force_not_quantize=False):
+        prec = self.prec
+        z = z.float().contiguous()
+        if not force_not_quantize:
+            z = ops.vq_nearest(z, self.codebook)
+        B = z.shape[0]
+        pool = StatsPool(self.n_norms, B, z.device)
+        zin = ops.pack_nchw_to_nhwc(z, None, self.post_quant.cin_pad, torch.float32)
+        h = self.post_quant(zin, out_dtype=prec.act)
+        h = self.conv_in(h)
+        h = self.mid1(h, None, None, pool)
+        h = self._attention(h, pool)
+        h = self.mid2(h, None, None, pool)
+        for blocks, upc in self.levels:
+            for rb in blocks:
+                h = rb(h, None, None, pool)
+            if upc is not None:
+                h = upc(h, upsample=True)
+        a = self.norm_out(h, None, True, prec.act, pool.next())
+        return self.conv_out(a, out_dtype=torch.float32, out_nchw=True)
+
+    def _attention(self, x, pool):
+        """AttnBlock.forward (model.py:178-202): single head, d = C, scale C^-1/2."""
+        prec = self.prec
+        B, H, W, Cc = x.shape
+        T = H * W
+        a = self.att_norm(x, None, False, prec.act, pool.next())
+        qkv = self.att_qkv(a)                                   # [B, H, W, 3C] = [q | k | v]
+        scale = float(Cc) ** -0.5
+        if prec.tc and ops.attention_tc_supported(Cc, T):
+            o = ops.attention_tc(qkv, qkv, qkv, 1, Cc, T, (T * 3 * Cc, 0, 3 * Cc), scale, q_off=0, k_off=Cc,
+                                 v_off=2 * Cc)
+        else:
+            o = None
+            # bound the materialised score matrix (B x T x T fp32) to ~2 GiB per chunk
+            chunk = max(1, min(B, (1 << 29) // (T * T)))
+            outs = []
+            for s in range(0, B, chunk):
+                q = qkv[s:s + chunk]
+                outs.append(ops.attention_simt(q, q, q, 1, Cc, T, 0, Cc, 2 * Cc, 3 * Cc, Cc, scale, prec.act))
+            o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return self.att_proj(o.view(B, H, W, Cc), residual=x)

@@ -1,0 +1,185 @@
+"""Drop-in for ``ldm.models.diffusion.ddim.DDIMSampler`` (reference ddim.py:11-210) — the hot loop of the path.
+
+Same constructor, ``make_schedule``, ``sample``, ``ddim_sampling`` and ``p_sample_ddim`` signatures and return
+structures ((x, {"x_inter": [...], "pred_x0": [...]})).  What changes is how a step is executed:
+
+* the conditional and unconditional eps predictions of STEDM's guidance (two separate ``apply_model`` calls in the
+  reference, ddim.py:177-178) run as ONE batched U-Net pass of 2B samples on the native engine — every op in the
+  network is per-sample, so the results are those of the two separate calls;
+* everything after them — guidance combine, the (C,H)-std rescale with phi = 0.7, pred_x0, direction and x_{t-1}
+  (ddim.py:179-209, ~25 ATen kernels + 4 scalar fills in the reference) — is the single ``stedm_cfg_ddim_step``
+  kernel;
+* schedule scalars are Python floats rounded through fp32 exactly like the reference's ``torch.full`` (§A.4);
+* with ``use_cuda_graph`` the U-Net pass is captured once per (batch, latent size) and replayed every step.
+"""
+import numpy as np
+import torch
+
+from ...modules.diffusionmodules.util import make_ddim_sampling_parameters, make_ddim_timesteps, noise_like
+from .... import ops
+
+
+def _f32(v):
+    """Round a python/numpy scalar through float32 (what torch.full(..., device=cuda) does in the reference)."""
+    return float(np.float32(v))
+
+
+class DDIMSampler(object):
+    def __init__(self, model, schedule="linear", use_cuda_graph=None, **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self.use_cuda_graph = getattr(model, "use_cuda_graph", False) if use_cuda_graph is None else use_cuda_graph
+
+    def register_buffer(self, name, attr):
+        if isinstance(attr, torch.Tensor) and attr.device != self.model.device:
+            attr = attr.to(self.model.device)
+        setattr(self, name, attr)
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        """ddim.py:24-53 (same buffer names; numpy members stay numpy like the reference's)."""
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
+                                                  num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
+        ac = self.model.alphas_cumprod
+        assert ac.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
+        to_torch = lambda x: torch.as_tensor(x).clone().detach().to(torch.float32).to(self.model.device)
+        ac_cpu = ac.detach().cpu()
+        self.register_buffer("betas", to_torch(self.model.betas))
+        self.register_buffer("alphas_cumprod", to_torch(ac))
+        self.register_buffer("alphas_cumprod_prev", to_torch(self.model.alphas_cumprod_prev))
+        self.register_buffer("sqrt_alphas_cumprod", to_torch(np.sqrt(ac_cpu)))
+        self.register_buffer("sqrt_one_minus_alphas_cumprod", to_torch(np.sqrt(1. - ac_cpu)))
+        self.register_buffer("log_one_minus_alphas_cumprod", to_torch(np.log(1. - ac_cpu)))
+        self.register_buffer("sqrt_recip_alphas_cumprod", to_torch(np.sqrt(1. / ac_cpu)))
+        self.register_buffer("sqrt_recipm1_alphas_cumprod", to_torch(np.sqrt(1. / ac_cpu - 1)))
+        sig, a, a_prev = make_ddim_sampling_parameters(alphacums=ac_cpu, ddim_timesteps=self.ddim_timesteps,
+                                                       eta=ddim_eta, verbose=verbose)
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sig, a, a_prev
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1. - a)                # fp32 ndarray (a is fp32)
+        self.register_buffer("ddim_sigmas_for_original_num_steps", ddim_eta * torch.sqrt(
+            (1 - self.alphas_cumprod_prev) / (1 - self.alphas_cumprod) * (1 - self.alphas_cumprod / self.alphas_cumprod_prev)))
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.,
+               unconditional_conditioning=None, **kwargs):
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
+        C, H, W = shape
+        return self.ddim_sampling(conditioning, (batch_size, C, H, W), callback=callback, img_callback=img_callback,
+                                  quantize_denoised=quantize_x0, mask=mask, x0=x0, ddim_use_original_steps=False,
+                                  noise_dropout=noise_dropout, temperature=temperature,
+                                  score_corrector=score_corrector, corrector_kwargs=corrector_kwargs, x_T=x_T,
+                                  log_every_t=log_every_t, unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning)
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None):
+        """ddim.py:112-162."""
+        if ddim_use_original_steps or score_corrector is not None or quantize_denoised:
+            raise NotImplementedError("original-step sampling / score correctors / quantize_x0 are not on STEDM's path")
+        device = self.model.betas.device
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T.to(device).float()
+        if timesteps is None:
+            timesteps = self.ddim_timesteps
+        else:
+            subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
+            timesteps = self.ddim_timesteps[:subset_end]
+        intermediates = {"x_inter": [img], "pred_x0": [img]}
+        time_range = np.flip(timesteps)
+        total_steps = timesteps.shape[0]
+        stepper = _GuidedStepper(self, cond, unconditional_conditioning, unconditional_guidance_scale, shape)
+        for i, step in enumerate(time_range):
+            index = total_steps - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            if mask is not None:
+                assert x0 is not None
+                img = self.model.q_sample(x0, ts) * mask + (1. - mask) * img
+            img, pred_x0 = stepper.step(img, ts, index, temperature=temperature, noise_dropout=noise_dropout)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total_steps - 1:
+                intermediates["x_inter"].append(img)
+                intermediates["pred_x0"].append(pred_x0)
+        return img, intermediates
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, rescale_phi=0.7):
+        """ddim.py:164-210, one step (kept for callers that drive the loop themselves)."""
+        if use_original_steps or score_corrector is not None or quantize_denoised:
+            raise NotImplementedError("original-step sampling / score correctors / quantize_x0 are not on STEDM's path")
+        stepper = _GuidedStepper(self, c, unconditional_conditioning, unconditional_guidance_scale, tuple(x.shape),
+                                 rescale_phi=rescale_phi, allow_graph=False)
+        return stepper.step(x, t, index, temperature=temperature, noise_dropout=noise_dropout,
+                            repeat_noise=repeat_noise)
+
+
+class _GuidedStepper:
+    """One DDIM step = batched (cond ‖ uncond) U-Net pass + the fused K11 kernel."""
+
+    def __init__(self, sampler, cond, uncond, scale, shape, rescale_phi=0.7, allow_graph=True):
+        self.s = sampler
+        self.model = sampler.model
+        self.scale, self.phi = float(scale), float(rescale_phi)
+        self.guided = not (uncond is None or scale == 1.)
+        self.b = shape[0]
+        unet = self.model.model.diffusion_model
+        self.unet = unet
+        cc = lambda c: c["c_concat"][0] if len(c["c_concat"]) == 1 else torch.cat(c["c_concat"], 1)
+        ca = lambda c: c["c_crossattn"][0] if len(c["c_crossattn"]) == 1 else torch.cat(c["c_crossattn"], 1)
+        if not isinstance(cond, dict):
+            raise NotImplementedError("STEDM's hybrid conditioning is a dict {'c_concat': [...], 'c_crossattn': [...]}")
+        if self.guided:
+            self.c_concat = torch.cat([cc(cond), cc(uncond)], 0).float().contiguous()
+            self.context = torch.cat([ca(cond), ca(uncond)], 0).float().contiguous()
+        else:
+            self.c_concat = cc(cond).float().contiguous()
+            self.context = ca(cond).float().contiguous()
+        self.graph = None
+        self.use_graph = allow_graph and sampler.use_cuda_graph
+        self._warm = 0
+
+    def _eps(self, x, t):
+        """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,)."""
+        if self.guided:
+            x2 = torch.cat([x, x], 0)
+            t2 = torch.cat([t, t], 0)
+        else:
+            x2, t2 = x, t
+        if not self.use_graph:
+            return self.unet.forward_split(x2, self.c_concat, t2, self.context)
+        if self.graph is None:
+            if self._warm < 1:  # one eager pass first: lazy kernel attribute setup must not happen under capture
+                self._warm += 1
+                return self.unet.forward_split(x2, self.c_concat, t2, self.context)
+            self.gx, self.gt = x2.clone(), t2.clone()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.geps = self.unet.forward_split(self.gx, self.c_concat, self.gt, self.context)
+        self.gx.copy_(x2)
+        self.gt.copy_(t2)
+        self.graph.replay()
+        return self.geps
+
+    def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False):
+        s = self.s
+        x = x.float().contiguous()
+        eps = self._eps(x, t)
+        e_c, e_u = (eps[:self.b], eps[self.b:]) if self.guided else (eps, None)
+        sigma = _f32(s.ddim_sigmas[index])
+        # the reference draws randn every step, also when sigma == 0 (ddim.py:206): keep the RNG stream aligned
+        noise = noise_like(x.shape, x.device, repeat_noise) * temperature
+        if noise_dropout > 0.:
+            noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+        return ops.cfg_ddim_step(e_c, e_u, x, _f32(s.ddim_alphas[index]), _f32(s.ddim_alphas_prev[index]), sigma,
+                                 _f32(s.ddim_sqrt_one_minus_alphas[index]), cfg_scale=self.scale, phi=self.phi,
+                                 noise=noise.contiguous() if sigma != 0.0 else None)

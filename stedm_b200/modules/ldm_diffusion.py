@@ -1,0 +1,86 @@
+"""Drop-in for the prediction side of ``modules.ldm_diffusion.LDM_Diffusion`` (reference ldm_diffusion.py:14-107)
+without the Lightning / wandb / training machinery: ``prepare_batch`` (:51-60) and ``predict_step`` (:76-107).
+
+``cfg`` is any attribute-style config with the reference's fields (cfg_scale, ddim_steps, eta, style_sampling,
+style_agg, diffusion, data.patch_size); see stedm_b200.config.load_config for a hydra-free loader of conf/.
+"""
+import numpy as np
+import torch
+
+from ..networks.s_zss_dm import S_ZSS_DM
+from .. import ops
+
+
+def _plain(node):
+    """hydra/omegaconf-style node (or our AttrDict) -> plain containers (OmegaConf.to_container in the reference)."""
+    if isinstance(node, dict):
+        return {k: _plain(v) for k, v in node.items()}
+    if isinstance(node, (list, tuple)):
+        return [_plain(v) for v in node]
+    return node
+
+
+class LDM_Diffusion(torch.nn.Module):
+    def __init__(self, cfg, wandb_id="", precision="bf16", load_first_stage_ckpt=True):
+        super().__init__()
+        self._cfg = cfg
+        self._lr = getattr(cfg, "lr", 1)
+        self._wandb_id = wandb_id
+        ldm_dict = _plain(cfg.diffusion)
+        fs = ldm_dict["first_stage_config"]["params"]
+        if load_first_stage_ckpt and fs.get("ckpt_path"):
+            fs["ckpt_path"] = cfg.location.result_dir + "/" + fs["ckpt_path"]          # ldm_diffusion.py:32
+        else:
+            fs.pop("ckpt_path", None)
+        if ldm_dict.get("ckpt_path") is not None and load_first_stage_ckpt:
+            ldm_dict["ckpt_path"] = cfg.location.result_dir + "/" + ldm_dict["ckpt_path"]
+        else:
+            for k in ("ckpt_path", "ignore_keys", "load_only_unet"):
+                ldm_dict.pop(k, None)
+        self._model = S_ZSS_DM(encoder="swin_v2_t", sampling_cfg=cfg.style_sampling, agg_cfg=cfg.style_agg, cfg=cfg,
+                               precision=precision, **ldm_dict)
+        self.register_module("model", self._model)
+        self.predict_dir = None
+
+    def prepare_batch(self, batch):
+        """(img (B,3,P,P), seg_oh (B,K,P,P), seg, style (B,N,3,P,P), idx) -> channels-last dict; classes 1..K-1 are
+        merged into the foreground channel and two channels are kept (ldm_diffusion.py:51-60)."""
+        img = batch[0].permute(0, 2, 3, 1)
+        seg_oh = batch[1].permute(0, 2, 3, 1)
+        style = batch[3].permute(0, 1, 3, 4, 2)
+        seg_oh[:, :, :, 1] = torch.sum(seg_oh[:, :, :, 1:], dim=-1)
+        seg_oh = seg_oh[:, :, :, :2]
+        return {"image": img, "segmentation": seg_oh, "style_imgs": style}
+
+    @torch.no_grad()
+    def generate(self, ldm_batch, x_T=None):
+        """predict_step minus file I/O: returns uint8 images (B,P,P,3) on the device (ldm_diffusion.py:79-96)."""
+        cfg = self._cfg
+        m = self._model
+        z, c_0 = m.get_input(ldm_batch, "image")
+        kw = dict(batch_size=len(z), ddim=True, ddim_steps=cfg.ddim_steps, eta=cfg.eta, log_every_t=1000)
+        if x_T is not None:
+            kw["x_T"] = x_T
+        if (cfg.cfg_scale == 1) or (cfg.style_sampling.name == "none"):
+            out, _ = m.sample_log(c_0, **kw)
+        else:
+            unc = {"image": torch.zeros_like(ldm_batch["image"]), "segmentation": ldm_batch["segmentation"],
+                   "style_imgs": torch.zeros_like(ldm_batch["style_imgs"]) - 2}
+            z, c_uncond = m.get_input(unc, "image")
+            out, _ = m.sample_log(c_0, unconditional_conditioning=c_uncond,
+                                  unconditional_guidance_scale=cfg.cfg_scale, **kw)
+        img = m.decode_first_stage(out)
+        # torch.clip(-1,1); (x+1)*127.5; truncating uint8; NHWC — fused (ldm_diffusion.py:94-96)
+        return ops.image_to_uint8(img.contiguous())
+
+    @torch.no_grad()
+    def predict_step(self, batch, batch_idx):
+        from PIL import Image
+        ldm_batch = self.prepare_batch(batch)
+        out_imgs = self.generate(ldm_batch).cpu().numpy()
+        segs = torch.argmax(ldm_batch["segmentation"], dim=-1).cpu().numpy().astype(np.uint8)
+        for img, seg, num in zip(out_imgs, segs, batch[4].cpu().numpy()):
+            num_str = str(num).zfill(5)
+            Image.fromarray(img).save(self.predict_dir + f"/img_{num_str}.png")
+            Image.fromarray(seg).save(self.predict_dir + f"/seg_{num_str}.png")
+        return out_imgs

@@ -1,0 +1,50 @@
+"""Drop-in for ``networks.s_zss_dm.S_ZSS_DM`` (reference s_zss_dm.py:11-60): LatentDiffusion plus a style encoder
+and aggregation block; ``get_input`` returns ``[z, {"c_concat": [layout], "c_crossattn": [style vector]}]``."""
+import torch
+import torchvision
+
+from ..ldm.models.diffusion.ddpm import LatentDiffusion
+from .agg_blocks import Agg_Linear, Agg_Max, Agg_Mean, Agg_None
+
+
+def _get(cfg, name, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    return getattr(cfg, name, default)
+
+
+class S_ZSS_DM(LatentDiffusion):
+    def __init__(self, encoder, sampling_cfg, agg_cfg, cfg, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._sampling_cfg, self._agg_cfg, self._cfg = sampling_cfg, agg_cfg, cfg
+        self.embed_key = "style_imgs"
+        embedder = torchvision.models.get_model(encoder)
+        embedder.head = torch.nn.Linear(768, 512)
+        s_name, a_name = _get(sampling_cfg, "name"), _get(agg_cfg, "name")
+        if s_name == "none":
+            self._agg_block = Agg_None(sampling_cfg, embedder)
+        elif a_name == "mean":
+            self._agg_block = Agg_Mean(sampling_cfg, embedder)
+        elif a_name == "max":
+            self._agg_block = Agg_Max(sampling_cfg, embedder)
+        elif a_name == "linear":
+            self._agg_block = Agg_Linear(sampling_cfg, embedder)
+        elif a_name == "svit":
+            raise NotImplementedError("style_agg=svit (networks/vit_set.py) is a 'next' row (SURVEY.md §8f rank 2)")
+        else:
+            raise Exception("Unkown aggregation function!")
+        self.register_module("agg_block", self._agg_block)
+        self._agg_block.eval()
+
+    @torch.no_grad()
+    def get_input(self, batch, k, cond_key=None, bs=None, **kwargs):
+        self.cond_stage_trainable = True
+        outputs = LatentDiffusion.get_input(self, batch, k, bs=bs, **kwargs)
+        self.cond_stage_trainable = False
+        z, c = outputs[0], outputs[1]
+        c = self.get_learned_conditioning(c)
+        style_imgs = batch[self.embed_key][:bs].to(self.device)
+        style_features = self._agg_block(style_imgs)
+        out = [z, {"c_concat": [c], "c_crossattn": [style_features]}]
+        out.extend(outputs[2:])
+        return out

@@ -1,0 +1,287 @@
+"""Torch-tensor front end of the C ABI: argument checking, output allocation, current-stream plumbing.
+
+PyTorch is used only for device memory and streams.  Every function launches hand-written sm_100a kernels from
+libstedm_b200.so and raises if the library is missing or the tensors are not CUDA tensors — there is no fallback.
+Activations are NHWC; ``F32``/``BF16`` tags follow include/stedm_b200.h.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ConvDesc
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+
+LAUNCHES = [0]  # number of native kernel launches issued through this module (bench.py's gpu_launches)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError("stedm_b200 ops take CUDA tensors only (no CPU fallback)")
+            if not t.is_contiguous():
+                raise RuntimeError("stedm_b200 ops take contiguous tensors")
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    _lib.check(getattr(lib, name)(*args), name)
+    LAUNCHES[0] += 1
+
+
+def tag(dtype):
+    return _DT[dtype]
+
+
+def torch_dtype(tag_):
+    return _TORCH_DT[tag_]
+
+
+# ------------------------------------------------------------------------------------------------ K11
+def cfg_ddim_step(e_c, e_u, x, a_t, a_prev, sigma_t, sqrt_one_minus_at, cfg_scale=1.0, phi=0.7, noise=None,
+                  out_x_prev=None, out_pred_x0=None):
+    """ddim.py:177-209 in one kernel.  NCHW fp32 tensors; ``e_u=None`` -> unguided."""
+    _cuda(e_c, e_u, x, noise)
+    assert e_c.dtype == torch.float32 and x.dtype == torch.float32 and e_c.shape == x.shape and x.dim() == 4
+    b, c, h, w = x.shape
+    x_prev = torch.empty_like(x) if out_x_prev is None else out_x_prev
+    pred_x0 = torch.empty_like(x) if out_pred_x0 is None else out_pred_x0
+    _call("stedm_cfg_ddim_step", _ptr(e_c), _ptr(e_u), _ptr(x), _ptr(noise), _ptr(x_prev), _ptr(pred_x0), b, c, h, w,
+          0 if e_u is None else 1, float(cfg_scale), float(phi), float(a_t), float(a_prev), float(sigma_t),
+          float(sqrt_one_minus_at), _stream())
+    return x_prev, pred_x0
+
+
+# ------------------------------------------------------------------------------------------------ K7
+_GN_CHUNKS = {}
+
+
+def gn_num_chunks(hw, channels):
+    """Number of per-sample partial-statistics chunks (a function of the per-sample shape only)."""
+    key = (hw, channels)
+    if key not in _GN_CHUNKS:
+        n = _lib.load().stedm_gn_num_chunks(hw, channels)
+        if n <= 0:
+            raise RuntimeError(f"stedm_gn_num_chunks({hw}, {channels}) failed")
+        _GN_CHUNKS[key] = n
+    return _GN_CHUNKS[key]
+
+
+def gn_stats(x0, x1, stats=None):
+    """Per-chunk (sum, sumsq) per (sample, group) of the concat [x0 | x1]: double [B, n_chunks, 32, 2]."""
+    _cuda(x0, x1, stats)
+    b, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    x1b = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]
+    n = gn_num_chunks(h * w, c0 + c1)
+    if stats is None:
+        stats = torch.empty((b, n, 32, 2), device=x0.device, dtype=torch.float64)
+    assert stats.dtype == torch.float64 and stats.numel() >= b * n * 64
+    _call("stedm_gn_stats", _ptr(x0), _ptr(x1), _DT[x0.dtype], b, x1b, h * w, c0, c1, _ptr(stats), _stream())
+    return stats
+
+
+def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype):
+    _cuda(x0, x1, stats, gamma, beta)
+    b, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    x1b = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]
+    out = torch.empty((b, h, w, c0 + c1), device=x0.device, dtype=out_dtype)
+    _call("stedm_gn_apply", _ptr(x0), _ptr(x1), _DT[x0.dtype], b, x1b, h * w, c0, c1, _ptr(stats), _ptr(gamma),
+          _ptr(beta), float(eps), 1 if silu else 0, _ptr(out), _DT[out_dtype], _stream())
+    return out
+
+
+def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
+    """GroupNorm(32) (+SiLU) of the channel concat [x0 | x1]; returns the normalised NHWC tensor."""
+    stats = gn_stats(x0, x1, stats)
+    return gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
+         upsample=False, out_nchw=False, tensor_core=True, out=None):
+    """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
+    [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
+    _cuda(x0, x1, weight, bias, residual)
+    if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
+        assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape == (x0.shape[0], cout)
+    b, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    out_dtype = out_dtype or x0.dtype
+    uh, uw = (2 * h, 2 * w) if upsample else (h, w)
+    oh, ow = uh // stride, uw // stride
+    if out is None:
+        shape = (b, cout, oh, ow) if out_nchw else (b, oh, ow, cout)
+        out = torch.empty(shape, device=x0.device, dtype=out_dtype)
+    d = ConvDesc()
+    d.x0, d.x1, d.weight, d.bias = _ptr(x0), _ptr(x1), _ptr(weight), _ptr(bias)
+    d.emb, d.residual, d.out = _ptr(emb), _ptr(residual), _ptr(out)
+    d.c0, d.c1, d.in_dtype = c0, c1, _DT[x0.dtype]
+    d.batch, d.in_h, d.in_w = b, h, w
+    d.x1_batch = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]
+    d.ksize, d.stride, d.upsample = ksize, stride, 1 if upsample else 0
+    d.emb_stride = 0 if emb is None else emb.stride(0)
+    d.res_dtype = F32 if residual is None else _DT[residual.dtype]
+    d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
+    if tensor_core:
+        assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ksize * ksize * (c0 + c1), \
+            (weight.shape, cout, ksize, c0, c1)
+        _call("stedm_conv_tc", C.byref(d), _stream())
+    else:
+        assert weight.dtype == torch.float32 and weight.numel() == cout * ksize * ksize * (c0 + c1), \
+            (weight.shape, cout, ksize, c0, c1)
+        _call("stedm_conv_simt", C.byref(d), _stream())
+    return out
+
+
+def gemm_simt(a, b, c, m, n, k, lda, ldb, ldc, b_is_nk, nb, nh, a_strides, b_strides, c_strides, alpha=1.0,
+              a_off=0, b_off=0, c_off=0):
+    """Batched CUDA-core GEMM on raw views (element offsets/strides); see include/stedm_b200.h."""
+    _cuda(a, b, c)
+    _call("stedm_gemm_simt", _ptr(a) + a_off * a.element_size(), _ptr(b) + b_off * b.element_size(),
+          _ptr(c) + c_off * c.element_size(), _DT[a.dtype], _DT[b.dtype], _DT[c.dtype], m, n, k, lda, ldb, ldc,
+          1 if b_is_nk else 0, nb, nh, a_strides[0], a_strides[1], b_strides[0], b_strides[1], c_strides[0],
+          c_strides[1], float(alpha), _stream())
+
+
+def softmax_rows(x):
+    _cuda(x)
+    assert x.dtype == torch.float32
+    cols = x.shape[-1]
+    _call("stedm_softmax_rows", _ptr(x), x.numel() // cols, cols, _stream())
+    return x
+
+
+def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
+                   scale, out_dtype):
+    """fp32-accumulate attention on CUDA cores with a materialised score matrix (parity mode).
+    q/k/v live in [B, T, token_stride] buffers at channel offset ``*_off + head*head_stride``; for the U-Net's
+    legacy head-major qkv layout head_stride = 3*head_dim, for separate q/k/v tensors head_stride = head_dim."""
+    b = q_src.shape[0]
+    hs = head_stride
+    s = torch.empty((b, heads, tokens, tokens), device=q_src.device, dtype=torch.float32)
+    gemm_simt(q_src, k_src, s, tokens, tokens, head_dim, token_stride, token_stride, tokens, True, b, heads,
+              (tokens * token_stride, hs), (tokens * token_stride, hs), (heads * tokens * tokens, tokens * tokens),
+              alpha=scale, a_off=q_off, b_off=k_off)
+    softmax_rows(s)
+    out = torch.empty((b, tokens, heads * head_dim), device=q_src.device, dtype=out_dtype)
+    gemm_simt(s, v_src, out, tokens, head_dim, tokens, tokens, token_stride, heads * head_dim, False, b, heads,
+              (heads * tokens * tokens, tokens * tokens), (tokens * token_stride, hs),
+              (tokens * heads * head_dim, head_dim), b_off=v_off)
+    return out
+
+
+def attention_tc_supported(head_dim, tokens):
+    """Shapes the fused tcgen05 attention kernel takes (none yet: the CUDA-core path runs)."""
+    return False
+
+
+def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0):
+    """Fused tcgen05 flash attention; q/k/v are bf16 views described by element offsets and (b, h, t) strides."""
+    _cuda(q, k, v)
+    b = q.shape[0]
+    out = torch.empty((b, tokens, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    es = 2
+    _call("stedm_attention_tc", _ptr(q) + q_off * es, _ptr(k) + k_off * es, _ptr(v) + v_off * es, _ptr(out), b, heads,
+          tokens, head_dim, strides[0], strides[1], strides[2], float(scale), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ movement
+def upsample_nearest2x(x):
+    _cuda(x)
+    b, h, w, c = x.shape
+    out = torch.empty((b, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
+    _call("stedm_upsample_nearest2x", _ptr(x), _ptr(out), _DT[x.dtype], b, h, w, c, _stream())
+    return out
+
+
+def im2col_3x3_s2(x):
+    _cuda(x)
+    b, h, w, c = x.shape
+    out = torch.empty((b, h // 2, w // 2, 9 * c), device=x.device, dtype=x.dtype)
+    _call("stedm_im2col_3x3_s2", _ptr(x), _ptr(out), _DT[x.dtype], b, h, w, c, _stream())
+    return out
+
+
+def pack_nchw_to_nhwc(x0, x1, c_pad, out_dtype):
+    """[x0 | x1] NCHW fp32 -> NHWC ``out_dtype`` zero-padded to c_pad channels (ddpm.py:1414-1415 concat)."""
+    _cuda(x0, x1)
+    assert x0.dtype == torch.float32 and (x1 is None or x1.dtype == torch.float32)
+    b, c0, h, w = x0.shape
+    c1 = 0 if x1 is None else x1.shape[1]
+    out = torch.empty((b, h, w, c_pad), device=x0.device, dtype=out_dtype)
+    _call("stedm_pack_nchw_to_nhwc", _ptr(x0), c0, _ptr(x1), c1, _ptr(out), _DT[out_dtype], b, h * w, c_pad, _stream())
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    _cuda(x)
+    b, h, w, c = x.shape
+    out = torch.empty((b, c, h, w), device=x.device, dtype=torch.float32)
+    _call("stedm_nhwc_to_nchw_f32", _ptr(x), _DT[x.dtype], _ptr(out), b, h * w, c, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K8
+def timestep_embedding(t, dim):
+    _cuda(t)
+    assert t.dtype == torch.int64
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
+    _call("stedm_timestep_embedding", _ptr(t), _ptr(out), t.shape[0], dim, _stream())
+    return out
+
+
+def linear(x, weight, bias, silu_in=False):
+    _cuda(x, weight, bias)
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
+    b, k = x.shape
+    n = weight.shape[0]
+    assert weight.shape[1] == k
+    out = torch.empty((b, n), device=x.device, dtype=torch.float32)
+    _call("stedm_linear", _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), b, k, n, 1 if silu_in else 0, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K12 / K13 / tail
+def vq_nearest(z, codebook, return_indices=False):
+    _cuda(z, codebook)
+    assert z.dtype == torch.float32 and codebook.dtype == torch.float32
+    b, c, h, w = z.shape
+    zq = torch.empty_like(z)
+    idx = torch.empty((b * h * w,), device=z.device, dtype=torch.int32) if return_indices else None
+    _call("stedm_vq_nearest", _ptr(z), _ptr(codebook), _ptr(zq), _ptr(idx), b, c, h * w, codebook.shape[0], _stream())
+    return (zq, idx) if return_indices else zq
+
+
+def spatial_rescale(seg, weight, n_stages):
+    _cuda(seg, weight)
+    assert seg.dtype == torch.float32 and weight.dtype == torch.float32
+    b, cin, p, p2 = seg.shape
+    assert p == p2
+    cout = weight.shape[0]
+    l = p >> n_stages
+    out = torch.empty((b, cout, l, l), device=seg.device, dtype=torch.float32)
+    _call("stedm_spatial_rescale", _ptr(seg), _ptr(weight), _ptr(out), b, cin, cout, p, n_stages, _stream())
+    return out
+
+
+def image_to_uint8(img):
+    _cuda(img)
+    assert img.dtype == torch.float32
+    b, c, h, w = img.shape
+    out = torch.empty((b, h, w, c), device=img.device, dtype=torch.uint8)
+    _call("stedm_image_to_uint8", _ptr(img), _ptr(out), b, c, h * w, _stream())
+    return out

@@ -1,0 +1,200 @@
+"""End-to-end parity of the native sampling path on a B200 against golden vectors produced by the reference's own
+code (tests/golden/*.npz, oracle/make_golden.py) and against the CPU oracle run live on the same seeded inputs.
+
+Bars (north_star): per-step eps within 1e-4 max-abs in fp32 mode and 2e-2 relative (max|d|/max|ref|) in bf16
+mode; decoded images at PSNR >= 40 dB (peak-to-peak 2) against the reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stedm_oracle as O
+from tests.util import build_model, load_golden, max_abs, oracle_state_dict, psnr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_EPS_BAR = 1e-4
+BF16_EPS_BAR = 2e-2
+PSNR_BAR = 40.0
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    """Library code outside the kernels (torchvision Swin) must not use TF32 while parity is measured."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _small_inputs():
+    g = load_golden("small_b2_l32")
+    seg, style, x_T = O.synthetic_batch(2, 128, 2, 0)
+    return g, seg, style, x_T
+
+
+def _cond(g, key, dev="cuda"):
+    return {"c_concat": [torch.from_numpy(g["c_concat"]).to(dev)], "c_crossattn": [torch.from_numpy(g[key]).to(dev)]}
+
+
+def test_conditioning_matches_reference():
+    g, seg, style, _ = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    batch = {"image": torch.zeros(2, 128, 128, 3).cuda(), "segmentation": seg.cuda(), "style_imgs": style.cuda()}
+    z, c = m._model.get_input(batch, "image")
+    assert tuple(z.shape) == (2, 3, 32, 32)
+    assert max_abs(c["c_concat"][0], g["c_concat"]) < 1e-6
+    assert max_abs(c["c_crossattn"][0], g["c_crossattn"]) < 2e-3     # torchvision Swin on GPU vs CPU (library code)
+    unc = dict(batch, style_imgs=torch.zeros_like(batch["style_imgs"]) - 2)
+    _, cu = m._model.get_input(unc, "image")
+    assert max_abs(cu["c_crossattn"][0], g["uc_crossattn"]) < 2e-3
+
+
+@pytest.mark.parametrize("t", [981, 481, 1])
+def test_eps_fp32_mode(t):
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    tt = torch.full((2,), t, dtype=torch.long, device="cuda")
+    e_c = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
+    e_u = m._model.apply_model(x_T.cuda(), tt, _cond(g, "uc_crossattn"))
+    assert max_abs(e_c, g[f"eps_c_{t}"]) < FP32_EPS_BAR, max_abs(e_c, g[f"eps_c_{t}"])
+    assert max_abs(e_u, g[f"eps_u_{t}"]) < FP32_EPS_BAR
+
+
+@pytest.mark.parametrize("t", [981, 481, 1])
+def test_eps_bf16_mode(t):
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="bf16")
+    tt = torch.full((2,), t, dtype=torch.long, device="cuda")
+    e_c = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
+    e_u = m._model.apply_model(x_T.cuda(), tt, _cond(g, "uc_crossattn"))
+    r_c, r_u = rel_err(e_c, g[f"eps_c_{t}"]), rel_err(e_u, g[f"eps_u_{t}"])
+    print(f"bf16 eps rel err t={t}: cond {r_c:.3e} uncond {r_u:.3e}")
+    assert r_c < BF16_EPS_BAR and r_u < BF16_EPS_BAR, (r_c, r_u)
+
+
+def test_unet_forward_api_equals_apply_model():
+    """UNetModel.forward(cat([x, c_concat]), t, context) == apply_model(x, t, cond) (ddpm.py:1414-1417)."""
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    tt = torch.full((2,), 481, dtype=torch.long, device="cuda")
+    cond = _cond(g, "c_crossattn")
+    a = m._model.apply_model(x_T.cuda(), tt, cond)
+    b = m._model.model.diffusion_model(torch.cat([x_T.cuda(), cond["c_concat"][0]], 1), tt, context=cond["c_crossattn"][0])
+    assert torch.equal(a, b)
+
+
+def _sample(m, g, x_T, steps_limit=None, **kw):
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    model = m._model
+    sampler = DDIMSampler(model, **kw)
+    sampler.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    cond, unc = _cond(g, "c_crossattn"), _cond(g, "uc_crossattn")
+    img = x_T.cuda()
+    total = sampler.ddim_timesteps.shape[0]
+    xs = {}
+    for i, step in enumerate(np.flip(sampler.ddim_timesteps)):
+        if steps_limit is not None and i >= steps_limit:
+            break
+        ts = torch.full((img.shape[0],), int(step), device="cuda", dtype=torch.long)
+        img, p0 = sampler.p_sample_ddim(img, cond, ts, index=total - i - 1, unconditional_guidance_scale=1.5,
+                                        unconditional_conditioning=unc)
+        xs[i + 1] = img
+        if i == 0:
+            xs["p0"] = p0
+    return xs
+
+
+def test_ddim_first_steps_fp32():
+    g, _, _, x_T = _small_inputs()
+    xs = _sample(build_model(32, n_style=2, precision="fp32"), g, x_T, steps_limit=3)
+    for k in (1, 2, 3):
+        assert rel_err(xs[k], g[f"x_after_{k}"]) < 1e-4, (k, rel_err(xs[k], g[f"x_after_{k}"]))
+    assert rel_err(xs["p0"], g["pred_x0_step0"]) < 1e-4
+
+
+def test_ddim_first_steps_bf16():
+    g, _, _, x_T = _small_inputs()
+    xs = _sample(build_model(32, n_style=2, precision="bf16"), g, x_T, steps_limit=3)
+    for k in (1, 2, 3):
+        r = rel_err(xs[k], g[f"x_after_{k}"])
+        print(f"bf16 x after {k} steps rel err {r:.3e}")
+        assert r < BF16_EPS_BAR
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_full_ddim50_sample_log(precision, bar):
+    """The whole DDIM-50 CFG loop through LatentDiffusion.sample_log vs the reference's final latent."""
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision=precision)
+    z, inter = m._model.sample_log(_cond(g, "c_crossattn"), batch_size=2, ddim=True, ddim_steps=50, eta=0.0,
+                                   log_every_t=1000, x_T=x_T.cuda(), unconditional_conditioning=_cond(g, "uc_crossattn"),
+                                   unconditional_guidance_scale=1.5)
+    assert len(inter["x_inter"]) == 2 and len(inter["pred_x0"]) == 2        # x_T + the step with index == total-1
+    r = rel_err(z, g["z_final"])
+    print(f"{precision} DDIM-50 final latent rel err {r:.3e}")
+    assert r < bar, r
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_first_stage(precision):
+    g, _, _, _ = _small_inputs()
+    m = build_model(32, n_style=2, precision=precision)
+    z = torch.from_numpy(g["z_final"]).cuda()
+    dec_n = m._model.decode_first_stage(z, force_not_quantize=True)
+    dec_q = m._model.decode_first_stage(z)
+    p_n, p_q = psnr(dec_n.clamp(-1, 1), np.clip(g["dec_noquant"], -1, 1)), psnr(dec_q.clamp(-1, 1), np.clip(g["dec_quant"], -1, 1))
+    print(f"{precision} decode PSNR: noquant {p_n:.1f} dB, quant {p_q:.1f} dB; max|d| {max_abs(dec_q, g['dec_quant']):.3e}")
+    assert p_n >= PSNR_BAR and p_q >= PSNR_BAR
+    if precision == "fp32":
+        assert max_abs(dec_n, g["dec_noquant"]) < 1e-3 and max_abs(dec_q, g["dec_quant"]) < 1e-3
+        from stedm_b200 import ops
+        u8 = ops.image_to_uint8(dec_q.contiguous()).cpu().numpy()
+        assert (u8 == g["img_u8"]).mean() > 0.995
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_predict_path_end_to_end(precision):
+    """prepare_batch -> get_input x2 -> sample_log -> decode -> uint8 (modules/ldm_diffusion.py:76-96)."""
+    g, seg, style, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision=precision)
+    B, P = 2, 128
+    seg_oh = seg.permute(0, 3, 1, 2).contiguous()
+    batch = (torch.zeros(B, 3, P, P).cuda(), seg_oh.cuda(), None, style.permute(0, 1, 4, 2, 3).contiguous().cuda(),
+             torch.arange(B))
+    u8 = m.generate(m.prepare_batch(batch), x_T=x_T.cuda()).cpu().numpy()
+    assert u8.shape == (B, P, P, 3) and u8.dtype == np.uint8
+    ref = g["img_u8"].astype(np.float64)
+    mse = ((u8.astype(np.float64) - ref) ** 2).mean()
+    p = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+    print(f"{precision} end-to-end uint8 PSNR vs reference: {p:.1f} dB")
+    assert p >= (PSNR_BAR if precision == "fp32" else 30.0)
+
+
+def test_batch_shard_invariance():
+    """A rank-sharded run is bit-identical to the single-GPU run on the same per-sample inputs."""
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="bf16")
+    tt = torch.full((2,), 481, dtype=torch.long, device="cuda")
+    full = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
+    for r in range(2):
+        cond = {"c_concat": [torch.from_numpy(g["c_concat"][r:r + 1]).cuda()],
+                "c_crossattn": [torch.from_numpy(g["c_crossattn"][r:r + 1]).cuda()]}
+        part = m._model.apply_model(x_T[r:r + 1].cuda(), tt[:1], cond)
+        assert torch.equal(part[0], full[r])
+
+
+def test_cuda_graph_sampler_matches_eager():
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="bf16")
+    kw = dict(batch_size=2, ddim=True, ddim_steps=20, eta=0.0, log_every_t=1000, x_T=x_T.cuda(),
+              unconditional_conditioning=_cond(g, "uc_crossattn"), unconditional_guidance_scale=1.5)
+    m._model.use_cuda_graph = False
+    z0, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw)
+    m._model.use_cuda_graph = True
+    try:
+        z1, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw)
+    finally:
+        m._model.use_cuda_graph = False
+    assert torch.equal(z0, z1)

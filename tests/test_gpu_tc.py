@@ -1,0 +1,105 @@
+"""The tcgen05/TMEM/TMA implicit-GEMM convolution (stedm_conv_tc) against torch fp32 convolution of the SAME
+bf16-rounded operands (so only the accumulation order differs), over every tile geometry the path uses:
+W >= 128, W | 128 with several rows per tile, several samples per tile, partial last tile, two-source concat,
+broadcast second source, every BN instantiation, fused bias + embedding + residual epilogue, bf16/fp32 output."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from stedm_b200 import ops as _ops
+    return _ops
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def tc_w(w):
+    """OIHW -> bf16 [Cout][kh*kw*Cin] (tap-major, channel-minor)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k
+    (2, 16, 16, 128, 256, 3),     # 16x8 pixel tiles, BN=256
+    (3, 8, 8, 64, 128, 3),        # two samples per tile, partial last tile (M = 192), BN=128
+    (1, 64, 64, 64, 128, 3),      # 64x2 tiles
+    (1, 2, 128, 64, 64, 3),       # full-row tiles, BN=64
+    (1, 4, 256, 64, 16, 3),       # half-row tiles, BN=16
+    (2, 32, 32, 192, 512, 1),     # 1x1, K not a power of two
+    (1, 16, 16, 1024, 1024, 3),   # deep K (144 slabs), 4 n-tiles
+    (5, 4, 4, 64, 48, 3),         # eight samples per tile, cout = 3 x 16
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k", CASES)
+def test_conv_tc_matches_fp32(ops, B, H, W, cin, cout, k):
+    g = torch.Generator().manual_seed(B * 1000 + H + cin)
+    x = bf(torch.randn(B, cin, H, W, generator=g))
+    w = bf(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    b = torch.randn(cout, generator=g)
+    want = F.conv2d(x, w, b, padding=k // 2)
+    got = ops.conv(nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), cout, k, out_dtype=torch.float32,
+                   tensor_core=True)
+    torch.cuda.synchronize()
+    err = max_abs(nchw(got.cpu()), want)
+    assert err < 2e-3, err
+    got_bf = ops.conv(nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), cout, k,
+                      out_dtype=torch.bfloat16, tensor_core=True)
+    assert max_abs(nchw(got_bf.float().cpu()), want) < 4e-2
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_conv_tc_concat_emb_residual(ops, k):
+    g = torch.Generator().manual_seed(77 + k)
+    B, c0, c1, co, hw = 4, 128, 64, 256, 16
+    x0, x1 = bf(torch.randn(B, c0, hw, hw, generator=g)), bf(torch.randn(2, c1, hw, hw, generator=g))
+    w = bf(torch.randn(co, c0 + c1, k, k, generator=g) / math.sqrt((c0 + c1) * k * k))
+    b, emb_all = torch.randn(co, generator=g), torch.randn(B, 700, generator=g)
+    res = bf(torch.randn(B, co, hw, hw, generator=g))
+    want = (F.conv2d(torch.cat([x0, torch.cat([x1, x1], 0)], 1), w, b, padding=k // 2)
+            + emb_all[:, 256:256 + co, None, None] + res)
+    emb = emb_all.cuda()[:, 256:256 + co]
+    for res_dt in (torch.bfloat16, torch.float32):
+        got = ops.conv(nhwc(x0).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), co, k,
+                       x1=nhwc(x1).to(torch.bfloat16).cuda(), emb=emb, residual=nhwc(res).to(res_dt).cuda(),
+                       out_dtype=torch.float32, tensor_core=True)
+        assert max_abs(nchw(got.cpu()), want) < 2e-3
+
+
+def test_conv_tc_stride2_via_im2col(ops):
+    """Downsample (3x3, stride 2, pad 1) = im2col_3x3_s2 + 1x1 tensor-core GEMM."""
+    g = torch.Generator().manual_seed(5)
+    B, c, hw = 2, 128, 32
+    x = bf(torch.randn(B, c, hw, hw, generator=g))
+    w = bf(torch.randn(c, c, 3, 3, generator=g) / math.sqrt(9 * c))
+    b = torch.randn(c, generator=g)
+    want = F.conv2d(x, w, b, stride=2, padding=1)
+    cols = ops.im2col_3x3_s2(nhwc(x).to(torch.bfloat16).cuda())
+    got = ops.conv(cols, tc_w(w).cuda(), b.cuda(), c, 1, out_dtype=torch.float32, tensor_core=True)
+    assert max_abs(nchw(got.cpu()), want) < 2e-3
+
+
+def test_conv_tc_rejects_unsupported(ops):
+    x = torch.zeros(1, 12, 12, 64, device="cuda", dtype=torch.bfloat16)   # width 12 does not tile 128 pixels
+    w = torch.zeros(64, 9 * 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.conv(x, w, None, 64, 3, tensor_core=True)
