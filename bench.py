@@ -1,0 +1,365 @@
+"""Benchmark of STEDM's synthetic-image sampling path on B200 (BASELINE.json: images/sec, DDIM-50, cfg 1.5, 256^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--latent L] [--no-graph]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one generation batch: conditioning (layout rescaler + style encoder,
+cond and uncond), the classifier-free-guided DDIM-50 loop over the eps U-Net (100 U-Net evaluations per image),
+the first-stage VQ decode and the uint8 conversion — i.e. modules/ldm_diffusion.py:76-96 of the reference minus
+PNG writing.  Workload at N=1 = BASELINE.json configs[1] (flowers, batch 64, 256^2, bf16); each extra rank gets its
+own batch of 64 (weak scaling; per-sample noise keyed by global sample index; uint8 images all-gathered over NCCL).
+
+Prints ONE JSON line (rank 0).  ``value`` = images/s with inputs resident in HBM; ``e2e`` = the same through
+LDM_Diffusion.predict-style calls with pinned HOST buffers, H2D and D2H inside the timed region.
+``--impl reference`` times the reference's algorithm on the host cores (oracle port — the reference itself is
+Python and cannot be installed offline: pytorch_lightning / taming / omegaconf are absent) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+DDIM_STEPS, CFG_SCALE, ETA = 50, 1.5, 0.0
+UNET_GFLOP_PER_SAMPLE_L64 = 217.29      # per sample per U-Net forward at latent 64
+VAE_GFLOP_PER_SAMPLE_L64 = 670.6        # first-stage decode per image at 256^2
+SWIN_GFLOP_PER_IMAGE_256 = 11.9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic workload: layout one-hot, U(-1,1) style images, x_T keyed by global sample index
+# ----------------------------------------------------------------------------------------------------------
+def synthetic_batch(B, P, n_style, first_index):
+    g = torch.Generator().manual_seed(99 + first_index)
+    low = torch.rand(B, 1, 8, 8, generator=g)
+    mask = (torch.nn.functional.interpolate(low, size=(P, P), mode="bilinear") > 0.5).float()[:, 0]
+    seg_oh = torch.stack([1.0 - mask, mask], dim=1)                                  # (B,2,P,P) as the dataloader gives
+    style = torch.rand(B, n_style, 3, P, P, generator=torch.Generator().manual_seed(3 + first_index)) * 2 - 1
+    L = P // 4
+    x_T = torch.stack([torch.randn(3, L, L, generator=torch.Generator().manual_seed(1234 + first_index + i))
+                       for i in range(B)])
+    img = torch.zeros(B, 3, P, P)
+    return img, seg_oh, style, x_T
+
+
+def build_model(latent, n_style, precision):
+    from stedm_b200.config import load_config
+    from stedm_b200.modules.ldm_diffusion import LDM_Diffusion
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    sampling = "mp" if n_style > 1 else "augmented"
+    cfg = load_config(["style_agg=mean", f"style_sampling={sampling}", f"ddim_steps={DDIM_STEPS}", f"eta={ETA}",
+                       f"cfg_scale={CFG_SCALE}", f"diffusion.image_size={latent}", f"data.patch_size={4 * latent}"])
+    if n_style > 1:
+        cfg.style_sampling.num_patches = n_style
+    m = LDM_Diffusion(cfg, precision=precision, load_first_stage_ckpt=False)
+    apply_fixture_weights(m._model, seed=0)          # random-init weights of the architecture (no checkpoints offline)
+    return m
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores, bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(latent, n_style, sample_batch=1, sample_steps=1, sd=None):
+    """Times cond x2 + `sample_steps` guided DDIM steps + decode for `sample_batch` images on all host threads and
+    scales the loop to DDIM-50: images/s = B / (t_cond + 50 * t_step + t_decode)."""
+    from oracle import stedm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = 4 * latent
+    if sd is None:
+        from tests.util import oracle_state_dict
+        sd = oracle_state_dict(build_model(latent, n_style, "bf16")._model)
+    seg, style, x_T = O.synthetic_batch(sample_batch, P, n_style, seed=11)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        cond = O.get_conditioning(sd, seg, style)
+        unc = O.get_conditioning(sd, seg, torch.zeros_like(style) - 2)
+        t1 = time.perf_counter()
+        z, _ = O.ddim_sample(sd, cond, unc, x_T, S=DDIM_STEPS, cfg_scale=CFG_SCALE, max_steps=sample_steps)
+        t2 = time.perf_counter()
+        img = O.decode_first_stage(sd, z)
+        O.to_uint8(img)
+        t3 = time.perf_counter()
+    t_cond, t_step, t_dec = t1 - t0, (t2 - t1) / sample_steps, t3 - t2
+    per_batch = t_cond + DDIM_STEPS * t_step + t_dec
+    return dict(value=sample_batch / per_batch, seconds_measured=t3 - t0, t_cond=t_cond, t_ddim_step=t_step,
+                t_decode=t_dec, cores=torch.get_num_threads(),
+                sample=(f"batch {sample_batch} at {P}x{P}: conditioning x2 + {sample_steps} of {DDIM_STEPS} guided DDIM "
+                        f"steps (2 U-Net passes each) + VQ decode, loop time scaled x{DDIM_STEPS}/{sample_steps}"))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    sd = None
+    from tests.util import oracle_state_dict
+    sd = oracle_state_dict(build_model(args.latent, args.n_style, "bf16")._model)
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_sample(args.latent, args.n_style, 1, 1, sd)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    line = {"metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    P = 4 * args.latent
+    return {"workload": f"flowers DDIM-{DDIM_STEPS} cfg {CFG_SCALE} sampling, batch {args.batch} per GPU, {P}x{P} image "
+                        f"(latent {args.latent}), style_agg=mean, {args.n_style} style image(s) per sample, "
+                        f"random-init fixture weights (BASELINE.json configs[1])",
+            "batch_per_gpu": args.batch, "image": P, "ddim_steps": DDIM_STEPS, "cfg_scale": CFG_SCALE, "eta": ETA,
+            "parallelism": f"dp{args.gpus} (one generation shard per rank, no per-step collective)",
+            "l2": "no flush: every step streams several GB of activations and 0.6 GB of weights, far above the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--n-style", type=int, default=1, dest="n_style")
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from stedm_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, L, P = args.batch, args.latent, 4 * args.latent
+
+    m = build_model(L, args.n_style, args.precision).to(dev).eval()
+    m._model.use_cuda_graph = not args.no_graph
+    first = rank * B                                              # global sample index of this rank's shard
+    img, seg_oh, style, x_T = synthetic_batch(B, P, args.n_style, first)
+    host = [t.pin_memory() for t in (img, seg_oh, style, x_T)]
+    devb = [t.to(dev) for t in host]
+    gathered = [torch.empty((B, P, P, 3), dtype=torch.uint8, device=dev) for _ in range(world)] if world > 1 else None
+    out_host = torch.empty((B, P, P, 3), dtype=torch.uint8).pin_memory()
+
+    def one_pass(bimg, bseg, bstyle, bx):
+        batch = (bimg, bseg.clone(), None, bstyle, None)           # prepare_batch edits seg_oh in place
+        u8 = m.generate(m.prepare_batch(batch), x_T=bx)
+        if world > 1:
+            dist.all_gather(gathered, u8)                          # final image gather over NVLink (north_star)
+        return u8
+
+    def resident_step():
+        return one_pass(*devb)
+
+    def e2e_step():
+        d = [t.to(dev, non_blocking=True) for t in host]
+        u8 = one_pass(*d)
+        out_host.copy_(u8, non_blocking=True)
+        return u8
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(k):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            resident_step()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        l0 = ops.LAUNCHES[0]
+        ms = timed(resident_step, args.steps)
+        launches = ops.LAUNCHES[0] - l0
+        clk = clocks.stop() if rank == 0 else None
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        roof = kernel_roofline(m, devb, B, L, args) if rank == 0 else None
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_img = world * B * args.steps
+    value = n_img / (ms / 1000.0)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = out_host.numel()
+    line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": n_img / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "unet_step_ms": roof.pop("unet_step_ms"), "unet_step_frac_of_peak": roof.pop("unet_step_frac"),
+            "roofline": roof}
+    if world == 1 and not args.skip_cpu_baseline:
+        cb = cpu_reference_sample(L, args.n_style, 1, 1)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": "images/s", "cores": cb["cores"], "kind": "port",
+                                "sample": cb["sample"]}
+    print(json.dumps(line))
+
+
+def kernel_roofline(m, devb, B, L, args):
+    """CUDA-event timing of every tensor-core convolution launch of one guided DDIM step (eager, after the timed
+    region, same stream) -> achieved TFLOP/s of the dominant kernel (stedm_conv_tc), plus the U-Net step time."""
+    from stedm_b200 import ops
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    model = m._model
+    pk = peaks()
+    img, seg_oh, style, x_T = devb
+    batch = m.prepare_batch((img, seg_oh.clone(), None, style, None))
+    _, c = model.get_input(batch, "image")
+    _, cu = model.get_input(dict(batch, style_imgs=torch.zeros_like(batch["style_imgs"]) - 2), "image")
+    sampler = DDIMSampler(model, use_cuda_graph=False)
+    sampler.make_schedule(ddim_num_steps=DDIM_STEPS, ddim_eta=ETA, verbose=False)
+    ts = torch.full((B,), 481, device=x_T.device, dtype=torch.long)
+    # whole-step time (2B-sample U-Net pass + K11), eager, averaged
+    for _ in range(2):
+        sampler.p_sample_ddim(x_T, c, ts, index=24, unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=cu)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        sampler.p_sample_ddim(x_T, c, ts, index=24, unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=cu)
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1) / 3
+    step_flops = 2 * B * UNET_GFLOP_PER_SAMPLE_L64 * (L / 64.0) ** 2 * 1e9
+    # per-launch timing of the tensor-core convolution
+    rec = []
+    orig = ops.conv
+
+    def timed_conv(x0, weight, bias, cout, ksize, **kw):
+        if not kw.get("tensor_core", True):
+            return orig(x0, weight, bias, cout, ksize, **kw)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig(x0, weight, bias, cout, ksize, **kw)
+        b.record()
+        bsz, h, w, c0 = x0.shape
+        c1 = 0 if kw.get("x1") is None else kw["x1"].shape[-1]
+        rec.append((a, b, 2.0 * bsz * h * w * cout * ksize * ksize * (c0 + c1), cout))
+        return out
+
+    ops.conv = timed_conv
+    try:
+        sampler.p_sample_ddim(x_T, c, ts, index=24, unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=cu)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv = orig
+    tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    tot_fl = sum(f for _, _, f, _ in rec)
+    big = [(a.elapsed_time(b), f) for a, b, f, co in rec if co % 256 == 0]
+    big_ms, big_fl = sum(t for t, _ in big), sum(f for _, f in big)
+    achieved = big_fl / (big_ms / 1e3) / 1e12 if big_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<256> (tcgen05 implicit-GEMM conv, BN=256)",
+            "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})", "traffic": None,
+            "launches_timed": len(big), "avg_launch_ms": big_ms / max(1, len(big)),
+            "algorithmic_flops_per_launch": big_fl / max(1, len(big)),
+            "all_tc_conv": {"launches": len(rec), "ms": tot_ms, "tflops": tot_fl / (tot_ms / 1e3) / 1e12 if tot_ms else 0.0,
+                            "share_of_unet_step": tot_ms / step_ms},
+            "unet_step_ms": step_ms, "unet_step_frac": step_flops / (step_ms / 1e3) / 1e12 / pk["tf_sustained"]}
+
+
+if __name__ == "__main__":
+    main()

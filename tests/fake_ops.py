@@ -1,0 +1,112 @@
+"""A torch-on-CPU stand-in for stedm_b200.ops, used ONLY by tests/test_engine_glue.py to check the host-side engine
+logic (block order, concat order, embedding offsets, weight repacking, padding) against the oracle without a GPU.
+It honours the kernels' data contracts: NHWC activations, packed weight layouts, NCHW fp32 at the boundary."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+LAUNCHES = [0]
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _bcast(x1, b):
+    if x1 is None or x1.shape[0] == b:
+        return x1
+    return x1.repeat(b // x1.shape[0], 1, 1, 1)
+
+
+def pack_nchw_to_nhwc(x0, x1, c_pad, out_dtype):
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    x = F.pad(x, (0, 0, 0, 0, 0, c_pad - x.shape[1]))
+    return _nhwc(x).to(out_dtype)
+
+
+def nhwc_to_nchw_f32(x):
+    return _nchw(x).float().contiguous()
+
+
+def timestep_embedding(t, dim):
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    a = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(a), torch.sin(a)], -1)
+
+
+def linear(x, w, b, silu_in=False):
+    return F.linear(F.silu(x) if silu_in else x, w, b)
+
+
+def gn_stats(x0, x1, stats=None):
+    return None
+
+
+def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype):
+    x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
+    y = F.group_norm(_nchw(x.float()), 32, gamma, beta, eps)
+    return _nhwc(F.silu(y) if silu else y).to(out_dtype)
+
+
+def upsample_nearest2x(x):
+    return _nhwc(F.interpolate(_nchw(x.float()), scale_factor=2, mode="nearest")).to(x.dtype)
+
+
+def im2col_3x3_s2(x):
+    b, h, w, c = x.shape
+    u = F.unfold(_nchw(x.float()), 3, padding=1, stride=2).reshape(b, c, 9, h // 2, w // 2)
+    return u.permute(0, 3, 4, 2, 1).reshape(b, h // 2, w // 2, 9 * c).to(x.dtype)
+
+
+def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
+         upsample=False, out_nchw=False, tensor_core=True, out=None):
+    x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
+    cin = x.shape[-1]
+    if tensor_core:   # [Cout][k*k*Cin]
+        w = weight.float().reshape(cout, ksize, ksize, cin).permute(0, 3, 1, 2)
+    else:             # [k*k*Cin][Cout]
+        w = weight.t().reshape(cout, ksize, ksize, cin).permute(0, 3, 1, 2)
+    xin = _nchw(x.float())
+    if upsample:
+        xin = F.interpolate(xin, scale_factor=2, mode="nearest")
+    y = F.conv2d(xin, w, bias, stride=stride, padding=ksize // 2)
+    if emb is not None:
+        y = y + emb[:, :, None, None]
+    if residual is not None:
+        y = y + _nchw(residual.float())
+    if out_nchw:
+        return y.contiguous()
+    return _nhwc(y).to(out_dtype or x0.dtype)
+
+
+def attention_tc_supported(head_dim, tokens):
+    return False
+
+
+def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
+                   scale, out_dtype):
+    b = q_src.shape[0]
+    flat = lambda t: t.reshape(b, tokens, token_stride).float()
+    outs = []
+    for h in range(heads):
+        q = flat(q_src)[:, :, q_off + h * head_stride: q_off + h * head_stride + head_dim]
+        k = flat(k_src)[:, :, k_off + h * head_stride: k_off + h * head_stride + head_dim]
+        v = flat(v_src)[:, :, v_off + h * head_stride: v_off + h * head_stride + head_dim]
+        w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) * scale, -1)
+        outs.append(torch.einsum("bts,bsc->btc", w, v))
+    return torch.cat(outs, -1).to(out_dtype)
+
+
+def vq_nearest(z, codebook, return_indices=False):
+    b, c, h, w = z.shape
+    zf = z.permute(0, 2, 3, 1).reshape(-1, c)
+    d = (zf ** 2).sum(1, keepdim=True) + (codebook ** 2).sum(1) - 2.0 * zf @ codebook.t()
+    idx = torch.argmin(d, 1)
+    zq = codebook[idx].reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+    return (zq, idx.int()) if return_indices else zq

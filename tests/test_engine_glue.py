@@ -1,0 +1,54 @@
+"""Host-side engine logic on CPU: the product's UNetRunner / DecoderRunner driven through a torch stand-in for the
+kernel layer (tests/fake_ops.py) must reproduce the reference's golden eps and decoded image.  This pins weight
+repacking, channel padding, concat order, embedding-table offsets and block order without needing a GPU; the
+kernels themselves are checked by the -m gpu tests."""
+import pytest
+import torch
+
+from tests import fake_ops
+from tests.util import build_config, load_golden, max_abs
+
+
+@pytest.fixture(scope="module")
+def cpu_model():
+    from stedm_b200.modules.ldm_diffusion import LDM_Diffusion
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    m = LDM_Diffusion(build_config(32, n_style=2), load_first_stage_ckpt=False)
+    apply_fixture_weights(m._model, seed=0)
+    return m.eval()
+
+
+@pytest.fixture()
+def patched(monkeypatch):
+    from stedm_b200 import engine
+    monkeypatch.setattr(engine, "ops", fake_ops)
+    return engine
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_unet_runner_glue(cpu_model, patched, precision, bar):
+    from oracle import stedm_oracle as O
+    g = load_golden("small_b2_l32")
+    _, _, x_T = O.synthetic_batch(2, 128, 2, 0)
+    runner = patched.UNetRunner(cpu_model._model.model.diffusion_model, precision)
+    t = torch.full((2,), 481, dtype=torch.long)
+    with torch.no_grad():
+        eps = runner(x_T, torch.from_numpy(g["c_concat"]), t, torch.from_numpy(g["c_crossattn"]))
+        # batched guidance: (cond | uncond) in one pass must equal the two separate passes
+        x2, t2 = torch.cat([x_T, x_T]), torch.cat([t, t])
+        cc = torch.from_numpy(g["c_concat"])
+        ctx = torch.cat([torch.from_numpy(g["c_crossattn"]), torch.from_numpy(g["uc_crossattn"])])
+        eps2 = runner(x2, torch.cat([cc, cc]), t2, ctx)
+    scale = float(torch.from_numpy(g["eps_c_481"]).abs().max())
+    assert max_abs(eps, g["eps_c_481"]) < bar * (scale if precision == "bf16" else 1.0)
+    assert max_abs(eps2[:2], g["eps_c_481"]) < bar * (scale if precision == "bf16" else 1.0)
+    assert max_abs(eps2[2:], g["eps_u_481"]) < bar * (scale if precision == "bf16" else 1.0)
+
+
+def test_decoder_runner_glue(cpu_model, patched):
+    g = load_golden("small_b2_l32")
+    runner = patched.DecoderRunner(cpu_model._model.first_stage_model, "fp32")
+    z = torch.from_numpy(g["z_final"])
+    with torch.no_grad():
+        assert max_abs(runner(z), g["dec_quant"]) < 1e-3
+        assert max_abs(runner(z, force_not_quantize=True), g["dec_noquant"]) < 1e-3

@@ -131,7 +131,7 @@ def test_full_ddim50_sample_log(precision, bar):
     z, inter = m._model.sample_log(_cond(g, "c_crossattn"), batch_size=2, ddim=True, ddim_steps=50, eta=0.0,
                                    log_every_t=1000, x_T=x_T.cuda(), unconditional_conditioning=_cond(g, "uc_crossattn"),
                                    unconditional_guidance_scale=1.5)
-    assert len(inter["x_inter"]) == 2 and len(inter["pred_x0"]) == 2        # x_T + the step with index == total-1
+    assert len(inter["x_inter"]) == 3 and len(inter["pred_x0"]) == 3        # x_T, index == total-1, and index 0 (0 % log_every_t == 0)
     r = rel_err(z, g["z_final"])
     print(f"{precision} DDIM-50 final latent rel err {r:.3e}")
     assert r < bar, r
