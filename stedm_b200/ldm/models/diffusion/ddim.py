@@ -163,11 +163,15 @@ class _GuidedStepper:
                 return self.unet.forward_split(x2, self.c_concat, t2, self.context)
             self.gx, self.gt = x2.clone(), t2.clone()
             self.graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES[0]
             with torch.cuda.graph(self.graph):
                 self.geps = self.unet.forward_split(self.gx, self.c_concat, self.gt, self.context)
+            self.graph_launches = ops.LAUNCHES[0] - n0
+            ops.LAUNCHES[0] = n0                      # capture enqueued nothing; replays are counted below
         self.gx.copy_(x2)
         self.gt.copy_(t2)
         self.graph.replay()
+        ops.LAUNCHES[0] += self.graph_launches
         return self.geps
 
     def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False):

@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference interface (no GPU): checkpoint-name compatibility, the plugin seam, the
+hydra-free config loader, fixture determinism, and the no-CPU-fallback rule."""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.util import build_config
+
+
+@pytest.fixture(scope="module")
+def model():
+    from stedm_b200.modules.ldm_diffusion import LDM_Diffusion
+    return LDM_Diffusion(build_config(32, n_style=1), load_first_stage_ckpt=False)
+
+
+def test_state_dict_names_match_reference(model, golden_dir):
+    """Every tensor of the reference's S_ZSS_DM state dict that is on the sampling path exists here with the same
+    name and shape (key list dumped from the reference by oracle/make_golden tooling)."""
+    ref = json.load(open(os.path.join(golden_dir, "reference_state_dict_keys.json")))
+    mine = {k: list(v.shape) for k, v in model._model.state_dict().items()}
+    skipped = ("model_ema.", "first_stage_model.encoder.")      # EMA shadow + VAE encoder: outside the path
+    for k, shape in ref.items():
+        if k.startswith(skipped):
+            continue
+        assert k in mine, k
+        assert mine[k] == shape, (k, mine[k], shape)
+    assert not [k for k in mine if k not in ref]
+
+
+def test_reference_checkpoint_loads_non_strict(model, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "reference_state_dict_keys.json")))
+    sd = {k: torch.zeros(s) for k, s in ref.items() if not k.endswith("relative_position_index")}
+    missing, unexpected = model._model.load_state_dict(sd, strict=False)
+    assert all(k.startswith(("model_ema.", "first_stage_model.encoder.")) for k in unexpected)
+    assert all(k.endswith("relative_position_index") for k in missing)
+
+
+def test_plugin_seam_redirects_reference_targets():
+    from stedm_b200.ldm.util import get_obj_from_str, instantiate_from_config
+    from stedm_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from stedm_b200.ldm.modules.encoders.modules import SpatialRescaler
+    assert get_obj_from_str("ldm.modules.diffusionmodules.openaimodel.UNetModel") is UNetModel
+    assert get_obj_from_str("torch.nn.Identity") is torch.nn.Identity
+    m = instantiate_from_config({"target": "ldm.modules.encoders.modules.SpatialRescaler",
+                                 "params": {"n_stages": 2, "in_channels": 2, "out_channels": 3}})
+    assert isinstance(m, SpatialRescaler) and tuple(m.channel_mapper.weight.shape) == (3, 2, 1, 1)
+    with pytest.raises(KeyError):
+        instantiate_from_config({"params": {}})
+
+
+def test_unet_rejects_configs_the_reference_cannot_build():
+    from stedm_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    with pytest.raises(TypeError):      # ds=1 in attention_resolutions -> reference: list.append() TypeError
+        UNetModel(64, 6, 64, 3, 1, [1], channel_mult=(1, 2), num_heads=4)
+    with pytest.raises(NotImplementedError):
+        UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, use_spatial_transformer=True, context_dim=512)
+
+
+def test_config_loader_composes_defaults_and_overrides():
+    from stedm_b200.config import load_config
+    c = load_config([])
+    assert c.ddim_steps == 128 and c.cfg_scale == 1.5 and c.style_agg.name == "linear" and c.diffusion.image_size == 128
+    assert c.diffusion.unet_config.params.channel_mult == [1, 4, 8] and c.data.patch_size == 512
+    c = load_config(["style_agg=mean", "style_sampling=mp", "location=cluster", "ddim_steps=50",
+                     "diffusion.image_size=64", "+predict_dir=/tmp/x"])
+    assert c.style_agg.name == "mean" and c.style_sampling.num_patches == 10 and c.location.n_gpus == 2
+    assert c.ddim_steps == 50 and c.diffusion.image_size == 64 and c.predict_dir == "/tmp/x"
+
+
+def test_fixture_weights_are_name_keyed_and_nonzero(model):
+    from stedm_b200.utils.fixture import apply_fixture_weights, fixture_tensor
+    apply_fixture_weights(model._model, seed=0)
+    sd = model._model.state_dict()
+    k = "model.diffusion_model.out.2.weight"                       # zero-initialised by the constructor
+    assert float(sd[k].abs().max()) > 0
+    assert torch.equal(sd[k], fixture_tensor(k, sd[k].shape, 0))
+    a, b = sd["agg_block._embedder.head.weight"], sd["_agg_block._embedder.head.weight"]
+    assert torch.equal(a, b)
+    assert float(sd["first_stage_model.quantize.embedding.weight"].std()) > 30
+
+
+def test_schedule_buffers_registered(model):
+    m = model._model
+    for name in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "posterior_variance",
+                 "posterior_mean_coef1", "logvar"):
+        assert getattr(m, name).shape == (1000,) and getattr(m, name).dtype == torch.float32
+    assert m.num_timesteps == 1000 and m.parameterization == "eps"
+
+
+def test_no_cpu_fallback(model):
+    """The product path must fail loudly off-GPU: no PyTorch/CPU fallback for the kernels."""
+    from stedm_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros(1, 8), torch.zeros(4, 8), None)
+    with pytest.raises(RuntimeError):
+        model._model.model.diffusion_model(torch.zeros(1, 6, 32, 32), torch.zeros(1, dtype=torch.long),
+                                           context=torch.zeros(1, 512))
+    with pytest.raises(RuntimeError):
+        model._model.first_stage_model.decode(torch.zeros(1, 3, 32, 32))
