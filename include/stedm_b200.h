@@ -94,11 +94,13 @@ typedef struct stedm_conv_desc {
   int32_t res_dtype;
   int32_t out_dtype;
   int32_t out_nchw;
-  int32_t cout;
+  int32_t cout;        /* GEMM N = rows of `weight` (tensor-core path: padded to a multiple of 16) */
+  int32_t cout_store;  /* NCHW output only: number of leading output channels actually stored (0 => cout) */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,
- * upsample 0, c0 % 64 == 0, c1 % 64 == 0, cout % 16 == 0, out NHWC. */
+ * upsample 0, c0 % 64 == 0, c1 % 64 == 0, cout % 16 == 0; output NHWC (bf16/fp32) or NCHW fp32 (the eps / image
+ * heads with 3 real channels: cout = 16 zero-padded weight rows, cout_store = 3). */
 int stedm_conv_tc(const stedm_conv_desc* d, void* stream);
 /* General fp32-accumulate SIMT implicit GEMM: the fp32 parity mode and every shape the tensor-core path rejects. */
 int stedm_conv_simt(const stedm_conv_desc* d, void* stream);

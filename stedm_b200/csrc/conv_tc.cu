@@ -37,6 +37,7 @@ struct TcParams {
   int c0_blks, c_blks;  // 64-channel slabs in source 0 / in the concat
   int x1_batch;
   int emb_stride, res_dtype, out_dtype;
+  int out_nchw, cout_store;
 };
 
 template <int BN>
@@ -195,7 +196,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       }
-      if (p.out_dtype == DT_BF16) {
+      if (p.out_nchw) {
+        // NCHW fp32 head (eps / image): consecutive lanes = consecutive pixels -> coalesced per channel plane
+        float* op = static_cast<float*>(p.out) + static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+      } else if (p.out_dtype == DT_BF16) {
         uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
 #pragma unroll
         for (int j = 0; j < CH; j += 8) {
@@ -241,8 +248,11 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
 extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_tc: null pointer");
   STEDM_REQUIRE(d->in_dtype == DT_BF16, "conv_tc: operands must be bf16");
-  STEDM_REQUIRE(d->stride == 1 && d->upsample == 0 && d->out_nchw == 0,
-                "conv_tc: stride/upsample/NCHW output are handled by im2col_3x3_s2 / upsample_nearest2x / conv_simt");
+  STEDM_REQUIRE(d->stride == 1 && d->upsample == 0,
+                "conv_tc: stride / upsample are handled by im2col_3x3_s2 / upsample_nearest2x");
+  STEDM_REQUIRE(!d->out_nchw || (d->out_dtype == DT_F32 && d->residual == nullptr && d->cout_store >= 0 &&
+                                 d->cout_store <= d->cout),
+                "conv_tc: NCHW output must be fp32, without residual, cout_store <= cout");
   STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
   STEDM_REQUIRE(d->c0 > 0 && d->c0 % TC_BK == 0 && d->c1 % TC_BK == 0 && (d->c1 == 0 || d->x1),
                 "conv_tc: channel counts must be multiples of 64 (%d, %d)", d->c0, d->c1);
@@ -311,6 +321,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.c0_blks = d->c0 / TC_BK; p.c_blks = ctot / TC_BK;
   p.x1_batch = x1b;
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
+  p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return launch_tc<256>(ma0, ma1, mw, p, s);

@@ -25,12 +25,13 @@ def _f32(v):
 
 
 class DDIMSampler(object):
-    def __init__(self, model, schedule="linear", use_cuda_graph=None, **kwargs):
+    def __init__(self, model, schedule="linear", use_cuda_graph=None, share_trunk=None, **kwargs):
         super().__init__()
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self.use_cuda_graph = getattr(model, "use_cuda_graph", False) if use_cuda_graph is None else use_cuda_graph
+        self.share_trunk = getattr(model, "share_trunk", True) if share_trunk is None else share_trunk
 
     def register_buffer(self, name, attr):
         if isinstance(attr, torch.Tensor) and attr.device != self.model.device:
@@ -138,9 +139,17 @@ class _GuidedStepper:
         ca = lambda c: c["c_crossattn"][0] if len(c["c_crossattn"]) == 1 else torch.cat(c["c_crossattn"], 1)
         if not isinstance(cond, dict):
             raise NotImplementedError("STEDM's hybrid conditioning is a dict {'c_concat': [...], 'c_crossattn': [...]}")
+        self.shared = False
         if self.guided:
-            self.c_concat = torch.cat([cc(cond), cc(uncond)], 0).float().contiguous()
             self.context = torch.cat([ca(cond), ca(uncond)], 0).float().contiguous()
+            # cond and uncond differ only in the style vector when their layouts agree (always so in predict_step):
+            # then the encoder trunk is evaluated once for both (bit-identical)
+            self.shared = (getattr(sampler, "share_trunk", True) and cc(cond).shape == cc(uncond).shape
+                           and bool(torch.equal(cc(cond), cc(uncond))) and unet.shared_trunk_ok(self.b, shape[-1]))
+            if self.shared:
+                self.c_concat = cc(cond).float().contiguous()
+            else:
+                self.c_concat = torch.cat([cc(cond), cc(uncond)], 0).float().contiguous()
         else:
             self.c_concat = cc(cond).float().contiguous()
             self.context = ca(cond).float().contiguous()
@@ -150,7 +159,7 @@ class _GuidedStepper:
 
     def _eps(self, x, t):
         """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,)."""
-        if self.guided:
+        if self.guided and not self.shared:
             x2 = torch.cat([x, x], 0)
             t2 = torch.cat([t, t], 0)
         else:

@@ -111,7 +111,7 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
     _cuda(x0, x1, weight, bias, residual)
@@ -123,7 +123,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     uh, uw = (2 * h, 2 * w) if upsample else (h, w)
     oh, ow = uh // stride, uw // stride
     if out is None:
-        shape = (b, cout, oh, ow) if out_nchw else (b, oh, ow, cout)
+        shape = (b, cout_store or cout, oh, ow) if out_nchw else (b, oh, ow, cout)
         out = torch.empty(shape, device=x0.device, dtype=out_dtype)
     d = ConvDesc()
     d.x0, d.x1, d.weight, d.bias = _ptr(x0), _ptr(x1), _ptr(weight), _ptr(bias)
@@ -135,6 +135,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.emb_stride = 0 if emb is None else emb.stride(0)
     d.res_dtype = F32 if residual is None else _DT[residual.dtype]
     d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
+    d.cout_store = cout_store if out_nchw else 0
     if tensor_core:
         assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ksize * ksize * (c0 + c1), \
             (weight.shape, cout, ksize, c0, c1)

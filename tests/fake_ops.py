@@ -65,7 +65,7 @@ def im2col_3x3_s2(x):
 
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
     if tensor_core:   # [Cout][k*k*Cin]
@@ -81,7 +81,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     if residual is not None:
         y = y + _nchw(residual.float())
     if out_nchw:
-        return y.contiguous()
+        return y[:, :cout_store or cout].contiguous()
     return _nhwc(y).to(out_dtype or x0.dtype)
 
 

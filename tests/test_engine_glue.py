@@ -39,6 +39,11 @@ def test_unet_runner_glue(cpu_model, patched, precision, bar):
         cc = torch.from_numpy(g["c_concat"])
         ctx = torch.cat([torch.from_numpy(g["c_crossattn"]), torch.from_numpy(g["uc_crossattn"])])
         eps2 = runner(x2, torch.cat([cc, cc]), t2, ctx)
+        # shared encoder trunk: B inputs, 2B contexts -> the same 2B eps
+        eps3 = runner(x_T, cc, t, ctx)
+    # (the CPU stand-in's conv picks batch-dependent algorithms, so bf16 emulation is not bit-stable here; the
+    #  bit-exactness of the real kernels is asserted on the GPU in tests/test_gpu_model.py)
+    assert max_abs(eps3, eps2) < (1e-5 if precision == "fp32" else 5e-2)
     scale = float(torch.from_numpy(g["eps_c_481"]).abs().max())
     assert max_abs(eps, g["eps_c_481"]) < bar * (scale if precision == "bf16" else 1.0)
     assert max_abs(eps2[:2], g["eps_c_481"]) < bar * (scale if precision == "bf16" else 1.0)

@@ -198,3 +198,20 @@ def test_cuda_graph_sampler_matches_eager():
     finally:
         m._model.use_cuda_graph = False
     assert torch.equal(z0, z1)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_shared_trunk_is_bit_identical(precision):
+    """Guided step with the encoder trunk evaluated once for (cond, uncond) == the batched 2B pass, bit for bit."""
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision=precision)
+    cond, unc = _cond(g, "c_crossattn"), _cond(g, "uc_crossattn")
+    ts = torch.full((2,), 481, device="cuda", dtype=torch.long)
+    outs = []
+    for share in (False, True):
+        s = DDIMSampler(m._model, share_trunk=share)
+        s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+        outs.append(s.p_sample_ddim(x_T.cuda(), cond, ts, index=24, unconditional_guidance_scale=1.5,
+                                    unconditional_conditioning=unc))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

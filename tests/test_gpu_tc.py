@@ -103,3 +103,22 @@ def test_conv_tc_rejects_unsupported(ops):
     w = torch.zeros(64, 9 * 64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         ops.conv(x, w, None, 64, 3, tensor_core=True)
+
+
+def test_conv_tc_nchw_head(ops):
+    """The eps / image heads (128 -> 3): weight rows zero-padded to one 16-wide UMMA tile, the epilogue stores the
+    3 real channels as NCHW fp32."""
+    g = torch.Generator().manual_seed(9)
+    B, c, hw = 3, 128, 32
+    x = bf(torch.randn(B, c, hw, hw, generator=g))
+    w = bf(torch.randn(3, c, 3, 3, generator=g) / math.sqrt(9 * c))
+    b = torch.randn(3, generator=g)
+    want = F.conv2d(x, w, b, padding=1)
+    wp = torch.zeros(16, c, 3, 3)
+    wp[:3] = w
+    bp = torch.zeros(16)
+    bp[:3] = b
+    got = ops.conv(nhwc(x).to(torch.bfloat16).cuda(), tc_w(wp).cuda(), bp.cuda(), 16, 3, out_dtype=torch.float32,
+                   tensor_core=True, out_nchw=True, cout_store=3)
+    assert tuple(got.shape) == (B, 3, hw, hw)
+    assert max_abs(got.cpu(), want) < 2e-3
