@@ -111,8 +111,18 @@ int stedm_conv_simt(const stedm_conv_desc* d, void* stream);
 int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_a, int dtype_b, int dtype_c, int m, int n, int k,
                     int lda, int ldb, int ldc, int b_is_nk, int nb, int nh, long long a_sb, long long a_sh,
                     long long b_sb, long long b_sh, long long c_sb, long long c_sh, float alpha, void* stream);
-/* In-place row softmax over the last dimension of a [rows][cols] fp32 matrix (openaimodel.py:392, model.py:190). */
-int stedm_softmax_rows(float* x, long long rows, int cols, void* stream);
+/* Row softmax of scale * x over the last dimension of a [rows][cols] fp32 matrix (openaimodel.py:392, model.py:189-190).
+ * x is used as scratch; the probabilities go to `out` (fp32 or bf16 [rows][cols]); out == NULL => in place. */
+int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale, void* stream);
+
+/* K5  Fused flash-style self-attention on tcgen05 (S and O accumulators in TMEM, online fp32 softmax, P staged as
+ * bf16 in shared memory): the U-Net AttentionBlock, head_dim 64 or 128, any token count.
+ * q, k, v: bf16, token-major: element (b, h, t, c) at base + b*stride_b + h*stride_h + t*stride_t + c (strides in
+ * elements, multiples of 8).  out: bf16 [batch][tokens][heads*head_dim].  scale multiplies q.k (= ch^-1/2).
+ * Replaces QKVAttentionLegacy.forward (openaimodel.py:378-394): (q*ch^-1/4).(k*ch^-1/4), fp32 softmax, .v */
+int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int tokens,
+                       int head_dim, long long stride_b, long long stride_h, long long stride_t, float scale,
+                       void* stream);
 
 
 /* ----------------------------------------------------------------------------------------------------

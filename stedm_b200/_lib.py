@@ -36,7 +36,8 @@ SIGNATURES = {
     "stedm_conv_simt": [C.POINTER(ConvDesc), vp],
     "stedm_gemm_simt": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64,
                         i64, i64, f32, vp],
-    "stedm_softmax_rows": [vp, i64, i32, vp],
+    "stedm_softmax_rows": [vp, vp, i32, i64, i32, f32, vp],
+    "stedm_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, f32, vp],
     "stedm_upsample_nearest2x": [vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_im2col_3x3_s2": [vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_pack_nchw_to_nhwc": [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp],

@@ -197,11 +197,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
       if (p.out_nchw) {
-        // NCHW fp32 head (eps / image): consecutive lanes = consecutive pixels -> coalesced per channel plane
-        float* op = static_cast<float*>(p.out) + static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+        // channel-major output (eps / image heads in fp32; V^T for the decoder attention in bf16): consecutive
+        // lanes = consecutive pixels -> coalesced per channel plane
+        const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+        if (p.out_dtype == DT_F32) {
+          float* op = static_cast<float*>(p.out) + base;
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+        } else {
+          __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + base;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+        }
       } else if (p.out_dtype == DT_BF16) {
         uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
 #pragma unroll
@@ -250,9 +259,8 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d->in_dtype == DT_BF16, "conv_tc: operands must be bf16");
   STEDM_REQUIRE(d->stride == 1 && d->upsample == 0,
                 "conv_tc: stride / upsample are handled by im2col_3x3_s2 / upsample_nearest2x");
-  STEDM_REQUIRE(!d->out_nchw || (d->out_dtype == DT_F32 && d->residual == nullptr && d->cout_store >= 0 &&
-                                 d->cout_store <= d->cout),
-                "conv_tc: NCHW output must be fp32, without residual, cout_store <= cout");
+  STEDM_REQUIRE(!d->out_nchw || (d->residual == nullptr && d->cout_store >= 0 && d->cout_store <= d->cout),
+                "conv_tc: NCHW output takes no residual and needs cout_store <= cout");
   STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
   STEDM_REQUIRE(d->c0 > 0 && d->c0 % TC_BK == 0 && d->c1 % TC_BK == 0 && (d->c1 == 0 || d->x1),
                 "conv_tc: channel counts must be multiples of 64 (%d, %d)", d->c0, d->c1);

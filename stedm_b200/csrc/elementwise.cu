@@ -432,27 +432,36 @@ extern "C" int stedm_image_to_uint8(const float* img, uint8_t* out, int batch, i
 // =====================================================================================================
 // Row softmax (fp32, in place), one warp per row; used by the fp32-mode attention.
 // =====================================================================================================
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long long rows, int cols) {
+template <typename TO>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, TO* __restrict__ out, long long rows,
+                                                           int cols, float scale) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
   float* r = x + row * cols;
+  TO* o = out + row * cols;
   float m = -INFINITY;
   for (int i = lane; i < cols; i += 32) m = fmaxf(m, r[i]);
-  m = warp_max(m);
+  m = warp_max(m) * scale;
   float s = 0.f;
   for (int i = lane; i < cols; i += 32) {
-    const float e = expf(r[i] - m);
-    r[i] = e;
+    const float e = expf(r[i] * scale - m);
+    r[i] = e;                      // each lane re-reads only what it wrote
     s += e;
   }
   s = warp_sum(s);
-  for (int i = lane; i < cols; i += 32) r[i] = __fdiv_rn(r[i], s);
+  for (int i = lane; i < cols; i += 32) o[i] = from_f32<TO>(__fdiv_rn(r[i], s));
 }
 
-extern "C" int stedm_softmax_rows(float* x, long long rows, int cols, void* stream) {
-  STEDM_REQUIRE(x && rows > 0 && cols > 0, "softmax_rows: bad argument");
+extern "C" int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale,
+                                  void* stream) {
+  STEDM_REQUIRE(x && rows > 0 && cols > 0 && scale > 0.f, "softmax_rows: bad argument");
   STEDM_REQUIRE((rows + 7) / 8 < 0x7fffffffLL, "softmax_rows: too many rows");
-  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (out == nullptr || out_dtype == DT_F32)
+    softmax_rows_kernel<float><<<grid, 256, 0, s>>>(x, out ? static_cast<float*>(out) : x, rows, cols, scale);
+  else
+    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), rows, cols, scale);
   return check_launch("softmax_rows");
 }

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-      for (int p = p_begin + lane; p < p_end; p += lanes) {
+#pragma unroll 4
+      for (int p = p_begin + lane; p < p_end; p += lanes) {  // independent 16 B loads: unrolled for MLP
         float v[8];
         load8<T>(item_ptr<T>(x0, x1, b, b1, p, hw, c0, c1, item), v);
 #pragma unroll
@@ -119,29 +120,35 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
                                                               TO* __restrict__ out) {
   extern __shared__ float s_ab[];  // scale[C], shift[C]
   __shared__ double s_tot[2 * GN_GROUPS];
+  __shared__ float s_mr[2 * GN_GROUPS];  // per group: mean, rstd
   const int C = c0 + c1, items = C / 8, cpg = C / GN_GROUPS;
   const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
   if (threadIdx.x < 2 * GN_GROUPS) {
     const double* src = partials + static_cast<size_t>(b) * n_chunks * GN_GROUPS * 2 + threadIdx.x;
     double acc = 0.0;
-    for (int k = 0; k < n_chunks; ++k) acc += src[static_cast<size_t>(k) * GN_GROUPS * 2];
+    for (int k = 0; k < n_chunks; ++k) acc += src[static_cast<size_t>(k) * GN_GROUPS * 2];  // fixed order
     s_tot[threadIdx.x] = acc;  // index = g*2 + which
   }
   __syncthreads();
-  const double n = static_cast<double>(hw) * cpg;
+  if (threadIdx.x < GN_GROUPS) {  // the only double-precision sqrt/div: 32 per block
+    const double n = static_cast<double>(hw) * cpg;
+    const double mean = s_tot[threadIdx.x * 2] / n;
+    double var = s_tot[threadIdx.x * 2 + 1] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mr[threadIdx.x * 2] = static_cast<float>(mean);
+    s_mr[threadIdx.x * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += GN_THREADS) {
     const int g = c / cpg;
-    const double mean = s_tot[g * 2] / n;
-    double var = s_tot[g * 2 + 1] / n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float a = rstd * gamma[c];
+    const float a = s_mr[g * 2 + 1] * gamma[c];
     s_ab[c] = a;
-    s_ab[C + c] = beta[c] - static_cast<float>(mean) * a;
+    s_ab[C + c] = beta[c] - s_mr[g * 2] * a;
   }
   __syncthreads();
   const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
   const size_t total = static_cast<size_t>(p_end - p_begin) * items;
+#pragma unroll 4
   for (size_t i = threadIdx.x; i < total; i += GN_THREADS) {
     const int item = static_cast<int>(i % items);
     const size_t p = p_begin + i / items;
@@ -159,16 +166,20 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
 
 // Pixel range per statistics block: a function of (hw, C) ONLY (never of the batch), at most 128 chunks per sample.
 int stats_pix_per_block(int hw, int C) {
-  const int by_bytes = max(4, 8192 / C);
+  const int by_bytes = max(4, 65536 / C);  // ~128 KB of bf16 per block
   const int by_count = (hw + 127) / 128;
   return min(hw, max(by_bytes, by_count));
 }
 
 int apply_pix_per_block(int batch, int hw, int C) {
-  const int min_pix = max(1, (16 * 1024) / (C * 2));
-  const int blocks_per_sample = max(1, (148 * 16 + batch - 1) / batch);
-  int ppb = (hw + blocks_per_sample - 1) / blocks_per_sample;
-  ppb = max(ppb, min_pix);
+  // >= 64 KB of input per block (amortises the per-block scale/shift prologue) unless that leaves the GPU short of
+  // ~4 blocks per SM, then smaller down to 8 KB
+  int ppb = max(1, 32768 / C);
+  const long long blocks = static_cast<long long>(batch) * ((hw + ppb - 1) / ppb);
+  if (blocks < 148 * 4) {
+    const int blocks_per_sample = max(1, (148 * 4 + batch - 1) / batch);
+    ppb = max(max(1, 4096 / C), (hw + blocks_per_sample - 1) / blocks_per_sample);
+  }
   return min(ppb, hw);
 }
 

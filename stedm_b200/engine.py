@@ -337,7 +337,13 @@ class DecoderRunner:
         # q, k, v 1x1 convs stacked into one GEMM: output channels [q | k | v]
         wq = torch.cat([at.q.weight, at.k.weight, at.v.weight], 0)
         bq = torch.cat([at.q.bias, at.k.bias, at.v.bias], 0)
-        self.att_qkv = PackedConv(wq, bq, prec)
+        if prec.tc:
+            # tensor-core path: separate dense q, k and (channel-major) v^T tensors feed two GEMMs per sample
+            self.att_q = PackedConv(at.q.weight, at.q.bias, prec)
+            self.att_k = PackedConv(at.k.weight, at.k.bias, prec)
+            self.att_v = PackedConv(at.v.weight, at.v.bias, prec)
+        else:
+            self.att_qkv = PackedConv(wq, bq, prec)
         self.att_proj = PackedConv(at.proj_out.weight, at.proj_out.bias, prec)
         self.att_c = at.q.weight.shape[0]
         self.mid2 = res(d.mid.block_2)
@@ -380,13 +386,24 @@ class DecoderRunner:
         B, H, W, Cc = x.shape
         T = H * W
         a = self.att_norm(x, None, False, prec.act, pool.next())
-        qkv = self.att_qkv(a)                                   # [B, H, W, 3C] = [q | k | v]
         scale = float(Cc) ** -0.5
-        if prec.tc and ops.attention_tc_supported(Cc, T):
-            o = ops.attention_tc(qkv, qkv, qkv, 1, Cc, T, (T * 3 * Cc, 0, 3 * Cc), scale, q_off=0, k_off=Cc,
-                                 v_off=2 * Cc)
+        if prec.tc:
+            # d = 512 is too wide for one CTA's TMEM (S + O accumulators), so the decoder attention runs as two
+            # tensor-core GEMMs per sample on the implicit-GEMM kernel: S = Q K^T (K as the "weight" [T][C]) into a
+            # reused fp32 T x T buffer, a scaled row softmax to bf16, and O = P V (V^T [C][T] written channel-major
+            # by the v conv's epilogue as the "weight").
+            q = self.att_q(a)
+            k = self.att_k(a)
+            vt = self.att_v(a, out_dtype=torch.bfloat16, out_nchw=True)          # [B, C, H, W]
+            o = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.bfloat16)
+            s = torch.empty((1, H, W, T), device=x.device, dtype=torch.float32)
+            pb = torch.empty((1, H, W, T), device=x.device, dtype=torch.bfloat16)
+            for i in range(B):
+                ops.conv(q[i:i + 1], k[i].view(T, Cc), None, T, 1, tensor_core=True, out=s)
+                ops.softmax_rows(s.view(T, T), scale, out=pb.view(T, T))
+                ops.conv(pb, vt[i].view(Cc, T), None, Cc, 1, tensor_core=True, out=o[i:i + 1])
         else:
-            o = None
+            qkv = self.att_qkv(a)                               # [B, H, W, 3C] = [q | k | v]
             # bound the materialised score matrix (B x T x T fp32) to ~2 GiB per chunk
             chunk = max(1, min(B, (1 << 29) // (T * T)))
             outs = []

@@ -153,9 +153,8 @@ class _GuidedStepper:
         else:
             self.c_concat = cc(cond).float().contiguous()
             self.context = ca(cond).float().contiguous()
-        self.graph = None
         self.use_graph = allow_graph and sampler.use_cuda_graph
-        self._warm = 0
+        self._graph_inputs_stale = True
 
     def _eps(self, x, t):
         """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,)."""
@@ -166,22 +165,34 @@ class _GuidedStepper:
             x2, t2 = x, t
         if not self.use_graph:
             return self.unet.forward_split(x2, self.c_concat, t2, self.context)
-        if self.graph is None:
-            if self._warm < 1:  # one eager pass first: lazy kernel attribute setup must not happen under capture
-                self._warm += 1
+        # CUDA graph of the U-Net pass (worth it only when a pass is launch-bound, i.e. small batches): captured
+        # once per shape signature and cached on the U-Net module, with static input buffers, so later sampler
+        # objects (sample_log builds a new DDIMSampler per call, like the reference) replay instead of re-capturing.
+        cache = self.unet.__dict__.setdefault("_graph_cache", {})
+        key = (tuple(x2.shape), tuple(self.c_concat.shape), tuple(self.context.shape), self.unet.precision)
+        ent = cache.get(key)
+        if ent is None:
+            warm = cache.setdefault(("warm",) + key, [0])
+            if warm[0] < 1:   # one eager pass first: lazy kernel attribute setup must not happen under capture
+                warm[0] += 1
                 return self.unet.forward_split(x2, self.c_concat, t2, self.context)
-            self.gx, self.gt = x2.clone(), t2.clone()
-            self.graph = torch.cuda.CUDAGraph()
+            ent = {"x": x2.clone(), "t": t2.clone(), "cc": self.c_concat.clone(), "ctx": self.context.clone(),
+                   "graph": torch.cuda.CUDAGraph()}
             n0 = ops.LAUNCHES[0]
-            with torch.cuda.graph(self.graph):
-                self.geps = self.unet.forward_split(self.gx, self.c_concat, self.gt, self.context)
-            self.graph_launches = ops.LAUNCHES[0] - n0
+            with torch.cuda.graph(ent["graph"]):
+                ent["eps"] = self.unet.forward_split(ent["x"], ent["cc"], ent["t"], ent["ctx"])
+            ent["launches"] = ops.LAUNCHES[0] - n0
             ops.LAUNCHES[0] = n0                      # capture enqueued nothing; replays are counted below
-        self.gx.copy_(x2)
-        self.gt.copy_(t2)
-        self.graph.replay()
-        ops.LAUNCHES[0] += self.graph_launches
-        return self.geps
+            cache[key] = ent
+        if self._graph_inputs_stale:
+            ent["cc"].copy_(self.c_concat)
+            ent["ctx"].copy_(self.context)
+            self._graph_inputs_stale = False
+        ent["x"].copy_(x2)
+        ent["t"].copy_(t2)
+        ent["graph"].replay()
+        ops.LAUNCHES[0] += ent["launches"]
+        return ent["eps"].clone()
 
     def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False):
         s = self.s

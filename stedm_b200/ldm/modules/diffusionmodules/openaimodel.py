@@ -144,23 +144,28 @@ class UNetModel(nn.Module):
         nn.init.zeros_(self.out[2].weight)
         nn.init.zeros_(self.out[2].bias)
         self._runner = None
+        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
 
     # ---- packed-weight lifecycle ------------------------------------------------------------------------
     def invalidate_packed(self):
         self._runner = None
+        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
 
     def _apply(self, fn, *a, **k):
         self._runner = None
+        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
         self._runner = None
+        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
         return super().load_state_dict(*a, **k)
 
     def set_precision(self, precision):
         if precision != self.precision:
             self.precision = precision
             self._runner = None
+            self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
 
     def runner(self):
         if self._runner is None:

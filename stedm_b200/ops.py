@@ -157,12 +157,14 @@ def gemm_simt(a, b, c, m, n, k, lda, ldb, ldc, b_is_nk, nb, nh, a_strides, b_str
           c_strides[1], float(alpha), _stream())
 
 
-def softmax_rows(x):
-    _cuda(x)
-    assert x.dtype == torch.float32
+def softmax_rows(x, scale=1.0, out=None):
+    """softmax(scale * x) over the last dim of fp32 ``x`` (used as scratch); result in ``out`` (fp32/bf16) or in place."""
+    _cuda(x, out)
+    assert x.dtype == torch.float32 and (out is None or out.shape == x.shape)
     cols = x.shape[-1]
-    _call("stedm_softmax_rows", _ptr(x), x.numel() // cols, cols, _stream())
-    return x
+    _call("stedm_softmax_rows", _ptr(x), _ptr(out), F32 if out is None else _DT[out.dtype], x.numel() // cols, cols,
+          float(scale), _stream())
+    return x if out is None else out
 
 
 def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
@@ -185,8 +187,8 @@ def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v
 
 
 def attention_tc_supported(head_dim, tokens):
-    """Shapes the fused tcgen05 attention kernel takes (none yet: the CUDA-core path runs)."""
-    return False
+    """Shapes the fused tcgen05 attention kernel takes (stedm_attention_tc)."""
+    return head_dim in (64, 128)
 
 
 def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0):

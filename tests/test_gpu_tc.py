@@ -122,3 +122,34 @@ def test_conv_tc_nchw_head(ops):
                    tensor_core=True, out_nchw=True, cout_store=3)
     assert tuple(got.shape) == (B, 3, hw, hw)
     assert max_abs(got.cpu(), want) < 2e-3
+
+
+@pytest.mark.parametrize("heads,ch,T,B", [(8, 128, 256, 2), (4, 64, 64, 3), (8, 128, 1024, 1), (2, 128, 100, 2),
+                                          (1, 64, 300, 1)])
+def test_attention_tc_legacy_layout(ops, heads, ch, T, B):
+    """Fused tcgen05 flash attention vs QKVAttentionLegacy math (openaimodel.py:378-394) on bf16-rounded q, k, v."""
+    g = torch.Generator().manual_seed(heads * 100 + T)
+    Cc = heads * ch
+    qkv = bf(torch.randn(B, 3 * Cc, T, generator=g))
+    q, k, v = qkv.reshape(B * heads, 3 * ch, T).split(ch, dim=1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s).float(), dim=-1)
+    want = torch.einsum("bts,bcs->bct", w, v).reshape(B, Cc, T).permute(0, 2, 1)          # [B, T, C]
+    buf = qkv.permute(0, 2, 1).contiguous().to(torch.bfloat16).cuda()                      # [B, T, 3C] head-major
+    got = ops.attention_tc(buf, buf, buf, heads, ch, T, (T * 3 * Cc, 3 * ch, 3 * Cc), 1 / math.sqrt(ch),
+                           q_off=0, k_off=ch, v_off=2 * ch)
+    torch.cuda.synchronize()
+    err = max_abs(got.float().cpu(), want)
+    assert err < 2e-2 * max(1.0, float(want.abs().max())), err
+
+
+def test_softmax_rows_scaled_bf16(ops):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(300, 1000, generator=g) * 3
+    want = torch.softmax(x * 0.25, dim=-1)
+    out = torch.empty(300, 1000, dtype=torch.bfloat16, device="cuda")
+    ops.softmax_rows(x.cuda(), 0.25, out=out)
+    assert max_abs(out.float().cpu(), want) < 2e-3
+    y = x.cuda()
+    ops.softmax_rows(y, 0.25)
+    assert max_abs(y.cpu(), want) < 1e-6
