@@ -1,6 +1,6 @@
 // K1/K3/K4/K10: convolution (3x3 pad 1 or 1x1, stride 1) and plain GEMM as an implicit GEMM on Blackwell's
 // 5th-generation tensor cores: tcgen05.mma (bf16 x bf16 -> fp32) issued by one thread, operands staged in
-// shared memory by TMA with the 128-byte swizzle, accumulator in TMEM, epilogue through tcgen05.ld.
+// shared memory by TMA with the 128-byte swizzle, accumulators in TMEM, epilogue through tcgen05.ld.
 //
 //   M = B*H*W output pixels (tile 128 = UMMA_M), N = Cout (tile BN = UMMA_N), K = taps * Cin (slab 64).
 //
@@ -9,14 +9,22 @@
 // and columns are zero-filled by the TMA unit, which is exactly the convolution's zero padding.  The box lands
 // in shared memory as 128 rows x 128 B, i.e. the canonical K-major SWIZZLE_128B UMMA layout.  A channel concat
 // [x0 | x1] (openaimodel.py:800) is a second tensor map selected per K slab — no concatenated copy exists.
-// B operand = weights repacked once at load time to bf16 [Cout][tap][Cin] (K-major), 2-D TMA box {64, BN}.
+// B operand = weights repacked once at load time to bf16 [Cout][tap][Cin] (K-major), 2-D TMA box {64, BN/CL}.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
-// elected lane), warps 2-5 = epilogue (TMEM lane quadrant = warp % 4).  smem ring of STAGES {A,B} slabs with
-// full/empty mbarriers; tcgen05.commit releases slabs and finally signals the epilogue.
+// PERSISTENT kernel: one CTA (or CTA pair) per SM loops over output tiles (output-channel tile fastest, so the
+// n-tiles of a pixel tile run concurrently and share activation slabs through L2).  Warp roles (192 threads):
+// warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-5 =
+// epilogue (TMEM lane quadrant = warp % 4).  Three pipelines: the smem ring of STAGES {A,B} slabs (full/empty
+// mbarriers, released by tcgen05.commit) runs continuously across tiles; the accumulator is DOUBLE-BUFFERED in
+// TMEM (tmem_full/tmem_empty), so the epilogue of tile i overlaps the main loop of tile i+1 — measured necessary:
+// with a single accumulator the tensor pipe idled ~30 % of the time behind the epilogue's global loads/stores.
+// CL = 2: the two CTAs of a cluster take neighbouring pixel tiles of the same channel tile and TMA-multicast one
+// half of the weight slab each into both CTAs (per-SM L2->SM traffic A+B/2 instead of A+B per slab).
 // Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287) + residual[m][n]
-// (skip connection, openaimodel.py:288), written as bf16 or fp32 NHWC with 16-byte stores.
+// (skip connection, openaimodel.py:288); bf16/fp32 NHWC with 16-byte stores, or channel-major (eps/image heads).
 #include "../../include/stedm_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace stedm;
@@ -27,6 +35,12 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;
 
+// STEDM_TC_CLUSTER=0 disables the 2-CTA weight multicast (A/B measurements, debugging)
+static bool g_tc_cluster_enabled = [] {
+  const char* e = getenv("STEDM_TC_CLUSTER");
+  return !(e && e[0] == '0');
+}();
+
 struct TcParams {
   const float* bias;
   const float* emb;
@@ -36,6 +50,8 @@ struct TcParams {
   int taps, ksize;
   int c0_blks, c_blks;  // 64-channel slabs in source 0 / in the concat
   int x1_batch;
+  int n_tiles;          // output-channel tiles
+  int num_work;         // cluster work items = ceil(m_tiles / CL) * n_tiles
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
 };
@@ -43,16 +59,18 @@ struct TcParams {
 template <int BN>
 struct TcCfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int ACC = 2;  // TMEM accumulator stages
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int ACC_COLS = BN;  // fp32 columns per accumulator
+  static constexpr int TMEM_COLS = (ACC * BN) < 32 ? 32 : ACC * BN;  // 32 / 128 / 256 / 512: powers of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;
+  static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
 };
 
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -61,11 +79,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;   // [ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const int num_kb = p.taps * p.c_blks;
 
   if (warp == 0 && elect_one()) {
@@ -74,9 +94,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);  // released by the MMA commit of every CTA whose smem the slab occupies
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < Cfg::ACC; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);  // every epilogue thread arrives
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -84,171 +107,229 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers must exist before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
-      const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
-      const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-        const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
-        int dy = 0, dx = 0;
-        if (p.ksize == 3) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
+      uint32_t it = 0;  // K-slab counter, runs across tiles
+      for (int work = cluster_id; work < p.num_work; work += num_clusters) {
+        const int n0 = (work % p.n_tiles) * BN;
+        const int m0 = ((work / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
+        const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
+        const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+          const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
+          int dy = 0, dx = 0;
+          if (p.ksize == 3) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          if (cb < p.c0_blks)
+            tma_load_4d(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
+          else
+            tma_load_4d(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
+          if (CL == 1) {
+            tma_load_2d(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0);
+          } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
+            constexpr int ROWS = BN / CL;
+            tma_load_2d_mcast(sa + Cfg::A_BYTES + cta_rank * (ROWS * TC_BK * 2), &map_w, &full_bar[s], kb * TC_BK,
+                              n0 + static_cast<int>(cta_rank) * ROWS, static_cast<uint16_t>((1u << CL) - 1));
+          }
         }
-        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-        if (cb < p.c0_blks)
-          tma_load_4d(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
-        else
-          tma_load_4d(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
-        tma_load_2d(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile = 0;
+      for (int work = cluster_id; work < p.num_work; work += num_clusters, ++tile) {
+        const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);  // frees the slab once these MMAs have read it
+          for (int k = 0; k < TC_BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          // frees the slab once these MMAs have read it — in every CTA that multicasts into it
+          if (CL == 1) umma_commit(&empty_bar[s]);
+          else umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1));
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       }
-      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
     }
   } else {
     // ===================================== epilogue =========================================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
     const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    const bool valid = m < p.M;
-    const int b = valid ? m / p.HW : 0;
-    const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
     constexpr int CH = BN < 32 ? 16 : 32;
+    uint32_t tile = 0;
+    for (int work = cluster_id; work < p.num_work; work += num_clusters, ++tile) {
+      const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
+      const int n_base = (work % p.n_tiles) * BN;
+      const int m = ((work / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM + row;
+      const bool valid = m < p.M;
+      const int b = valid ? m / p.HW : 0;
+      const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += CH) {
-      float v[CH];
-      if constexpr (CH == 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
-        tmem_ld_wait();
+      for (int c = 0; c < BN; c += CH) {
+        float v[CH];
+        if constexpr (CH == 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + c, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      } else {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      }
-      if (!valid) continue;
-      const int n = n0 + c;
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-        }
-      }
-      if (emb_row) {
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-        }
-      }
-      const size_t o = static_cast<size_t>(m) * p.cout + n;
-      if (p.residual) {
-        if (p.res_dtype == DT_BF16) {
-          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
-#pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            const uint4 u = rp[j / 8];
-            float2 f;
-            f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
-            f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
-            f = unpack_bf16x2(u.z); v[j + 4] += f.x; v[j + 5] += f.y;
-            f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         } else {
-          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o);
+          uint32_t r[16];
+          tmem_ld16(tmem_acc + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (!valid) continue;
+        const int n = n_base + c;
+        if (p.bias) {
 #pragma unroll
           for (int j = 0; j < CH; j += 4) {
-            const float4 t = rp[j / 4];
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
             v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
         }
-      }
-      if (p.out_nchw) {
-        // channel-major output (eps / image heads in fp32; V^T for the decoder attention in bf16): consecutive
-        // lanes = consecutive pixels -> coalesced per channel plane
-        const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
-        if (p.out_dtype == DT_F32) {
-          float* op = static_cast<float*>(p.out) + base;
+        if (emb_row) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+          for (int j = 0; j < CH; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+        }
+        const size_t o = static_cast<size_t>(m) * p.cout + n;
+        if (p.residual) {
+          if (p.res_dtype == DT_BF16) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              const uint4 u = rp[j / 8];
+              float2 f;
+              f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
+              f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
+              f = unpack_bf16x2(u.z); v[j + 4] += f.x; v[j + 5] += f.y;
+              f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
+            }
+          } else {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o);
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 t = rp[j / 4];
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          }
+        }
+        if (p.out_nchw) {
+          // channel-major output (eps / image heads in fp32; V^T for the decoder attention in bf16): consecutive
+          // lanes = consecutive pixels -> coalesced per channel plane
+          const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+          if (p.out_dtype == DT_F32) {
+            float* op = static_cast<float*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+          } else {
+            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + base;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+          }
+        } else if (p.out_dtype == DT_BF16) {
+          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(v[j], v[j + 1]);
+            u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            op[j / 8] = u;
+          }
         } else {
-          __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + base;
+          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+          for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
-      } else if (p.out_dtype == DT_BF16) {
-        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
-#pragma unroll
-        for (int j = 0; j < CH; j += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(v[j], v[j + 1]);
-          u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          op[j / 8] = u;
-        }
-      } else {
-        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while a peer can still write into it
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const TcParams& p,
-              cudaStream_t stream) {
+int tc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int CL>
+int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, TcParams p, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;  // per-process; the attribute is per-function and idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return ERR_CUDA;
     }
     configured = true;
   }
-  dim3 grid((p.M + TC_BM - 1) / TC_BM, p.cout / BN);
-  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(ma0, ma1, mw, p);
+  const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  const int m_groups = (m_tiles + CL - 1) / CL;  // an odd tile count gets one all-out-of-bounds tile (zero-filled loads, no stores)
+  p.num_work = m_groups * p.n_tiles;
+  const int max_clusters = tc_num_sms() * Cfg::MIN_BLOCKS / CL;   // persistent: one resident wave
+  const int clusters = p.num_work < max_clusters ? p.num_work : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters) * CL);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL>, ma0, ma1, mw, p);
+  if (e != cudaSuccess) {
+    set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
+    return ERR_CUDA;
+  }
   return check_launch("conv_tc");
 }
 
@@ -315,10 +396,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   }
   const int ctot = d->c0 + d->c1, taps = d->ksize * d->ksize;
   const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 16));
+  // weight multicast across a 2-CTA cluster for the wide tiles whenever there are at least two pixel tiles
+  const int cl = (bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(d->cout)};
     const uint64_t str[1] = {static_cast<uint64_t>(taps) * ctot * 2};
-    const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn / cl)};
     int rc = make_tmap_bf16(&mw, d->weight, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -328,13 +411,14 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.taps = taps; p.ksize = d->ksize;
   p.c0_blks = d->c0 / TC_BK; p.c_blks = ctot / TC_BK;
   p.x1_batch = x1b;
+  p.n_tiles = d->cout / bn;
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return launch_tc<256>(ma0, ma1, mw, p, s);
-    case 128: return launch_tc<128>(ma0, ma1, mw, p, s);
-    case 64: return launch_tc<64>(ma0, ma1, mw, p, s);
-    default: return launch_tc<16>(ma0, ma1, mw, p, s);
+    case 256: return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);
+    case 128: return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, p, s) : launch_tc<128, 1>(ma0, ma1, mw, p, s);
+    case 64: return launch_tc<64, 1>(ma0, ma1, mw, p, s);
+    default: return launch_tc<16, 1>(ma0, ma1, mw, p, s);
   }
 }
