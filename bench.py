@@ -158,7 +158,7 @@ def cpu_reference_sample(latent, n_style, sample_batch=1, sample_steps=1, sd=Non
                         f"steps (2 U-Net passes each) + VQ decode, loop time scaled x{DDIM_STEPS}/{sample_steps}"))
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -179,7 +179,7 @@ def run_reference_arm(args):
                              "sample": last["sample"]},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -208,8 +208,17 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the U-Net pass from a CUDA graph (small batches)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
 
     from stedm_b200 import ops
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -300,7 +309,7 @@ def main():
         cb = cpu_reference_sample(L, args.n_style, 1, 1)
         line["cpu_baseline"] = {"value": cb["value"], "unit": "images/s", "cores": cb["cores"], "kind": "port",
                                 "sample": cb["sample"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 def kernel_roofline(m, devb, B, L, args):
@@ -342,7 +351,8 @@ def kernel_roofline(m, devb, B, L, args):
         b.record()
         bsz, h, w, c0 = x0.shape
         c1 = 0 if kw.get("x1") is None else kw["x1"].shape[-1]
-        rec.append((a, b, 2.0 * bsz * h * w * cout * ksize * ksize * (c0 + c1), cout))
+        taps = 4 if kw.get("up_phase") is not None else ksize * ksize   # executed taps (folded upsample: 4, not 9)
+        rec.append((a, b, 2.0 * bsz * h * w * cout * taps * (c0 + c1), cout))
         return out
 
     ops.conv = timed_conv

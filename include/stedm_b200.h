@@ -96,6 +96,11 @@ typedef struct stedm_conv_desc {
   int32_t out_nchw;
   int32_t cout;        /* GEMM N = rows of `weight` (tensor-core path: padded to a multiple of 16) */
   int32_t cout_store;  /* NCHW output only: number of leading output channels actually stored (0 => cout) */
+  int32_t tap_mode;    /* tensor-core path: 0 = dense k x k taps; 1 = one 2x2 sub-pixel phase of "nearest x2 upsample
+                          then 3x3 conv" (K9 folded into the conv: 4 taps on the LOW-resolution input instead of 9 on
+                          the upsampled one): weight = bf16 [cout][4*c0] with taps (a,b) reading (y+a-1+py, x+b-1+px),
+                          `out` = NHWC [batch, 2*in_h, 2*in_w, cout] written at (2y+py, 2x+px) */
+  int32_t phase;       /* tap_mode 1: py*2 + px */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,

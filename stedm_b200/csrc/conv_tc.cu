@@ -54,6 +54,7 @@ struct TcParams {
   int num_work;         // cluster work items = ceil(m_tiles / CL) * n_tiles
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
+  int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
 };
 
 template <int BN>
@@ -127,7 +128,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
           const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
           int dy = 0, dx = 0;
-          if (p.ksize == 3) {
+          if (p.tap_mode == 1) {        // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
+            dy = (tap >> 1) - 1 + p.py;
+            dx = (tap & 1) - 1 + p.px;
+          } else if (p.ksize == 3) {
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
@@ -222,7 +226,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
         }
-        const size_t o = static_cast<size_t>(m) * p.cout + n;
+        size_t o = static_cast<size_t>(m) * p.cout + n;
+        if (p.tap_mode == 1) {  // this phase's pixel (y, x) lands at (2y + py, 2x + px) of the [B, 2H, 2W, C] output
+          const int pix = m - b * p.HW, y = pix / p.W, x = pix - y * p.W;
+          o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
+        }
         if (p.residual) {
           if (p.res_dtype == DT_BF16) {
             const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
@@ -343,6 +351,9 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(!d->out_nchw || (d->residual == nullptr && d->cout_store >= 0 && d->cout_store <= d->cout),
                 "conv_tc: NCHW output takes no residual and needs cout_store <= cout");
   STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
+  STEDM_REQUIRE(d->tap_mode == 0 || (d->tap_mode == 1 && d->phase >= 0 && d->phase < 4 && d->residual == nullptr &&
+                                     d->out_nchw == 0 && d->c1 == 0),
+                "conv_tc: sub-pixel phase convolution takes one source, no residual, NHWC output, phase in [0,4)");
   STEDM_REQUIRE(d->c0 > 0 && d->c0 % TC_BK == 0 && d->c1 % TC_BK == 0 && (d->c1 == 0 || d->x1),
                 "conv_tc: channel counts must be multiples of 64 (%d, %d)", d->c0, d->c1);
   STEDM_REQUIRE(d->cout >= 16 && d->cout % 16 == 0, "conv_tc: cout %d must be a multiple of 16", d->cout);
@@ -394,7 +405,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   } else {
     ma1 = ma0;
   }
-  const int ctot = d->c0 + d->c1, taps = d->ksize * d->ksize;
+  const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
   const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 16));
   // weight multicast across a 2-CTA cluster for the wide tiles whenever there are at least two pixel tiles
   const int cl = (bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
@@ -414,6 +425,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.n_tiles = d->cout / bn;
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
+  p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);

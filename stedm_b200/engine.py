@@ -41,7 +41,8 @@ class PackedConv:
       SIMT:        fp32 [kh*kw*Cin_pad][Cout]
     ``cin_split`` = (c0, c1) when the input is a two-source concat (each part padded separately)."""
 
-    def __init__(self, weight, bias, prec, *, stride=1, force_simt=False, cin_split=None, cout_pad=None):
+    def __init__(self, weight, bias, prec, *, stride=1, force_simt=False, cin_split=None, cout_pad=None,
+                 fold_upsample=False):
         w = weight.detach()
         if w.dim() == 3:  # Conv1d k=1
             w = w[:, :, :, None]
@@ -74,6 +75,22 @@ class PackedConv:
                     b = torch.nn.functional.pad(b, (0, cp - cout))
                 self.cout = cp
             self.weight = w.reshape(self.cout, -1).to(torch.bfloat16).contiguous()
+            self.phase_weights = None
+            if fold_upsample:
+                # nearest-x2 upsample followed by a 3x3 conv == four 2x2 convs on the low-resolution input, one per
+                # output sub-pixel phase (py, px): rows/cols of the 3x3 kernel that read the same source pixel are
+                # summed (in fp32, before the bf16 rounding): py=0 -> {-1: w0, 0: w1+w2}, py=1 -> {0: w0+w1, +1: w2}
+                assert kh == 3 and len(parts) == 1
+                groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+                self.phase_weights = []
+                for py in (0, 1):
+                    for px in (0, 1):
+                        taps = []
+                        for ra in groups[py]:
+                            for cb in groups[px]:
+                                taps.append(sum(w[:, r, c, :] for r in ra for c in cb))      # [Cout, Cin]
+                        wp = torch.stack(taps, dim=1)                                          # [Cout, 4, Cin]
+                        self.phase_weights.append(wp.reshape(self.cout, -1).to(torch.bfloat16).contiguous())
         else:
             if cout_pad and cout_pad != cout:
                 w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, cout_pad - cout))
@@ -92,6 +109,14 @@ class PackedConv:
                 cols = ops.im2col_3x3_s2(x0)            # [B, H/2, W/2, 9*C]: Downsample as a plain GEMM
                 return ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
                                 out_dtype=out_dtype, tensor_core=True)
+            if upsample and self.phase_weights is not None:
+                assert x1 is None and emb is None and residual is None and not out_nchw
+                b, h, w_, _ = x0.shape
+                out = torch.empty((b, 2 * h, 2 * w_, self.cout), device=x0.device, dtype=out_dtype)
+                for ph, wp in enumerate(self.phase_weights):
+                    ops.conv(x0, wp, self.bias, self.cout, 3, out_dtype=out_dtype, tensor_core=True, out=out,
+                             up_phase=ph)
+                return out
             if upsample:
                 assert x1 is None
                 x0 = ops.upsample_nearest2x(x0)
@@ -220,7 +245,7 @@ class UNetRunner:
             up = None
             if len(blk) > 1:
                 conv = blk[1].conv
-                up = PackedConv(conv.weight, conv.bias, prec)
+                up = PackedConv(conv.weight, conv.bias, prec, fold_upsample=True)
             self.dec.append((rb, ("out", i), up))
         self.out_norm = PackedNorm(unet.out[0], 1e-5)
         self.n_norms += 1
@@ -353,7 +378,7 @@ class DecoderRunner:
             blocks = [res(b) for b in up.block]
             upc = None
             if hasattr(up, "upsample"):
-                upc = PackedConv(up.upsample.conv.weight, up.upsample.conv.bias, prec)
+                upc = PackedConv(up.upsample.conv.weight, up.upsample.conv.bias, prec, fold_upsample=True)
             self.levels.append((blocks, upc))
         self.norm_out = PackedNorm(d.norm_out, 1e-6)
         self.n_norms += 1

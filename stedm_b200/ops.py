@@ -111,7 +111,7 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
     _cuda(x0, x1, weight, bias, residual)
@@ -120,7 +120,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     b, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     out_dtype = out_dtype or x0.dtype
-    uh, uw = (2 * h, 2 * w) if upsample else (h, w)
+    uh, uw = (2 * h, 2 * w) if (upsample or up_phase is not None) else (h, w)
     oh, ow = uh // stride, uw // stride
     if out is None:
         shape = (b, cout_store or cout, oh, ow) if out_nchw else (b, oh, ow, cout)
@@ -136,8 +136,10 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.res_dtype = F32 if residual is None else _DT[residual.dtype]
     d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
     d.cout_store = cout_store if out_nchw else 0
+    d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
     if tensor_core:
-        assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ksize * ksize * (c0 + c1), \
+        ntaps = 4 if up_phase is not None else ksize * ksize
+        assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ntaps * (c0 + c1), \
             (weight.shape, cout, ksize, c0, c1)
         _call("stedm_conv_tc", C.byref(d), _stream())
     else:

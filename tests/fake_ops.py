@@ -65,9 +65,16 @@ def im2col_3x3_s2(x):
 
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
+    if up_phase is not None:   # one 2x2 sub-pixel phase: taps (a,b) read (y+a-1+py, x+b-1+px); write (2y+py, 2x+px)
+        py, px = up_phase >> 1, up_phase & 1
+        w = weight.float().reshape(cout, 2, 2, cin).permute(0, 3, 1, 2)
+        xin = F.pad(_nchw(x.float()), (1 - px, px, 1 - py, py))
+        y = F.conv2d(xin, w, bias)
+        out[:, py::2, px::2, :] = _nhwc(y).to(out.dtype)
+        return out
     if tensor_core:   # [Cout][k*k*Cin]
         w = weight.float().reshape(cout, ksize, ksize, cin).permute(0, 3, 1, 2)
     else:             # [k*k*Cin][Cout]

@@ -153,3 +153,20 @@ def test_softmax_rows_scaled_bf16(ops):
     y = x.cuda()
     ops.softmax_rows(y, 0.25)
     assert max_abs(y.cpu(), want) < 1e-6
+
+
+def test_conv_tc_folded_upsample(ops):
+    """nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel phase convs on the low-resolution input
+    (openaimodel.py:123-132 / model.py:53-57) against F.interpolate + conv2d."""
+    from stedm_b200.engine import PackedConv, Precision
+    g = torch.Generator().manual_seed(21)
+    B, c, co, hw = 2, 128, 256, 16
+    x = bf(torch.randn(B, c, hw, hw, generator=g))
+    w = torch.randn(co, c, 3, 3, generator=g) / math.sqrt(9 * c)
+    b = torch.randn(co, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    pc = PackedConv(w.cuda(), b.cuda(), Precision("bf16"), fold_upsample=True)
+    got = pc(nhwc(x).to(torch.bfloat16).cuda(), upsample=True, out_dtype=torch.float32)
+    assert tuple(got.shape) == (B, 2 * hw, 2 * hw, co)
+    # the phase weights are sums of fp32 taps rounded once to bf16 (not sums of bf16-rounded taps): ~1e-2 abs
+    assert max_abs(nchw(got.cpu()), want) < 3e-2
