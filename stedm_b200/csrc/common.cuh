@@ -35,7 +35,15 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// Fast SiLU for the bf16 path: x*sigmoid(x) = h*tanh(h) + h with h = x/2 — one MUFU (tanh.approx, rel. error ~2^-11,
+// below the 2^-9 of the bf16 result it feeds) and two FMA-pipe ops, instead of exp + IEEE division (~30 instructions),
+// which made the GroupNorm apply kernel issue-bound rather than HBM-bound.
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // exact-ish SiLU for the fp32 parity mode (expf, true division)
 __device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
 

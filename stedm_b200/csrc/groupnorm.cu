@@ -8,6 +8,8 @@
 // owns one sample and a slice of its pixels; thread -> (pixel lane, channel item) so that a warp touches
 // consecutive 16 B items of the same pixel rows (fully coalesced).
 #include "../../include/stedm_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace stedm;
@@ -16,6 +18,7 @@ namespace {
 
 constexpr int GN_GROUPS = 32;
 constexpr int GN_THREADS = 256;
+constexpr int GN_MLP = 4;  // independent loads in flight per thread
 
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
@@ -82,10 +85,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-#pragma unroll 4
-      for (int p = p_begin + lane; p < p_end; p += lanes) {  // independent 16 B loads: unrolled for MLP
+      const T* src = item_ptr<T>(x0, x1, b, b1, 0, hw, c0, c1, item);
+      const size_t stride = (item * 8 < c0) ? c0 : c1;
+      // batches of GN_MLP independent 16/32-byte loads are issued before any is consumed (memory-level parallelism)
+      int p = p_begin + lane;
+      for (; p + (GN_MLP - 1) * lanes < p_end; p += GN_MLP * lanes) {
+        float v[GN_MLP][8];
+#pragma unroll
+        for (int u = 0; u < GN_MLP; ++u) load8<T>(src + static_cast<size_t>(p + u * lanes) * stride, v[u]);
+#pragma unroll
+        for (int u = 0; u < GN_MLP; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += v[u][j];
+            q[j] += v[u][j] * v[u][j];
+          }
+      }
+      for (; p < p_end; p += lanes) {
         float v[8];
-        load8<T>(item_ptr<T>(x0, x1, b, b1, p, hw, c0, c1, item), v);
+        load8<T>(src + static_cast<size_t>(p) * stride, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j] += v[j];
@@ -100,14 +118,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
     }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * GN_GROUPS) {
-    const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
+  {
+    // 64 outputs (32 groups x {sum, sumsq}), 4 threads each: fixed strided partition + fixed shuffle tree =
+    // deterministic, and 4x shorter than one thread per output
+    const int o = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const int g = o % GN_GROUPS, which = o / GN_GROUPS;
     const int cpg = C / GN_GROUPS;
-    const float* src = which ? s_sq : s_sum;
+    const float* src = (which ? s_sq : s_sum) + g * cpg;
     double acc = 0.0;
-    for (int l = 0; l < lanes; ++l)
-      for (int c = 0; c < cpg; ++c) acc += static_cast<double>(src[l * C + g * cpg + c]);
-    partials[((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * GN_GROUPS + g) * 2 + which] = acc;
+    const int n = lanes * cpg;
+    for (int i = sub; i < n; i += 4) {
+      const int l = i / cpg, c = i - l * cpg;
+      acc += static_cast<double>(src[l * C + c]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0) partials[((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * GN_GROUPS + g) * 2 + which] = acc;
   }
 }
 
@@ -123,11 +149,17 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
   __shared__ float s_mr[2 * GN_GROUPS];  // per group: mean, rstd
   const int C = c0 + c1, items = C / 8, cpg = C / GN_GROUPS;
   const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
-  if (threadIdx.x < 2 * GN_GROUPS) {
-    const double* src = partials + static_cast<size_t>(b) * n_chunks * GN_GROUPS * 2 + threadIdx.x;
+  {
+    // fold the per-chunk partials: 64 outputs x 4 threads, fixed strided partition + fixed shuffle tree
+    // (deterministic); the loads of one thread are independent, so they are issued in batches
+    const int o = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const double* src = partials + static_cast<size_t>(b) * n_chunks * GN_GROUPS * 2 + o;
     double acc = 0.0;
-    for (int k = 0; k < n_chunks; ++k) acc += src[static_cast<size_t>(k) * GN_GROUPS * 2];  // fixed order
-    s_tot[threadIdx.x] = acc;  // index = g*2 + which
+#pragma unroll 8
+    for (int k = sub; k < n_chunks; k += 4) acc += src[static_cast<size_t>(k) * GN_GROUPS * 2];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0) s_tot[o] = acc;  // index = g*2 + which
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {  // the only double-precision sqrt/div: 32 per block
@@ -146,27 +178,56 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
     s_ab[C + c] = beta[c] - s_mr[g * 2] * a;
   }
   __syncthreads();
+  // thread -> (pixel lane, channel item): no integer division in the streaming loop, the item's scale/shift
+  // live in registers, and the unrolled pixel loop keeps several independent 16 B loads in flight per thread
   const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
-  const size_t total = static_cast<size_t>(p_end - p_begin) * items;
-#pragma unroll 4
-  for (size_t i = threadIdx.x; i < total; i += GN_THREADS) {
-    const int item = static_cast<int>(i % items);
-    const size_t p = p_begin + i / items;
-    float v[8];
-    load8<TI>(item_ptr<TI>(x0, x1, b, b1, p, hw, c0, c1, item), v);
+  const int tpi = min(items, GN_THREADS), lanes = GN_THREADS / tpi;
+  const int lane = threadIdx.x / tpi, it0 = threadIdx.x % tpi;
+  if (lane >= lanes) return;
+  for (int item = it0; item < items; item += tpi) {
+    float a[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = v[j] * s_ab[item * 8 + j] + s_ab[C + item * 8 + j];
-      if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
-      v[j] = y;
+      a[j] = s_ab[item * 8 + j];
+      sh[j] = s_ab[C + item * 8 + j];
     }
-    store8<TO>(out + (static_cast<size_t>(b) * hw + p) * C + item * 8, v);
+    const TI* src = item_ptr<TI>(x0, x1, b, b1, 0, hw, c0, c1, item);
+    const size_t src_stride = (item * 8 < c0) ? c0 : c1;
+    TO* dst = out + static_cast<size_t>(b) * hw * C + item * 8;
+    int p = p_begin + lane;
+    for (; p + (GN_MLP - 1) * lanes < p_end; p += GN_MLP * lanes) {
+      float v[GN_MLP][8];
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u) load8<TI>(src + static_cast<size_t>(p + u * lanes) * src_stride, v[u]);
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = v[u][j] * a[j] + sh[j];
+          if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
+          v[u][j] = y;
+        }
+        store8<TO>(dst + static_cast<size_t>(p + u * lanes) * C, v[u]);
+      }
+    }
+    for (; p < p_end; p += lanes) {
+      float v[8];
+      load8<TI>(src + static_cast<size_t>(p) * src_stride, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = v[j] * a[j] + sh[j];
+        if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
+        v[j] = y;
+      }
+      store8<TO>(dst + static_cast<size_t>(p) * C, v);
+    }
   }
 }
 
 // Pixel range per statistics block: a function of (hw, C) ONLY (never of the batch), at most 128 chunks per sample.
 int stats_pix_per_block(int hw, int C) {
-  const int by_bytes = max(4, 65536 / C);  // ~128 KB of bf16 per block
+  static const int kStatsBytes = [] { const char* e = getenv("STEDM_GN_STATS_ELEMS"); return e ? atoi(e) : 65536; }();
+  const int by_bytes = max(2, kStatsBytes / C);  // elements per block (~128 KB of bf16 by default)
   const int by_count = (hw + 127) / 128;
   return min(hw, max(by_bytes, by_count));
 }
@@ -174,7 +235,8 @@ int stats_pix_per_block(int hw, int C) {
 int apply_pix_per_block(int batch, int hw, int C) {
   // >= 64 KB of input per block (amortises the per-block scale/shift prologue) unless that leaves the GPU short of
   // ~4 blocks per SM, then smaller down to 8 KB
-  int ppb = max(1, 32768 / C);
+  static const int kApplyElems = [] { const char* e = getenv("STEDM_GN_APPLY_ELEMS"); return e ? atoi(e) : 32768; }();
+  int ppb = max(1, kApplyElems / C);
   const long long blocks = static_cast<long long>(batch) * ((hw + ppb - 1) / ppb);
   if (blocks < 148 * 4) {
     const int blocks_per_sample = max(1, (148 * 4 + batch - 1) / batch);
