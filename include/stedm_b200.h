@@ -64,9 +64,18 @@ int stedm_cfg_ddim_step(const float* e_c, const float* e_u, const float* x, cons
 int stedm_gn_num_chunks(int hw, int channels);
 int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
                    double* partials, void* stream);
+/* n_chunks: number of chunks in `partials` (0 => stedm_gn_num_chunks(hw, c0+c1), the layout stedm_gn_stats writes;
+ * 1 => the folded layout stedm_gn_fold_tiles writes). */
 int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
-                   const double* partials, const float* gamma, const float* beta, float eps, int apply_silu, void* out,
-                   int out_dtype, void* stream);
+                   const double* partials, int n_chunks, const float* gamma, const float* beta, float eps,
+                   int apply_silu, void* out, int out_dtype, void* stream);
+/* Statistics pass folded into the producing convolutions: reduce the per-(128-pixel tile, channel) sums written by
+ * stedm_conv_tc (stedm_conv_desc.stats_out) for the one or two producers of a GroupNorm input into
+ * out = double [batch][1][32][2].  Source s: fp32 [reps_s][rep_stride_s tiles][c_s][2]; sample b owns tile rows
+ * (b % batch_s)*tps_s + j, j < tps_s, in each of the reps_s repetitions (4 for the sub-pixel upsample phases). */
+int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long long rep_stride0, int tps0, int batch0,
+                        const float* tiles1, int c1, int reps1, long long rep_stride1, int tps1, int batch1, int batch,
+                        double* out, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * K1/K2/K3/K4/K9/K10  Convolution as implicit GEMM, M = B*Ho*Wo pixels, N = Cout, K = k*k*(c0+c1).
@@ -83,6 +92,9 @@ typedef struct stedm_conv_desc {
   const float* emb;    /* per-sample additive vector emb[b*emb_stride + n], or NULL */
   const void* residual;/* NHWC [batch, out_h, out_w, cout] added in the epilogue, or NULL */
   void* out;           /* NHWC [batch, out_h, out_w, cout], or NCHW when out_nchw != 0 */
+  float* stats_out;    /* tensor-core path, optional: fp32 [tiles][cout][2] = per-(128-pixel tile, channel) sum and sum
+                          of squares of the values written (tiles = batch*in_h*in_w/128, x4 phases in tap_mode 1):
+                          the GroupNorm statistics pass folded into the producer; consumed by stedm_gn_fold_tiles */
   int32_t c0, c1;
   int32_t in_dtype;    /* dtype of x0/x1 */
   int32_t batch, in_h, in_w;

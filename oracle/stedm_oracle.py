@@ -61,7 +61,7 @@ def ddim_tables(S, eta=0.0, T=1000, linear_start=0.0015, linear_end=0.0205):
 def timestep_embedding(t, dim, max_period=10000):
     """[cos | sin] sinusoid, util.py:151-171."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 

@@ -155,6 +155,27 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem, const CUtensorMap*
       : "memory");
 }
 
+// Named barrier among a subset of the CTA's warps (id 0 is __syncthreads' barrier).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Column sums across the 32 lanes of a warp of a 32-value-per-lane array by recursive halving: 31 shuffles
+// instead of 32 x 5; afterwards lane L holds in v[0] the sum over all lanes of the original v[L].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // ---- PTX: thread-block clusters ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

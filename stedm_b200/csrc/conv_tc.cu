@@ -55,6 +55,8 @@ struct TcParams {
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
+  float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
+  int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
 
 template <int BN>
@@ -67,7 +69,8 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
   static constexpr int ACC_COLS = BN;  // fp32 columns per accumulator
   static constexpr int TMEM_COLS = (ACC * BN) < 32 ? 32 : ACC * BN;  // 32 / 128 / 256 / 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STATS_BYTES = 4 * BN * 2 * 4;  // [4 epilogue warps][BN][sum, sumsq] fp32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES;
   static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
 };
 
@@ -83,6 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;   // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -210,8 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        if (!valid) continue;
         const int n = n_base + c;
+        if (valid) {
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < CH; j += 4) {
@@ -283,10 +287,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
+        }  // valid
+        if constexpr (CH == 32) {
+          if (p.stats_out != nullptr) {
+            // GroupNorm statistics of the tensor being written (K7's statistics pass folded into its producer):
+            // per-channel sum and sum of squares over this warp's 32 pixel rows; lane L ends up with channel c + L
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = valid ? v[j] : 0.f;
+              sq[j] = v[j] * v[j];
+            }
+            const float cs = warp_transpose_reduce32(v, lane);
+            const float cq = warp_transpose_reduce32(sq, lane);
+            *reinterpret_cast<float2*>(&s_stats[((quad * BN) + c + lane) * 2]) = make_float2(cs, cq);
+          }
+        }
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (CH == 32) {
+        if (p.stats_out != nullptr) {
+          // fold the four warps' partials in a fixed order and publish this tile's per-channel statistics
+          named_bar_sync(1, 128);
+          const int m_tile = (work / p.n_tiles) * CL + static_cast<int>(cta_rank);
+          if (m_tile * TC_BM < p.M) {
+            float* dst = p.stats_out + (static_cast<size_t>(p.stats_tile_base + m_tile) * p.cout + n_base) * 2;
+            for (int ch = threadIdx.x - 64; ch < BN; ch += 128) {
+              float a = 0.f, b2 = 0.f;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const float2 t = *reinterpret_cast<const float2*>(&s_stats[((w * BN) + ch) * 2]);
+                a += t.x;
+                b2 += t.y;
+              }
+              *reinterpret_cast<float2*>(dst + ch * 2) = make_float2(a, b2);
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -426,6 +467,14 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
+  p.stats_out = nullptr; p.stats_tile_base = 0;
+  if (d->stats_out != nullptr) {
+    STEDM_REQUIRE(bn >= 64 && d->out_nchw == 0 && (H * W) % TC_BM == 0,
+                  "conv_tc: fused GroupNorm statistics need cout %% 64 == 0, NHWC output and H*W %% 128 == 0");
+    const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
+    p.stats_out = d->stats_out;
+    p.stats_tile_base = d->tap_mode == 1 ? d->phase * m_tiles : 0;
+  }
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);

@@ -232,6 +232,39 @@ int stats_pix_per_block(int hw, int C) {
   return min(hw, max(by_bytes, by_count));
 }
 
+// Fold the per-(128-pixel tile, channel) statistics that stedm_conv_tc's epilogue wrote for the producer(s) of a
+// GroupNorm input into the per-sample, per-group (sum, sumsq) the apply kernel consumes — the statistics pass over
+// the activation itself disappears.  One block per sample; 64 outputs x 4 threads, fixed partition + fixed shuffle
+// tree in double precision (deterministic, independent of the batch).
+struct FoldSrc {
+  const float* tiles;   // [reps][rep_stride tiles][c][2]
+  int c, reps, tps, batch;
+  long long rep_stride;  // in tiles
+};
+
+__global__ void __launch_bounds__(256) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int C = s0.c + s1.c, cpg = C / GN_GROUPS;
+  const int o = threadIdx.x >> 2, sub = threadIdx.x & 3;
+  const int g = o >> 1, which = o & 1;
+  double acc = 0.0;
+  int k = 0;  // running index over (channel in group, rep, tile): strided partition over the 4 sub-threads
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int ch = g * cpg + cc;
+    const FoldSrc& s = (ch < s0.c) ? s0 : s1;
+    const int lc = (ch < s0.c) ? ch : ch - s0.c;
+    const int bs = b % s.batch;
+    for (int r = 0; r < s.reps; ++r) {
+      const float* base = s.tiles + ((static_cast<size_t>(r) * s.rep_stride + static_cast<size_t>(bs) * s.tps) * s.c + lc) * 2 + which;
+      for (int j = 0; j < s.tps; ++j, ++k)
+        if ((k & 3) == sub) acc += static_cast<double>(base[static_cast<size_t>(j) * s.c * 2]);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (sub == 0) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which] = acc;
+}
+
 int apply_pix_per_block(int batch, int hw, int C) {
   // >= 64 KB of input per block (amortises the per-block scale/shift prologue) unless that leaves the GPU short of
   // ~4 blocks per SM, then smaller down to 8 KB
@@ -275,15 +308,28 @@ extern "C" int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int 
   return check_launch("gn_stats");
 }
 
+extern "C" int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long long rep_stride0, int tps0, int batch0,
+                                   const float* tiles1, int c1, int reps1, long long rep_stride1, int tps1, int batch1,
+                                   int batch, double* out, void* stream) {
+  STEDM_REQUIRE(tiles0 && out && (c1 == 0 || tiles1), "gn_fold_tiles: null pointer");
+  STEDM_REQUIRE(batch > 0 && c0 > 0 && (c0 + c1) % GN_GROUPS == 0 && reps0 > 0 && tps0 > 0 && batch0 > 0 &&
+                    (c1 == 0 || (reps1 > 0 && tps1 > 0 && batch1 > 0)),
+                "gn_fold_tiles: bad shape");
+  FoldSrc s0{tiles0, c0, reps0, tps0, batch0, rep_stride0};
+  FoldSrc s1{tiles1, c1, c1 ? reps1 : 1, c1 ? tps1 : 1, c1 ? batch1 : 1, rep_stride1};
+  gn_fold_tiles_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(s0, s1, out);
+  return check_launch("gn_fold_tiles");
+}
+
 extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0,
-                              int c1, const double* partials, const float* gamma, const float* beta, float eps,
-                              int apply_silu, void* out, int out_dtype, void* stream) {
+                              int c1, const double* partials, int n_chunks_in, const float* gamma, const float* beta,
+                              float eps, int apply_silu, void* out, int out_dtype, void* stream) {
   const int C = c0 + c1;
   STEDM_REQUIRE(x0 && partials && gamma && beta && out && (c1 == 0 || x1), "gn_apply: null pointer");
   STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0 && C <= 4096,
                 "gn_apply: bad channel counts (%d + %d)", c0, c1);
   const int sppb = stats_pix_per_block(hw, C);
-  const int n_chunks = (hw + sppb - 1) / sppb;
+  const int n_chunks = n_chunks_in > 0 ? n_chunks_in : (hw + sppb - 1) / sppb;
   const int ppb = apply_pix_per_block(batch, hw, C);
   dim3 grid((hw + ppb - 1) / ppb, batch);
   const size_t smem = static_cast<size_t>(2) * C * sizeof(float);

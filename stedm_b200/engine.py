@@ -101,28 +101,47 @@ class PackedConv:
         self.bias = None if b is None else b.contiguous()
         self.prec = prec
 
-    def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False):
+    def _tile_stats(self, x, want, reps=1):
+        """Buffer for the GroupNorm statistics the epilogue folds into this convolution (None if not wanted or the
+        128-pixel tiles would straddle samples).  x = the tensor whose pixels index the GEMM rows."""
+        b, h, w_, _ = x.shape
+        if not want or (h * w_) % 128 != 0 or self.cout % 64 != 0:
+            return None, None
+        m_tiles = b * h * w_ // 128
+        tiles = torch.empty((reps * m_tiles, self.cout, 2), device=x.device, dtype=torch.float32)
+        return tiles, (tiles, self.cout, reps, m_tiles, h * w_ // 128, b)
+
+    def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False,
+                 want_stats=False):
         out_dtype = out_dtype or self.prec.act
         if self.tc:
             if self.stride == 2:
                 assert x1 is None and self.ksize == 3
                 cols = ops.im2col_3x3_s2(x0)            # [B, H/2, W/2, 9*C]: Downsample as a plain GEMM
-                return ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
-                                out_dtype=out_dtype, tensor_core=True)
+                tiles, meta = self._tile_stats(cols, want_stats)
+                out = ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
+                               out_dtype=out_dtype, tensor_core=True, stats_out=tiles)
+                out._gn_tiles = meta
+                return out
             if upsample and self.phase_weights is not None:
                 assert x1 is None and emb is None and residual is None and not out_nchw
                 b, h, w_, _ = x0.shape
                 out = torch.empty((b, 2 * h, 2 * w_, self.cout), device=x0.device, dtype=out_dtype)
+                tiles, meta = self._tile_stats(x0, want_stats, reps=4)
                 for ph, wp in enumerate(self.phase_weights):
                     ops.conv(x0, wp, self.bias, self.cout, 3, out_dtype=out_dtype, tensor_core=True, out=out,
-                             up_phase=ph)
+                             up_phase=ph, stats_out=tiles)
+                out._gn_tiles = meta
                 return out
             if upsample:
                 assert x1 is None
                 x0 = ops.upsample_nearest2x(x0)
-            return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
-                            out_dtype=out_dtype, tensor_core=True, out_nchw=out_nchw,
-                            cout_store=self.cout_real if out_nchw else 0)
+            tiles, meta = self._tile_stats(x0, want_stats and not out_nchw)
+            out = ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
+                           out_dtype=out_dtype, tensor_core=True, out_nchw=out_nchw,
+                           cout_store=self.cout_real if out_nchw else 0, stats_out=tiles)
+            out._gn_tiles = meta
+            return out
         return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
                         out_dtype=out_dtype, stride=self.stride, upsample=upsample, out_nchw=out_nchw,
                         tensor_core=False)
@@ -135,6 +154,12 @@ class PackedNorm:
         self.eps = eps
 
     def __call__(self, x0, x1, silu, out_dtype, stats):
+        t0 = getattr(x0, "_gn_tiles", None)
+        t1 = getattr(x1, "_gn_tiles", None) if x1 is not None else None
+        if t0 is not None and (x1 is None or t1 is not None):
+            # statistics were produced by the epilogues of the convolutions that wrote x0 / x1: fold them per sample
+            folded = ops.gn_fold_tiles(t0, t1, x0.shape[0])
+            return ops.gn_apply(x0, x1, folded, self.gamma, self.beta, self.eps, silu, out_dtype, n_chunks=1)
         stats = ops.gn_stats(x0, x1, stats)
         return ops.gn_apply(x0, x1, stats, self.gamma, self.beta, self.eps, silu, out_dtype)
 
@@ -162,14 +187,14 @@ class PackedResBlock:
 
     def __call__(self, x0, x1, emb, pool):
         a = self.n1(x0, x1, True, self.prec.act, pool.next())
-        h = self.c1(a, emb=emb)
+        h = self.c1(a, emb=emb, want_stats=True)
         a = self.n2(h, None, True, self.prec.act, pool.next())
         if self.skip is not None:
             xs = self.skip(x0, x1)
         else:
             assert x1 is None
             xs = x0
-        return self.c2(a, residual=xs)
+        return self.c2(a, residual=xs, want_stats=True)
 
 
 class UNetRunner:
@@ -285,15 +310,17 @@ class UNetRunner:
         hs = []
         for entry in self.enc:
             if entry[0] == "stem":
-                h = self.stem(h)
+                h = self.stem(h, want_stats=True)
             elif entry[0] == "down":
-                h = entry[1](h)
+                h = entry[1](h, want_stats=True)
             else:
                 h = entry[1](h, None, self._emb_view(emb_all, entry[2]), pool)
             hs.append(h)
         h = self.mid0(h, None, self._emb_view(emb_all, ("mid", 0)), pool)
         if G > 1:
+            tiles = getattr(h, "_gn_tiles", None)
             h = torch.cat([h] * G, 0)
+            h._gn_tiles = tiles                 # sample b of the copy owns the tile rows of sample b % B
             emb_all = torch.cat([emb_all] * G, 0)
         h = self.mid1(h, None, emb_style, pool)
         h = self._attention(h, pool)
@@ -301,7 +328,7 @@ class UNetRunner:
         for rb, key, up in self.dec:
             h = rb(h, hs.pop(), self._emb_view(emb_all, key), pool)
             if up is not None:
-                h = up(h, upsample=True)
+                h = up(h, upsample=True, want_stats=True)
         a = self.out_norm(h, None, True, prec.act, pool.next())
         return self.head(a, out_dtype=torch.float32, out_nchw=True)
 
@@ -331,7 +358,7 @@ class UNetRunner:
                                  q_off=0, k_off=ch, v_off=2 * ch)
         else:
             o = ops.attention_simt(qkv, qkv, qkv, self.heads, ch, T, 0, ch, 2 * ch, 3 * Cc, 3 * ch, scale, prec.act)
-        return self.att_proj(o.view(B, H, W, Cc), residual=x)
+        return self.att_proj(o.view(B, H, W, Cc), residual=x, want_stats=True)
 
 
 class DecoderRunner:
@@ -393,7 +420,7 @@ class DecoderRunner:
         pool = StatsPool(self.n_norms, B, z.device)
         zin = ops.pack_nchw_to_nhwc(z, None, self.post_quant.cin_pad, torch.float32)
         h = self.post_quant(zin, out_dtype=prec.act)
-        h = self.conv_in(h)
+        h = self.conv_in(h, want_stats=True)
         h = self.mid1(h, None, None, pool)
         h = self._attention(h, pool)
         h = self.mid2(h, None, None, pool)
@@ -401,7 +428,7 @@ class DecoderRunner:
             for rb in blocks:
                 h = rb(h, None, None, pool)
             if upc is not None:
-                h = upc(h, upsample=True)
+                h = upc(h, upsample=True, want_stats=True)
         a = self.norm_out(h, None, True, prec.act, pool.next())
         return self.conv_out(a, out_dtype=torch.float32, out_nchw=True)
 
@@ -436,4 +463,4 @@ class DecoderRunner:
                 q = qkv[s:s + chunk]
                 outs.append(ops.attention_simt(q, q, q, 1, Cc, T, 0, Cc, 2 * Cc, 3 * Cc, Cc, scale, prec.act))
             o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-        return self.att_proj(o.view(B, H, W, Cc), residual=x)
+        return self.att_proj(o.view(B, H, W, Cc), residual=x, want_stats=True)

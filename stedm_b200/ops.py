@@ -92,13 +92,27 @@ def gn_stats(x0, x1, stats=None):
     return stats
 
 
-def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype):
+def gn_fold_tiles(src0, src1, batch, out=None):
+    """Fold the per-tile statistics written by the producing convolutions (conv(..., stats_out=...)) into the
+    per-sample GroupNorm partials [batch, 1, 32, 2] (double).  src = (tiles fp32 [reps*rep_stride, c, 2], c, reps,
+    rep_stride, tiles_per_sample, batch_of_source); src1 = None for a single-source input."""
+    if out is None:
+        out = torch.empty((batch, 1, 32, 2), device=src0[0].device, dtype=torch.float64)
+    t1, c1, r1, rs1, tps1, b1 = src1 if src1 is not None else (None, 0, 1, 0, 1, 1)
+    t0, c0, r0, rs0, tps0, b0 = src0
+    _cuda(t0, t1, out)
+    _call("stedm_gn_fold_tiles", _ptr(t0), c0, r0, rs0, tps0, b0, _ptr(t1), c1, r1, rs1, tps1, b1, batch, _ptr(out),
+          _stream())
+    return out
+
+
+def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
     _cuda(x0, x1, stats, gamma, beta)
     b, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     x1b = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]
     out = torch.empty((b, h, w, c0 + c1), device=x0.device, dtype=out_dtype)
-    _call("stedm_gn_apply", _ptr(x0), _ptr(x1), _DT[x0.dtype], b, x1b, h * w, c0, c1, _ptr(stats), _ptr(gamma),
+    _call("stedm_gn_apply", _ptr(x0), _ptr(x1), _DT[x0.dtype], b, x1b, h * w, c0, c1, _ptr(stats), n_chunks, _ptr(gamma),
           _ptr(beta), float(eps), 1 if silu else 0, _ptr(out), _DT[out_dtype], _stream())
     return out
 
@@ -111,7 +125,7 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
     _cuda(x0, x1, weight, bias, residual)
@@ -128,6 +142,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d = ConvDesc()
     d.x0, d.x1, d.weight, d.bias = _ptr(x0), _ptr(x1), _ptr(weight), _ptr(bias)
     d.emb, d.residual, d.out = _ptr(emb), _ptr(residual), _ptr(out)
+    d.stats_out = _ptr(stats_out)
     d.c0, d.c1, d.in_dtype = c0, c1, _DT[x0.dtype]
     d.batch, d.in_h, d.in_w = b, h, w
     d.x1_batch = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]

@@ -48,7 +48,11 @@ def gn_stats(x0, x1, stats=None):
     return None
 
 
-def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype):
+def gn_fold_tiles(src0, src1, batch, out=None):
+    return None
+
+
+def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     y = F.group_norm(_nchw(x.float()), 32, gamma, beta, eps)
     return _nhwc(F.silu(y) if silu else y).to(out_dtype)
@@ -65,7 +69,7 @@ def im2col_3x3_s2(x):
 
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
     if up_phase is not None:   # one 2x2 sub-pixel phase: taps (a,b) read (y+a-1+py, x+b-1+px); write (2y+py, 2x+px)

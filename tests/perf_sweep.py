@@ -1,0 +1,71 @@
+"""BASELINE configs[4]: single U-Net eps-step microbench sweep (batch 1-256, 256^2 / 512^2) of the native engine
+against the reference's PyTorch ops on the same B200.
+
+The reference package cannot be imported on the GPU box (no pytorch_lightning / taming there, and /root/reference
+does not travel), so "reference PyTorch" = the oracle's functional restatement of UNetModel.forward
+(oracle/stedm_oracle.py — pinned bit-equal to the reference on CPU) executed by torch 2.11 + cuDNN/cuBLAS on the GPU,
+with the reference's own settings (TF32, predict_diff.py:68) and again under bf16 autocast.  Test infrastructure.
+
+    python tests/perf_sweep.py [--latents 64 128] [--batches 1 4 16 64 256]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from oracle import stedm_oracle as O
+from tests.util import build_model, oracle_state_dict
+
+GFLOP_L64 = 217.29
+
+
+def time_ms(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--latents", type=int, nargs="+", default=[64, 128])
+    ap.add_argument("--batches", type=int, nargs="+", default=[1, 4, 16, 64, 256])
+    a = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    print(f"{'latent':>6} {'batch':>5} | {'native bf16 ms':>14} {'TFLOP/s':>8} | {'torch TF32 ms':>13} {'torch bf16 ms':>13} | "
+          f"{'x TF32':>6} {'x bf16':>6}", flush=True)
+    m = build_model(64, n_style=1, precision="bf16")
+    unet = m._model.model.diffusion_model
+    sd = {k: v.cuda() for k, v in oracle_state_dict(m._model).items() if k.startswith(O.UNET)}
+    for L in a.latents:
+        for B in a.batches:
+            if B * (L / 64) ** 2 > 300:
+                continue
+            g = torch.Generator().manual_seed(B + L)
+            x = torch.randn(B, 3, L, L, generator=g).cuda()
+            cc = torch.randn(B, 3, L, L, generator=g).cuda()
+            ctx = torch.randn(B, 512, generator=g).cuda()
+            t = torch.full((B,), 481, dtype=torch.long, device="cuda")
+            reps = 3 if B * (L / 64) ** 2 >= 64 else 10
+            with torch.no_grad():
+                native = time_ms(lambda: unet.forward_split(x, cc, t, ctx), reps)
+                xc = torch.cat([x, cc], 1)
+                ref32 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    ref16 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
+            tf = B * GFLOP_L64 * (L / 64) ** 2 / native
+            print(f"{L:6d} {B:5d} | {native:14.3f} {tf:8.1f} | {ref32:13.3f} {ref16:13.3f} | {ref32 / native:6.2f} "
+                  f"{ref16 / native:6.2f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

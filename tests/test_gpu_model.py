@@ -215,3 +215,61 @@ def test_shared_trunk_is_bit_identical(precision):
         outs.append(s.p_sample_ddim(x_T.cuda(), cond, ts, index=24, unconditional_guidance_scale=1.5,
                                     unconditional_conditioning=unc))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_latent128_eps_and_decode_vs_oracle():
+    """BASELINE configs[3] geometry (512^2 image, latent 128: full-row 128-pixel tiles, 16 384-token decoder
+    attention) against the CPU oracle run live on the same fixture weights, batch 1."""
+    m = build_model(128, n_style=1, precision="bf16")
+    model = m._model
+    sd = oracle_state_dict(model)
+    seg, style, x_T = O.synthetic_batch(1, 512, 1, seed=5)
+    g = torch.Generator().manual_seed(17)
+    cond = {"c_concat": [torch.randn(1, 3, 128, 128, generator=g)], "c_crossattn": [torch.randn(1, 512, generator=g)]}
+    t = torch.full((1,), 481, dtype=torch.long)
+    with torch.no_grad():
+        want = O.apply_model(sd, x_T, t, cond)
+    got = model.apply_model(x_T.cuda(), t.cuda(), {k: [v[0].cuda()] for k, v in cond.items()})
+    r = rel_err(got, want)
+    print(f"latent-128 bf16 eps rel err {r:.3e}")
+    assert r < BF16_EPS_BAR
+    z = x_T * 60
+    with torch.no_grad():
+        want_img = O.decode_first_stage(sd, z, force_not_quantize=True)
+    img = model.decode_first_stage(z.cuda(), force_not_quantize=True)
+    p = psnr(img.clamp(-1, 1), want_img.clamp(-1, 1))
+    print(f"latent-128 bf16 decode PSNR {p:.1f} dB")
+    assert tuple(img.shape) == (1, 3, 512, 512) and p >= PSNR_BAR
+
+
+def test_multi_style_aggregation_her2_shape():
+    """BASELINE configs[2]: N = 10 style patches per sample aggregated by Agg_Mean (conf/style_sampling/mp.yaml)."""
+    m = build_model(32, n_style=10, precision="bf16")
+    model = m._model
+    sd = oracle_state_dict(model)
+    seg, style, _ = O.synthetic_batch(2, 128, 10, seed=3)
+    batch = {"image": torch.zeros(2, 128, 128, 3).cuda(), "segmentation": seg.cuda(), "style_imgs": style.cuda()}
+    _, c = model.get_input(batch, "image")
+    with torch.no_grad():
+        want = O.get_conditioning(sd, seg, style)
+    assert tuple(c["c_crossattn"][0].shape) == (2, 512)
+    assert max_abs(c["c_crossattn"][0], want["c_crossattn"][0]) < 2e-3
+    assert max_abs(c["c_concat"][0], want["c_concat"][0]) < 1e-6
+
+
+def test_ddpm_ancestral_last_step_is_deterministic_and_matches_formula():
+    """Kept API (ddpm.py:1081-1110): p_sample at t = 0 adds no noise; mean = coef1*x0 + coef2*x_t with
+    x0 = sqrt(1/acp)*x - sqrt(1/acp - 1)*eps."""
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    model = m._model
+    cond = _cond(g, "c_crossattn")
+    t = torch.zeros(2, dtype=torch.long, device="cuda")
+    x = x_T.cuda()
+    out = model.p_sample(x, cond, t, clip_denoised=False)
+    eps = model.apply_model(x, t, cond)
+    x0 = model.sqrt_recip_alphas_cumprod[0] * x - model.sqrt_recipm1_alphas_cumprod[0] * eps
+    want = model.posterior_mean_coef1[0] * x0 + model.posterior_mean_coef2[0] * x
+    assert max_abs(out, want) < 1e-5
+    z = model.sample(cond, batch_size=2, x_T=x, timesteps=2, verbose=False)
+    assert tuple(z.shape) == (2, 3, 32, 32) and bool(torch.isfinite(z).all())

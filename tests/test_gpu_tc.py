@@ -170,3 +170,28 @@ def test_conv_tc_folded_upsample(ops):
     assert tuple(got.shape) == (B, 2 * hw, 2 * hw, co)
     # the phase weights are sums of fp32 taps rounded once to bf16 (not sums of bf16-rounded taps): ~1e-2 abs
     assert max_abs(nchw(got.cpu()), want) < 3e-2
+
+
+@pytest.mark.parametrize("cout,hw,B", [(256, 16, 3), (128, 32, 2), (64, 16, 2)])
+def test_conv_tc_fused_groupnorm_statistics(ops, cout, hw, B):
+    """The epilogue's per-(tile, channel) sums, folded per sample, equal the GroupNorm statistics of the conv
+    output; the normalised result matches F.group_norm of that output."""
+    g = torch.Generator().manual_seed(cout + hw)
+    c = 128
+    x = bf(torch.randn(B, c, hw, hw, generator=g))
+    w = bf(torch.randn(cout, c, 3, 3, generator=g) / math.sqrt(9 * c))
+    b = torch.randn(cout, generator=g)
+    res = bf(torch.randn(B, cout, hw, hw, generator=g))
+    m_tiles = B * hw * hw // 128
+    tiles = torch.full((m_tiles, cout, 2), float("nan"), device="cuda")
+    y = ops.conv(nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), cout, 3, residual=nhwc(res).to(torch.bfloat16).cuda(),
+                 out_dtype=torch.bfloat16, tensor_core=True, stats_out=tiles)
+    want_y = F.conv2d(x, w, b, padding=1) + res
+    sums = tiles.cpu().double().reshape(B, hw * hw // 128, cout, 2).sum(1)              # per sample, per channel
+    assert max_abs(sums[..., 0], want_y.double().sum((2, 3))) < 0.05
+    assert float(((sums[..., 1] - (want_y.double() ** 2).sum((2, 3))).abs() / (want_y.double() ** 2).sum((2, 3))).max()) < 1e-3
+    folded = ops.gn_fold_tiles((tiles, cout, 1, m_tiles, hw * hw // 128, B), None, B)
+    gamma, beta = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
+    got = ops.gn_apply(y, None, folded, gamma.cuda(), beta.cuda(), 1e-5, True, torch.float32, n_chunks=1)
+    want = F.silu(F.group_norm(nchw(y.float().cpu()), 32, gamma, beta, 1e-5))
+    assert max_abs(nchw(got.cpu()), want) < 2e-2
