@@ -232,6 +232,7 @@ def main():
     dev = torch.device("cuda", local)
     B, L, P = args.batch, args.latent, 4 * args.latent
 
+    torch.set_float32_matmul_precision("high")                    # as predict_diff.py:68 (TF32 for the library-run Swin)
     m = build_model(L, args.n_style, args.precision).to(dev).eval()
     m._model.use_cuda_graph = args.graph                          # B=64 passes are GPU-bound: eager is as fast
     first = rank * B                                              # global sample index of this rank's shard

@@ -242,13 +242,14 @@ struct FoldSrc {
   long long rep_stride;  // in tiles
 };
 
-__global__ void __launch_bounds__(256) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out) {
+// 1024 threads: 64 outputs (32 groups x {sum, sumsq}) x 16 threads; thread `sub` takes the tiles j == sub (mod 16)
+// of every (channel, repetition) of its group, so its loads are independent and few.
+__global__ void __launch_bounds__(1024) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int C = s0.c + s1.c, cpg = C / GN_GROUPS;
-  const int o = threadIdx.x >> 2, sub = threadIdx.x & 3;
+  const int o = threadIdx.x >> 4, sub = threadIdx.x & 15;
   const int g = o >> 1, which = o & 1;
   double acc = 0.0;
-  int k = 0;  // running index over (channel in group, rep, tile): strided partition over the 4 sub-threads
   for (int cc = 0; cc < cpg; ++cc) {
     const int ch = g * cpg + cc;
     const FoldSrc& s = (ch < s0.c) ? s0 : s1;
@@ -256,12 +257,12 @@ __global__ void __launch_bounds__(256) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc 
     const int bs = b % s.batch;
     for (int r = 0; r < s.reps; ++r) {
       const float* base = s.tiles + ((static_cast<size_t>(r) * s.rep_stride + static_cast<size_t>(bs) * s.tps) * s.c + lc) * 2 + which;
-      for (int j = 0; j < s.tps; ++j, ++k)
-        if ((k & 3) == sub) acc += static_cast<double>(base[static_cast<size_t>(j) * s.c * 2]);
+#pragma unroll 4
+      for (int j = sub; j < s.tps; j += 16) acc += static_cast<double>(base[static_cast<size_t>(j) * s.c * 2]);
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+#pragma unroll
+  for (int off = 1; off < 16; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);  // fixed tree: deterministic
   if (sub == 0) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which] = acc;
 }
 
@@ -317,7 +318,7 @@ extern "C" int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long 
                 "gn_fold_tiles: bad shape");
   FoldSrc s0{tiles0, c0, reps0, tps0, batch0, rep_stride0};
   FoldSrc s1{tiles1, c1, c1 ? reps1 : 1, c1 ? tps1 : 1, c1 ? batch1 : 1, rep_stride1};
-  gn_fold_tiles_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(s0, s1, out);
+  gn_fold_tiles_kernel<<<batch, 1024, 0, static_cast<cudaStream_t>(stream)>>>(s0, s1, out);
   return check_launch("gn_fold_tiles");
 }
 

@@ -36,6 +36,21 @@ class S_ZSS_DM(LatentDiffusion):
         self.register_module("agg_block", self._agg_block)
         self._agg_block.eval()
 
+    def _style_features(self, style_imgs):
+        """Aggregated style vector.  predict_step's unconditional branch feeds a CONSTANT image (-2 everywhere,
+        modules/ldm_diffusion.py:86): every sample then has the same feature, so the encoder runs once on one
+        sample's style set per (shape, weights) and the row is broadcast — identical values, no recomputation per batch."""
+        first = style_imgs.reshape(-1)[0]
+        if style_imgs.numel() > 0 and bool((style_imgs == first).all()):
+            key = (tuple(style_imgs.shape[1:]), float(first), self._agg_version())
+            if getattr(self, "_const_style_cache", (None, None))[0] != key:
+                self._const_style_cache = (key, self._agg_block(style_imgs[:1]))
+            return self._const_style_cache[1].expand(style_imgs.shape[0], -1).contiguous()
+        return self._agg_block(style_imgs)
+
+    def _agg_version(self):
+        return tuple(p._version for p in self._agg_block.parameters())
+
     @torch.no_grad()
     def get_input(self, batch, k, cond_key=None, bs=None, **kwargs):
         self.cond_stage_trainable = True
@@ -44,7 +59,7 @@ class S_ZSS_DM(LatentDiffusion):
         z, c = outputs[0], outputs[1]
         c = self.get_learned_conditioning(c)
         style_imgs = batch[self.embed_key][:bs].to(self.device)
-        style_features = self._agg_block(style_imgs)
+        style_features = self._style_features(style_imgs)
         out = [z, {"c_concat": [c], "c_crossattn": [style_features]}]
         out.extend(outputs[2:])
         return out
