@@ -41,6 +41,12 @@ static bool g_tc_cluster_enabled = [] {
   return !(e && e[0] == '0');
 }();
 
+// STEDM_TC_PAIR=0 falls back from the cta_group::2 (CTA-pair MMA) variant to cta_group::1 + weight multicast
+static bool g_tc_pair_enabled = [] {
+  const char* e = getenv("STEDM_TC_PAIR");
+  return !(e && e[0] == '0');
+}();
+
 struct TcParams {
   const float* bias;
   const float* emb;
@@ -59,12 +65,16 @@ struct TcParams {
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
 
-template <int BN>
+// PAIR: cta_group::2 — the two CTAs of a cluster form one 256 x BN MMA tile (128 pixel rows each); each CTA stages
+// only its HALF of the weight slab and the tensor core reads both halves, so the bytes that must enter an SM per
+// MMA drop from A + B to A + B/2 (the measured limiter of cta_group::1 at BN = 256: ~75 B/clk/SM of SM ingest
+// against 96 B/clk/SM needed -> tensor pipe 79 % active).
+template <int BN, bool PAIR = false>
 struct TcCfg {
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int STAGES = PAIR ? (BN >= 256 ? 6 : 4) : ((BN >= 256) ? 4 : (BN >= 128 ? 3 : 4));
   static constexpr int ACC = 2;  // TMEM accumulator stages
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;  // bytes of the weight slab staged in THIS CTA
   static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
   static constexpr int ACC_COLS = BN;  // fp32 columns per accumulator
@@ -74,11 +84,12 @@ struct TcCfg {
   static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
 };
 
-template <int BN, int CL>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::MIN_BLOCKS)
+template <int BN, int CL, bool PAIR>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, PAIR>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  static_assert(!PAIR || CL == 2, "cta_group::2 needs a 2-CTA cluster");
+  using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -98,18 +109,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < Cfg::STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);  // released by the MMA commit of every CTA whose smem the slab occupies
+      // PAIR: the leader's full barrier collects both CTAs' producers; its single commit frees the slab in both
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);
+      mbar_init(&empty_bar[i], PAIR ? 1 : CL);  // multicast: released by the MMA commit of every CTA writing into it
     }
     for (int i = 0; i < Cfg::ACC; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);  // every epilogue thread arrives
+      mbar_init(&tmem_empty_bar[i], PAIR ? 256 : 128);  // every epilogue thread (of both CTAs) arrives
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers must exist before any multicast lands
@@ -129,7 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+          if constexpr (PAIR) mbar_arrive_expect_tx_cluster(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES, 0);
+          else mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
           const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
           int dy = 0, dx = 0;
           if (p.tap_mode == 1) {        // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
@@ -140,6 +158,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             dx = tap % 3 - 1;
           }
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          if constexpr (PAIR) {
+            if (cb < p.c0_blks)
+              tma_load_4d_2sm(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
+            else
+              tma_load_4d_2sm(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
+            // this CTA's half of the weight slab: rows [rank*BN/2, +BN/2)
+            tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            continue;
+          }
           if (cb < p.c0_blks)
             tma_load_4d(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
           else
@@ -156,8 +183,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+    if ((!PAIR || cta_rank == 0) && elect_one()) {  // PAIR: only the leader CTA issues (for both)
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
       uint32_t it = 0, tile = 0;
       for (int work = cluster_id; work < p.num_work; work += num_clusters, ++tile) {
         const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
@@ -173,13 +200,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          // frees the slab once these MMAs have read it — in every CTA that multicasts into it
-          if (CL == 1) umma_commit(&empty_bar[s]);
+          for (int k = 0; k < TC_BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
+            if constexpr (PAIR) umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // frees the slab once these MMAs have read it — in every CTA that multicasts into it / of the pair
+          if constexpr (PAIR) umma_commit_2sm_mcast(&empty_bar[s], 3);
+          else if (CL == 1) umma_commit(&empty_bar[s]);
           else umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1));
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs in PAIR mode)
+        if constexpr (PAIR) umma_commit_2sm_mcast(&tmem_full_bar[acc], 3);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -306,7 +338,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (PAIR) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's MMA thread waits for both CTAs
+      else mbar_arrive(&tmem_empty_bar[acc]);
       if constexpr (CH == 32) {
         if (p.stats_out != nullptr) {
           // fold the four warps' partials in a fixed order and publish this tile's per-channel statistics
@@ -332,7 +365,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while a peer can still write into it
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 int tc_num_sms() {
@@ -345,12 +381,12 @@ int tc_num_sms() {
   return n;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool PAIR = false>
 int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, TcParams p, cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR>;
   static bool configured = false;  // per-process; the attribute is per-function and idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return ERR_CUDA;
@@ -374,7 +410,7 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL>, ma0, ma1, mw, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR>, ma0, ma1, mw, p);
   if (e != cudaSuccess) {
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
@@ -450,10 +486,11 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 16));
   // weight multicast across a 2-CTA cluster for the wide tiles whenever there are at least two pixel tiles
   const int cl = (bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
+  const bool pair = cl == 2 && g_tc_pair_enabled;   // cta_group::2: each CTA stages half of the weight slab
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(d->cout)};
     const uint64_t str[1] = {static_cast<uint64_t>(taps) * ctot * 2};
-    const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn / cl)};
+    const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn / cl)};  // multicast half / pair half / whole slab
     int rc = make_tmap_bf16(&mw, d->weight, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -477,8 +514,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   }
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);
-    case 128: return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, p, s) : launch_tc<128, 1>(ma0, ma1, mw, p, s);
+    case 256:
+      if (pair) return launch_tc<256, 2, true>(ma0, ma1, mw, p, s);
+      return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);
+    case 128:
+      if (pair) return launch_tc<128, 2, true>(ma0, ma1, mw, p, s);
+      return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, p, s) : launch_tc<128, 1>(ma0, ma1, mw, p, s);
     case 64: return launch_tc<64, 1>(ma0, ma1, mw, p, s);
     default: return launch_tc<16, 1>(ma0, ma1, mw, p, s);
   }
