@@ -103,19 +103,34 @@ extern "C" int stedm_cfg_ddim_step(const float* e_c, const float* e_u, const flo
 // coalesced along the pixel index for every channel, the c_pad-wide row is written with 16 B stores.
 // =====================================================================================================
 template <typename TO>
-__global__ void pack_nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
-                                         TO* __restrict__ out, int hw, int c_pad) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) pack_nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0,
+                                                                const float* __restrict__ x1, int c1,
+                                                                TO* __restrict__ out, int hw, int c_pad) {
+  // one thread = one 16-byte chunk of one pixel's channel row: consecutive threads write consecutive chunks
+  // (fully coalesced 16 B stores; the zero padding is most of the row), the few real channels are gathered
+  constexpr int VEC = 16 / sizeof(TO);
+  const int chunks = c_pad / VEC;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const int b = blockIdx.y;
-  if (p >= hw) return;
-  TO* o = out + (static_cast<size_t>(b) * hw + p) * c_pad;
-  for (int c = 0; c < c_pad; ++c) {
-    float v = 0.f;
+  if (i >= static_cast<size_t>(hw) * chunks) return;
+  const int p = static_cast<int>(i / chunks), ch0 = static_cast<int>(i % chunks) * VEC;
+  float v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c = ch0 + j;
+    float t = 0.f;
     if (c < c0)
-      v = x0[(static_cast<size_t>(b) * c0 + c) * hw + p];
+      t = x0[(static_cast<size_t>(b) * c0 + c) * hw + p];
     else if (c < c0 + c1)
-      v = x1[(static_cast<size_t>(b) * c1 + (c - c0)) * hw + p];
-    o[c] = from_f32<TO>(v);
+      t = x1[(static_cast<size_t>(b) * c1 + (c - c0)) * hw + p];
+    v[j] = t;
+  }
+  TO* o = out + (static_cast<size_t>(b) * hw + p) * c_pad + ch0;
+  if constexpr (sizeof(TO) == 2) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+  } else {
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -123,12 +138,15 @@ extern "C" int stedm_pack_nchw_to_nhwc(const float* x0, int c0, const float* x1,
                                        int batch, int hw, int c_pad, void* stream) {
   STEDM_REQUIRE(x0 && out && (c1 == 0 || x1), "pack_nchw_to_nhwc: null pointer");
   STEDM_REQUIRE(c0 + c1 <= c_pad && batch > 0 && hw > 0, "pack_nchw_to_nhwc: bad shape");
-  dim3 grid((hw + 127) / 128, batch);
+  const int vec = out_dtype == DT_BF16 ? 8 : 4;
+  STEDM_REQUIRE(c_pad % vec == 0, "pack_nchw_to_nhwc: c_pad must be a multiple of %d", vec);
+  const size_t items = static_cast<size_t>(hw) * (c_pad / vec);
+  dim3 grid(static_cast<unsigned>((items + 255) / 256), batch);
   auto s = static_cast<cudaStream_t>(stream);
   if (out_dtype == DT_BF16)
-    pack_nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(x0, c0, x1, c1, static_cast<__nv_bfloat16*>(out), hw, c_pad);
+    pack_nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x0, c0, x1, c1, static_cast<__nv_bfloat16*>(out), hw, c_pad);
   else
-    pack_nchw_to_nhwc_kernel<float><<<grid, 128, 0, s>>>(x0, c0, x1, c1, static_cast<float*>(out), hw, c_pad);
+    pack_nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(x0, c0, x1, c1, static_cast<float*>(out), hw, c_pad);
   return check_launch("pack_nchw_to_nhwc");
 }
 

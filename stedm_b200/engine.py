@@ -282,7 +282,11 @@ class UNetRunner:
         self.emb_b = torch.cat(emb_b, 0).contiguous()
 
     # -- embedding path (K8): sinusoid -> time_embed MLP -> all 17 emb_layers in one stacked linear
-    def embeddings(self, t, context):
+    def embeddings(self, t, context, uniform_t=False):
+        """``uniform_t``: the caller guarantees every sample has the same timestep (a DDIM step): the time-embedding
+        MLP and all 17 emb_layers are then evaluated for ONE row and broadcast by the conv epilogues (row stride 0)."""
+        if uniform_t:
+            t = t[:1]
         temb = ops.timestep_embedding(t, self.mc)
         e = ops.linear(temb, *self.te0)
         e = ops.linear(e, *self.te2, silu_in=True)
@@ -290,7 +294,7 @@ class UNetRunner:
         emb_style = ops.linear(context.float().contiguous(), *self.style_emb, silu_in=True)
         return emb_all, emb_style
 
-    def __call__(self, x, c_concat, t, context):
+    def __call__(self, x, c_concat, t, context, uniform_t=False):
         """x (B,3,L,L) and c_concat (B,3,L,L) NCHW fp32 (the 'hybrid' concat of ddpm.py:1414 is fused into the
         packing kernel), t (B,) int64, context (B,512) -> eps (B,3,L,L) NCHW fp32.
 
@@ -304,7 +308,7 @@ class UNetRunner:
         B = x.shape[0]
         G = context.shape[0] // B
         assert context.shape[0] == G * B and G >= 1
-        emb_all, emb_style = self.embeddings(t, context)
+        emb_all, emb_style = self.embeddings(t, context, uniform_t)
         pool = StatsPool(self.n_norms, G * B, x.device)
         h = ops.pack_nchw_to_nhwc(x.contiguous(), c_concat, self.stem.cin_pad, prec.act)
         hs = []
@@ -321,7 +325,8 @@ class UNetRunner:
             tiles = getattr(h, "_gn_tiles", None)
             h = torch.cat([h] * G, 0)
             h._gn_tiles = tiles                 # sample b of the copy owns the tile rows of sample b % B
-            emb_all = torch.cat([emb_all] * G, 0)
+            if emb_all.shape[0] > 1:
+                emb_all = torch.cat([emb_all] * G, 0)
         h = self.mid1(h, None, emb_style, pool)
         h = self._attention(h, pool)
         h = self.mid3(h, None, self._emb_view(emb_all, ("mid", 3)), pool)

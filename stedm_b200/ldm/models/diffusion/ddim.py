@@ -101,7 +101,9 @@ class DDIMSampler(object):
             if mask is not None:
                 assert x0 is not None
                 img = self.model.q_sample(x0, ts) * mask + (1. - mask) * img
-            img, pred_x0 = stepper.step(img, ts, index, temperature=temperature, noise_dropout=noise_dropout)
+            # ts is torch.full(step): one timestep for the whole batch -> embeddings are computed for one row
+            img, pred_x0 = stepper.step(img, ts, index, temperature=temperature, noise_dropout=noise_dropout,
+                                        uniform_t=True)
             if callback:
                 callback(i)
             if img_callback:
@@ -156,7 +158,7 @@ class _GuidedStepper:
         self.use_graph = allow_graph and sampler.use_cuda_graph
         self._graph_inputs_stale = True
 
-    def _eps(self, x, t):
+    def _eps(self, x, t, uniform_t=False):
         """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,)."""
         if self.guided and not self.shared:
             x2 = torch.cat([x, x], 0)
@@ -164,23 +166,23 @@ class _GuidedStepper:
         else:
             x2, t2 = x, t
         if not self.use_graph:
-            return self.unet.forward_split(x2, self.c_concat, t2, self.context)
+            return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t)
         # CUDA graph of the U-Net pass (worth it only when a pass is launch-bound, i.e. small batches): captured
         # once per shape signature and cached on the U-Net module, with static input buffers, so later sampler
         # objects (sample_log builds a new DDIMSampler per call, like the reference) replay instead of re-capturing.
         cache = self.unet.__dict__.setdefault("_graph_cache", {})
-        key = (tuple(x2.shape), tuple(self.c_concat.shape), tuple(self.context.shape), self.unet.precision)
+        key = (tuple(x2.shape), tuple(self.c_concat.shape), tuple(self.context.shape), self.unet.precision, uniform_t)
         ent = cache.get(key)
         if ent is None:
             warm = cache.setdefault(("warm",) + key, [0])
             if warm[0] < 1:   # one eager pass first: lazy kernel attribute setup must not happen under capture
                 warm[0] += 1
-                return self.unet.forward_split(x2, self.c_concat, t2, self.context)
+                return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t)
             ent = {"x": x2.clone(), "t": t2.clone(), "cc": self.c_concat.clone(), "ctx": self.context.clone(),
                    "graph": torch.cuda.CUDAGraph()}
             n0 = ops.LAUNCHES[0]
             with torch.cuda.graph(ent["graph"]):
-                ent["eps"] = self.unet.forward_split(ent["x"], ent["cc"], ent["t"], ent["ctx"])
+                ent["eps"] = self.unet.forward_split(ent["x"], ent["cc"], ent["t"], ent["ctx"], uniform_t=uniform_t)
             ent["launches"] = ops.LAUNCHES[0] - n0
             ops.LAUNCHES[0] = n0                      # capture enqueued nothing; replays are counted below
             cache[key] = ent
@@ -194,10 +196,10 @@ class _GuidedStepper:
         ops.LAUNCHES[0] += ent["launches"]
         return ent["eps"].clone()
 
-    def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False):
+    def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False, uniform_t=False):
         s = self.s
         x = x.float().contiguous()
-        eps = self._eps(x, t)
+        eps = self._eps(x, t, uniform_t)
         e_c, e_u = (eps[:self.b], eps[self.b:]) if self.guided else (eps, None)
         sigma = _f32(s.ddim_sigmas[index])
         # the reference draws randn every step, also when sigma == 0 (ddim.py:206): keep the RNG stream aligned

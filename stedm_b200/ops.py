@@ -130,7 +130,8 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
     _cuda(x0, x1, weight, bias, residual)
     if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
-        assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape == (x0.shape[0], cout)
+        assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] == cout
+        assert emb.shape[0] in (1, x0.shape[0])          # one row per sample, or one row broadcast to all samples
     b, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     out_dtype = out_dtype or x0.dtype
@@ -147,7 +148,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.batch, d.in_h, d.in_w = b, h, w
     d.x1_batch = 0 if x1 is None or x1.shape[0] == b else x1.shape[0]
     d.ksize, d.stride, d.upsample = ksize, stride, 1 if upsample else 0
-    d.emb_stride = 0 if emb is None else emb.stride(0)
+    d.emb_stride = 0 if (emb is None or emb.shape[0] == 1) else emb.stride(0)
     d.res_dtype = F32 if residual is None else _DT[residual.dtype]
     d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
     d.cout_store = cout_store if out_nchw else 0

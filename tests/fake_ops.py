@@ -88,7 +88,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
     y = F.conv2d(xin, w, bias, stride=stride, padding=ksize // 2)
     if emb is not None:
-        y = y + emb[:, :, None, None]
+        y = y + emb[:, :, None, None]        # (1, C) broadcasts like the kernel's row stride 0
     if residual is not None:
         y = y + _nchw(residual.float())
     if out_nchw:
