@@ -317,3 +317,28 @@ def test_predict_entry_point_writes_pngs(tmp_path):
         img = Image.open(f"{out}/img_{i:05d}.png")
         assert img.size == (128, 128) and img.mode == "RGB"
         assert Image.open(f"{out}/seg_{i:05d}.png").size == (128, 128)
+
+
+@pytest.mark.parametrize("precision,z_bar,psnr_bar", [("fp32", 1e-3, 40.0), ("bf16", 5e-2, 30.0)])
+def test_config0_flowers_b4_256_full_path_vs_reference_golden(precision, z_bar, psnr_bar):
+    """BASELINE configs[0] (flowers proof of concept: batch 4, 256^2, DDIM-50, cfg 1.5) end to end against the
+    golden produced by the reference's own code on CPU (tests/golden/c1_b4_l64.npz)."""
+    g = load_golden("c1_b4_l64")
+    seg, style, x_T = O.synthetic_batch(4, 256, 1, 1)
+    m = build_model(64, n_style=1, precision=precision)
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"]).cuda()], "c_crossattn": [torch.from_numpy(g["c_crossattn"]).cuda()]}
+    unc = {"c_concat": [torch.from_numpy(g["c_concat"]).cuda()], "c_crossattn": [torch.from_numpy(g["uc_crossattn"]).cuda()]}
+    tt = torch.full((4,), 481, dtype=torch.long, device="cuda")
+    e = m._model.apply_model(x_T.cuda(), tt, cond)
+    r_e = rel_err(e, g["eps_c_481"])
+    assert (max_abs(e, g["eps_c_481"]) < FP32_EPS_BAR) if precision == "fp32" else (r_e < BF16_EPS_BAR)
+    z, _ = m._model.sample_log(cond, batch_size=4, ddim=True, ddim_steps=50, eta=0.0, log_every_t=1000, x_T=x_T.cuda(),
+                               unconditional_conditioning=unc, unconditional_guidance_scale=1.5)
+    r_z = rel_err(z, g["z_final"])
+    img = m._model.decode_first_stage(torch.from_numpy(g["z_final"]).cuda())
+    p_dec = psnr(img.clamp(-1, 1), np.clip(g["dec_quant"].astype(np.float32), -1, 1))
+    img_e2e = m._model.decode_first_stage(z)
+    p_e2e = psnr(img_e2e.clamp(-1, 1), np.clip(g["dec_quant"].astype(np.float32), -1, 1))
+    print(f"config0 {precision}: eps rel {r_e:.2e}  DDIM-50 latent rel {r_z:.2e}  decode PSNR {p_dec:.1f} dB  "
+          f"end-to-end PSNR {p_e2e:.1f} dB")
+    assert r_z < z_bar and p_dec >= PSNR_BAR and p_e2e >= psnr_bar
