@@ -95,6 +95,9 @@ typedef struct stedm_conv_desc {
   float* stats_out;    /* tensor-core path, optional: fp32 [tiles][cout][2] = per-(128-pixel tile, channel) sum and sum
                           of squares of the values written (tiles = batch*in_h*in_w/128, x4 phases in tap_mode 1):
                           the GroupNorm statistics pass folded into the producer; consumed by stedm_gn_fold_tiles */
+  void* workspace;     /* tensor-core path, optional: scratch for split-K (launches with few output tiles and a deep
+                          K loop, i.e. small batches); size from stedm_conv_tc_workspace_bytes(); NULL => single pass */
+  int64_t workspace_bytes;
   int32_t c0, c1;
   int32_t in_dtype;    /* dtype of x0/x1 */
   int32_t batch, in_h, in_w;
@@ -119,6 +122,9 @@ typedef struct stedm_conv_desc {
  * upsample 0, c0 % 64 == 0, c1 % 64 == 0, cout % 16 == 0; output NHWC (bf16/fp32) or NCHW fp32 (the eps / image
  * heads with 3 real channels: cout = 16 zero-padded weight rows, cout_store = 3). */
 int stedm_conv_tc(const stedm_conv_desc* d, void* stream);
+/* Bytes of `workspace` stedm_conv_tc would use for this descriptor (0 when it runs in a single pass; always 0 when
+ * stats_out is set: the fused statistics need the single-pass epilogue). */
+long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d);
 /* General fp32-accumulate SIMT implicit GEMM: the fp32 parity mode and every shape the tensor-core path rejects. */
 int stedm_conv_simt(const stedm_conv_desc* d, void* stream);
 

@@ -17,7 +17,7 @@ vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 class ConvDesc(C.Structure):
     """Mirror of ``struct stedm_conv_desc``."""
     _fields_ = [("x0", vp), ("x1", vp), ("weight", vp), ("bias", vp), ("emb", vp), ("residual", vp), ("out", vp),
-                ("stats_out", vp), ("c0", C.c_int32), ("c1", C.c_int32), ("in_dtype", C.c_int32), ("batch", C.c_int32),
+                ("stats_out", vp), ("workspace", vp), ("workspace_bytes", C.c_int64), ("c0", C.c_int32), ("c1", C.c_int32), ("in_dtype", C.c_int32), ("batch", C.c_int32),
                 ("in_h", C.c_int32), ("in_w", C.c_int32), ("x1_batch", C.c_int32), ("ksize", C.c_int32),
                 ("stride", C.c_int32), ("upsample", C.c_int32), ("emb_stride", C.c_int32), ("res_dtype", C.c_int32),
                 ("out_dtype", C.c_int32), ("out_nchw", C.c_int32), ("cout", C.c_int32), ("cout_store", C.c_int32), ("tap_mode", C.c_int32), ("phase", C.c_int32)]
@@ -34,6 +34,7 @@ SIGNATURES = {
     "stedm_gn_apply": [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, i32, vp, i32, vp],
     "stedm_gn_fold_tiles": [vp, i32, i32, i64, i32, i32, vp, i32, i32, i64, i32, i32, i32, vp, vp],
     "stedm_conv_tc": [C.POINTER(ConvDesc), vp],
+    "stedm_conv_tc_workspace_bytes": [C.POINTER(ConvDesc)],
     "stedm_conv_simt": [C.POINTER(ConvDesc), vp],
     "stedm_gemm_simt": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64,
                         i64, i64, f32, vp],
@@ -49,7 +50,7 @@ SIGNATURES = {
     "stedm_spatial_rescale": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_image_to_uint8": [vp, vp, i32, i32, i32, vp],
 }
-_RESTYPES = {"stedm_last_error": C.c_char_p}
+_RESTYPES = {"stedm_last_error": C.c_char_p, "stedm_conv_tc_workspace_bytes": C.c_longlong}
 
 _lib = None
 

@@ -41,6 +41,12 @@ static bool g_tc_cluster_enabled = [] {
   return !(e && e[0] == '0');
 }();
 
+// STEDM_TC_SPLITK=0 disables split-K for launches with few output tiles
+static bool g_tc_splitk_enabled = [] {
+  const char* e = getenv("STEDM_TC_SPLITK");
+  return !(e && e[0] == '0');
+}();
+
 // STEDM_TC_PAIR=0 falls back from the cta_group::2 (CTA-pair MMA) variant to cta_group::1 + weight multicast
 static bool g_tc_pair_enabled = [] {
   const char* e = getenv("STEDM_TC_PAIR");
@@ -57,7 +63,11 @@ struct TcParams {
   int c0_blks, c_blks;  // 64-channel slabs in source 0 / in the concat
   int x1_batch;
   int n_tiles;          // output-channel tiles
-  int num_work;         // cluster work items = ceil(m_tiles / CL) * n_tiles
+  int num_work;         // cluster work items = ceil(m_tiles / CL) * n_tiles * ksplit
+  int ksplit;           // split-K factor (1 = off): work item = (tile, K range); partials go to `ws`
+  int kb_per_split;     // K slabs per split
+  float* ws;            // split-K workspace: fp32 [ksplit][m_pad][cout]
+  int m_pad;            // rows of one workspace slice (all tiles, including the out-of-bounds one)
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
@@ -138,11 +148,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (elect_one()) {
       uint32_t it = 0;  // K-slab counter, runs across tiles
       for (int work = cluster_id; work < p.num_work; work += num_clusters) {
-        const int n0 = (work % p.n_tiles) * BN;
-        const int m0 = ((work / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
+        const int tile_id = work / p.ksplit, split = work - tile_id * p.ksplit;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        const int n0 = (tile_id % p.n_tiles) * BN;
+        const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
         const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
         const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -191,7 +203,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int split = work % p.ksplit;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -201,8 +215,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
-            if constexpr (PAIR) umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accumulate = ((kb - kb0) | k) != 0 ? 1u : 0u;
+            if constexpr (PAIR) umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
           }
           // frees the slab once these MMAs have read it — in every CTA that multicasts into it / of the pair
           if constexpr (PAIR) umma_commit_2sm_mcast(&empty_bar[s], 3);
@@ -222,8 +237,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint32_t tile = 0;
     for (int work = cluster_id; work < p.num_work; work += num_clusters, ++tile) {
       const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
-      const int n_base = (work % p.n_tiles) * BN;
-      const int m = ((work / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM + row;
+      const int tile_id = work / p.ksplit, split = work - tile_id * p.ksplit;
+      const int n_base = (tile_id % p.n_tiles) * BN;
+      const int m = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM + row;
       const bool valid = m < p.M;
       const int b = valid ? m / p.HW : 0;
       const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
@@ -247,6 +263,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int n = n_base + c;
+        if (p.ksplit > 1) {  // split-K: raw fp32 partial tile -> workspace; splitk_finish_kernel applies the epilogue
+          float4* wp = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.m_pad + m) * p.cout + n);
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) wp[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          continue;
+        }
         if (valid) {
         if (p.bias) {
 #pragma unroll
@@ -344,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (p.stats_out != nullptr) {
           // fold the four warps' partials in a fixed order and publish this tile's per-channel statistics
           named_bar_sync(1, 128);
-          const int m_tile = (work / p.n_tiles) * CL + static_cast<int>(cta_rank);
+          const int m_tile = (tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank);
           if (m_tile * TC_BM < p.M) {
             float* dst = p.stats_out + (static_cast<size_t>(p.stats_tile_base + m_tile) * p.cout + n_base) * 2;
             for (int ch = threadIdx.x - 64; ch < BN; ch += 128) {
@@ -368,6 +390,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1) {
     if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
     else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// Split-K second pass: out = epilogue(sum over splits of the fp32 partial tiles).  One thread = 8 channels of one pixel.
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
+  const int groups = p.cout / 8;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(p.M) * groups) return;
+  const int m = static_cast<int>(i / groups), n = static_cast<int>(i % groups) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  for (int s = 0; s < p.ksplit; ++s) {  // fixed order: deterministic
+    const float4* wp = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(s) * p.m_pad + m) * p.cout + n);
+    const float4 a = wp[0], b = wp[1];
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  const int b = m / p.HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (p.bias) v[j] += p.bias[n + j];
+    if (p.emb) v[j] += p.emb[static_cast<size_t>(b) * p.emb_stride + n + j];
+  }
+  size_t o = static_cast<size_t>(m) * p.cout + n;
+  if (p.tap_mode == 1) {
+    const int pix = m - b * p.HW, y = pix / p.W, x = pix - y * p.W;
+    o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
+  }
+  if (p.residual) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[o + j]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[o + j]);
+  }
+  if (p.out_nchw) {
+    const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n + j >= p.cout_store) continue;
+      if (p.out_dtype == DT_F32) static_cast<float*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = v[j];
+      else static_cast<__nv_bfloat16*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+    }
+  } else if (p.out_dtype == DT_BF16) {
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else {
+    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+    op[0] = make_float4(v[0], v[1], v[2], v[3]);
+    op[1] = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 
@@ -395,7 +466,7 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
   }
   const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
   const int m_groups = (m_tiles + CL - 1) / CL;  // an odd tile count gets one all-out-of-bounds tile (zero-filled loads, no stores)
-  p.num_work = m_groups * p.n_tiles;
+  p.num_work = m_groups * p.n_tiles * p.ksplit;
   const int max_clusters = tc_num_sms() * Cfg::MIN_BLOCKS / CL;   // persistent: one resident wave
   const int clusters = p.num_work < max_clusters ? p.num_work : max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -415,10 +486,58 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
   }
-  return check_launch("conv_tc");
+  int rc = check_launch("conv_tc");
+  if (rc == 0 && p.ksplit > 1) {
+    const size_t items = static_cast<size_t>(p.M) * (p.cout / 8);
+    splitk_finish_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(p);
+    rc = check_launch("conv_tc split-K finish");
+  }
+  return rc;
+}
+
+// Tile / cluster / split-K plan of one launch: shared by stedm_conv_tc and stedm_conv_tc_workspace_bytes.
+// Split-K is chosen when the output tiles would occupy less than half of the persistent grid and K is deep
+// (small batches: the deep layers have a handful of tiles but hundreds of K slabs).
+struct TcPlan {
+  int bn, cl, ksplit, kb_per_split, m_pad;
+  bool pair;
+  size_t ws_bytes;
+};
+
+TcPlan tc_plan(long long M, int cout, int num_kb, bool want_stats) {
+  TcPlan t;
+  t.bn = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 16));
+  t.cl = (t.bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
+  t.pair = t.cl == 2 && g_tc_pair_enabled;
+  const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
+  const int m_groups = (m_tiles + t.cl - 1) / t.cl;
+  const int tiles = m_groups * (cout / t.bn);
+  const int max_clusters = tc_num_sms() * (t.bn >= 256 ? 1 : 2) / t.cl;
+  t.m_pad = m_groups * t.cl * TC_BM;
+  t.ksplit = 1;
+  t.kb_per_split = num_kb;
+  t.ws_bytes = 0;
+  if (g_tc_splitk_enabled && !want_stats && t.bn >= 64 && tiles * 2 <= max_clusters && num_kb >= 8) {
+    int ks = max_clusters / tiles;
+    if (ks > num_kb / 4) ks = num_kb / 4;
+    if (ks >= 2) {
+      t.kb_per_split = (num_kb + ks - 1) / ks;
+      t.ksplit = (num_kb + t.kb_per_split - 1) / t.kb_per_split;
+      t.ws_bytes = static_cast<size_t>(t.ksplit) * t.m_pad * cout * sizeof(float);
+    }
+  }
+  return t;
 }
 
 }  // namespace
+
+extern "C" long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d) {
+  if (d == nullptr || d->cout < 16 || d->cout % 16 != 0 || d->batch <= 0) return 0;
+  const long long M = static_cast<long long>(d->batch) * d->in_h * d->in_w;
+  const int taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
+  const int num_kb = taps * ((d->c0 + d->c1) / TC_BK);
+  return static_cast<long long>(tc_plan(M, d->cout, num_kb, d->stats_out != nullptr).ws_bytes);
+}
 
 extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_tc: null pointer");
@@ -483,10 +602,14 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
     ma1 = ma0;
   }
   const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
-  const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0 ? 128 : (d->cout % 64 == 0 ? 64 : 16));
-  // weight multicast across a 2-CTA cluster for the wide tiles whenever there are at least two pixel tiles
-  const int cl = (bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
-  const bool pair = cl == 2 && g_tc_pair_enabled;   // cta_group::2: each CTA stages half of the weight slab
+  // channel tile, 2-CTA cluster (cta_group::2 pair or weight multicast) and split-K plan
+  TcPlan plan = tc_plan(M, d->cout, taps * (ctot / TC_BK), d->stats_out != nullptr);
+  if (plan.ksplit > 1 && (d->workspace == nullptr || static_cast<size_t>(d->workspace_bytes) < plan.ws_bytes)) {
+    plan.ksplit = 1;                        // no (or too small a) workspace: single pass
+    plan.kb_per_split = taps * (ctot / TC_BK);
+  }
+  const int bn = plan.bn, cl = plan.cl;
+  const bool pair = plan.pair;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(d->cout)};
     const uint64_t str[1] = {static_cast<uint64_t>(taps) * ctot * 2};
@@ -501,6 +624,8 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.c0_blks = d->c0 / TC_BK; p.c_blks = ctot / TC_BK;
   p.x1_batch = x1b;
   p.n_tiles = d->cout / bn;
+  p.ksplit = plan.ksplit; p.kb_per_split = plan.kb_per_split; p.m_pad = plan.m_pad;
+  p.ws = static_cast<float*>(d->workspace);
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;

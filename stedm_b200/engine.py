@@ -121,7 +121,7 @@ class PackedConv:
                 tiles, meta = self._tile_stats(cols, want_stats)
                 out = ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
                                out_dtype=out_dtype, tensor_core=True, stats_out=tiles)
-                out._gn_tiles = meta
+                out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
                 return out
             if upsample and self.phase_weights is not None:
                 assert x1 is None and emb is None and residual is None and not out_nchw
@@ -131,7 +131,7 @@ class PackedConv:
                 for ph, wp in enumerate(self.phase_weights):
                     ops.conv(x0, wp, self.bias, self.cout, 3, out_dtype=out_dtype, tensor_core=True, out=out,
                              up_phase=ph, stats_out=tiles)
-                out._gn_tiles = meta
+                out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
                 return out
             if upsample:
                 assert x1 is None
@@ -140,7 +140,7 @@ class PackedConv:
             out = ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
                            out_dtype=out_dtype, tensor_core=True, out_nchw=out_nchw,
                            cout_store=self.cout_real if out_nchw else 0, stats_out=tiles)
-            out._gn_tiles = meta
+            out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
             return out
         return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
                         out_dtype=out_dtype, stride=self.stride, upsample=upsample, out_nchw=out_nchw,

@@ -15,6 +15,17 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
 LAUNCHES = [0]  # number of native kernel launches issued through this module (bench.py's gpu_launches)
+SPLITK_MAX_PIXELS = 148 * 128 * 4  # above this the output tiles alone fill the persistent grid: never split-K
+# Split-K changes the fp32 summation order as a function of how many tiles a launch has, i.e. of the batch size:
+# it trades the bit-exact batch/rank-shard invariance of the default path for small-batch latency.  Opt-in.
+SPLIT_K = [False]
+
+
+def enable_split_k(flag=True):
+    """Latency mode for small batches (BASELINE configs[4]): split the K loop of launches with few output tiles
+    across the idle SMs.  Results stay within fp32 reassociation of the default path but are no longer bit-identical
+    across batch sizes, so it is off by default."""
+    SPLIT_K[0] = bool(flag)
 
 
 def _ptr(t):
@@ -153,6 +164,19 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
     d.cout_store = cout_store if out_nchw else 0
     d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
+    out._stats_written = stats_out is not None
+    if tensor_core and SPLIT_K[0] and b * h * w <= SPLITK_MAX_PIXELS:
+        # small launches (few output tiles, deep K): split-K over the idle SMs through a caller-owned workspace.
+        # The fused GroupNorm statistics need the single-pass epilogue, so they are dropped for such launches and
+        # the consumer falls back to the separate statistics kernel (tensors this small cost nothing to re-read).
+        d.stats_out = None
+        need = _lib.load().stedm_conv_tc_workspace_bytes(C.byref(d))
+        if need > 0:
+            ws = torch.empty((need,), device=x0.device, dtype=torch.uint8)
+            d.workspace, d.workspace_bytes = _ptr(ws), need
+            out._stats_written = False
+        else:
+            d.stats_out = _ptr(stats_out)
     if tensor_core:
         ntaps = 4 if up_phase is not None else ksize * ksize
         assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ntaps * (c0 + c1), \

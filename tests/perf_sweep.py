@@ -63,13 +63,22 @@ def main():
                     unet.forward_split(x, cc, t, ctx)
                 replay = time_ms(graph.replay, reps)
                 del graph
+                from stedm_b200 import ops as _ops            # opt-in latency mode: split-K for launches with few tiles
+                _ops.enable_split_k(True)
+                graph = torch.cuda.CUDAGraph()
+                unet.forward_split(x, cc, t, ctx)
+                with torch.cuda.graph(graph):
+                    unet.forward_split(x, cc, t, ctx)
+                splitk = time_ms(graph.replay, reps)
+                _ops.enable_split_k(False)
+                del graph
                 xc = torch.cat([x, cc], 1)
                 ref32 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     ref16 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
             tf = B * GFLOP_L64 * (L / 64) ** 2 / replay
             print(f"{L:6d} {B:5d} | {native:14.3f} {replay:8.3f} {tf:8.1f} | {ref32:13.3f} {ref16:13.3f} | "
-                  f"{ref32 / replay:6.2f} {ref16 / replay:6.2f}", flush=True)
+                  f"{ref32 / replay:6.2f} {ref16 / replay:6.2f}   split-K graph {splitk:8.3f} ms", flush=True)
 
 
 if __name__ == "__main__":

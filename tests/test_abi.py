@@ -27,7 +27,7 @@ def test_library_exports_header_symbols():
 
 def test_conv_desc_layout_matches_header():
     from stedm_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 8 * 8 + 18 * 4  # 8 pointers, 18 int32
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 18 * 4  # 9 pointers, int64, 18 int32
 
 
 def test_sass_is_blackwell_native():

@@ -42,7 +42,7 @@ def test_unet_runner_glue(cpu_model, patched, precision, bar):
         # shared encoder trunk: B inputs, 2B contexts -> the same 2B eps
         eps3 = runner(x_T, cc, t, ctx)
         # one timestep for the whole batch: embeddings computed for one row and broadcast
-        assert max_abs(runner(x_T, cc, t, ctx, uniform_t=True), eps3) < (1e-6 if precision == "fp32" else 5e-2)
+        assert max_abs(runner(x_T, cc, t, ctx, uniform_t=True), eps3) < (5e-5 if precision == "fp32" else 5e-2)
     # (the CPU stand-in's conv picks batch-dependent algorithms, so bf16 emulation is not bit-stable here; the
     #  bit-exactness of the real kernels is asserted on the GPU in tests/test_gpu_model.py)
     assert max_abs(eps3, eps2) < (1e-5 if precision == "fp32" else 5e-2)

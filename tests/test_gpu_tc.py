@@ -195,3 +195,34 @@ def test_conv_tc_fused_groupnorm_statistics(ops, cout, hw, B):
     got = ops.gn_apply(y, None, folded, gamma.cuda(), beta.cuda(), 1e-5, True, torch.float32, n_chunks=1)
     want = F.silu(F.group_norm(nchw(y.float().cpu()), 32, gamma, beta, 1e-5))
     assert max_abs(nchw(got.cpu()), want) < 2e-2
+
+
+@pytest.mark.parametrize("B,hw,cin,cout,k", [(1, 16, 1024, 1024, 3), (2, 16, 512, 256, 3), (1, 32, 256, 128, 1),
+                                             (1, 8, 2048, 1024, 3)])
+def test_conv_tc_split_k_small_batch(ops, B, hw, cin, cout, k):
+    """Few output tiles + deep K: the launch splits K across the idle SMs (workspace + finish kernel); the result
+    must equal the single-pass one up to fp32 summation order, with every epilogue term applied exactly once."""
+    g = torch.Generator().manual_seed(B + cin)
+    x = bf(torch.randn(B, cin, hw, hw, generator=g))
+    w = bf(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    b = torch.randn(cout, generator=g)
+    res = bf(torch.randn(B, cout, hw, hw, generator=g))
+    emb = torch.randn(B, cout, generator=g)
+    want = F.conv2d(x, w, b, padding=k // 2) + res + emb[:, :, None, None]
+    xd, wd = nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda()
+    from stedm_b200 import _lib
+    import ctypes
+    ops.enable_split_k(True)
+    try:
+        got = ops.conv(xd, wd, b.cuda(), cout, k, emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(),
+                       out_dtype=torch.float32, tensor_core=True)
+    finally:
+        ops.enable_split_k(False)
+    assert got._stats_written is False
+    assert max_abs(nchw(got.cpu()), want) < 3e-3
+    # the same launch with split-K disabled by withholding the workspace is covered by the other tests; here check
+    # that a statistics request forces the single-pass path
+    tiles = torch.empty((max(1, B * hw * hw // 128), cout, 2), device="cuda")
+    if (hw * hw) % 128 == 0:
+        got2 = ops.conv(xd, wd, b.cuda(), cout, k, out_dtype=torch.float32, tensor_core=True, stats_out=tiles)
+        assert max_abs(nchw(got2.cpu()), F.conv2d(x, w, b, padding=k // 2)) < 3e-3
