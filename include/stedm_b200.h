@@ -24,10 +24,13 @@
 extern "C" {
 #endif
 
-#define STEDM_ABI_VERSION 1
+#define STEDM_ABI_VERSION 2
 
 #define STEDM_F32 0
 #define STEDM_BF16 1
+
+#define STEDM_ACT_NONE 0
+#define STEDM_ACT_GELU 1
 
 #define STEDM_ERR_ARG (-1)
 #define STEDM_ERR_CUDA (-2)
@@ -116,11 +119,15 @@ typedef struct stedm_conv_desc {
                           the upsampled one): weight = bf16 [cout][4*c0] with taps (a,b) reading (y+a-1+py, x+b-1+px),
                           `out` = NHWC [batch, 2*in_h, 2*in_w, cout] written at (2y+py, 2x+px) */
   int32_t phase;       /* tap_mode 1: py*2 + px */
+  int32_t act;         /* activation applied to (acc + bias + emb) before the residual add: STEDM_ACT_NONE, or
+                          STEDM_ACT_GELU = exact erf GELU (the Swin-V2 MLP, torchvision swin_transformer.py MLP/nn.GELU) */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,
  * upsample 0, c0 % 64 == 0, c1 % 64 == 0, cout % 16 == 0; output NHWC (bf16/fp32) or NCHW fp32 (the eps / image
- * heads with 3 real channels: cout = 16 zero-padded weight rows, cout_store = 3). */
+ * heads with 3 real channels: cout = 16 zero-padded weight rows, cout_store = 3).
+ * Plain GEMMs (ksize 1, one source: the token-major linear layers of the style encoder) relax this to c0 % 8 == 0
+ * (the last K slab is zero-filled by TMA) and cout % 32 == 0 (the last output-channel tile is partially stored). */
 int stedm_conv_tc(const stedm_conv_desc* d, void* stream);
 /* Bytes of `workspace` stedm_conv_tc would use for this descriptor (0 when it runs in a single pass; always 0 when
  * stats_out is set: the fused statistics need the single-pass epilogue). */
@@ -167,11 +174,49 @@ int stedm_nhwc_to_nchw_f32(const void* x, int dtype, float* out, int batch, int 
  * K8  Embedding path.
  * timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out[b] = [cos(t f) | sin(t f)], dim even. */
 int stedm_timestep_embedding(const long long* t, float* out, int batch, int dim, void* stream);
-/* out[b][n] = bias[n] + sum_k act(in[b][k]) * w[n][k], act = SiLU when silu_in != 0 (nn.Linear (out,in) layout).
- * Covers time_embed (openaimodel.py:530-534) and all emb_layers (openaimodel.py:231-237) in one launch when their
- * weights are stacked along n. */
-int stedm_linear(const float* in, const float* w, const float* bias, float* out, int batch, int k, int n,
-                 int silu_in, void* stream);
+/* out[b][n] = g(bias[n] + sum_k f(in[b][k]) * w[n][k]) (nn.Linear (out,in) layout); act is a bit set:
+ * 1 = f is SiLU, 2 = f is ReLU, 4 = g is ReLU.  Covers time_embed (openaimodel.py:530-534), all emb_layers
+ * (openaimodel.py:231-237) in one launch when their weights are stacked along n, the style encoder's head
+ * (s_zss_dm.py:20) and Agg_Linear's ReLU-Linear-ReLU-Linear-ReLU block (agg_blocks.py:15-19). */
+int stedm_linear(const float* in, const float* w, const float* bias, float* out, int batch, int k, int n, int act,
+                 void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Style encoder: torchvision swin_v2_t (networks/s_zss_dm.py:19-20, embedder.head = Linear(768, 512)) called by the
+ * aggregation blocks (networks/agg_blocks.py:24-33, 47-54, 66-75).  The token-major linear layers (qkv, proj, MLP,
+ * PatchMergingV2.reduction) run on stedm_conv_tc / stedm_conv_simt with ksize 1; these are the kernels between them.
+ * Token maps are NHWC [batch, h, w, c]; torchvision file = torchvision/models/swin_transformer.py.
+ */
+/* features.0 = Conv2d(3, embed, 4, stride 4) + Permute + LayerNorm(embed).  img: NHWC fp32 [batch, p, p, 3] (the
+ * layout style_imgs arrive in, modules/ldm_diffusion.py:51-60); w: fp32 [48][embed] with row (dy*4+dx)*3 + c;
+ * outputs [batch, p/4, p/4, embed] as fp32 and/or bf16 (either may be NULL). */
+int stedm_patch_embed_ln(const float* img, const float* w, const float* bias, const float* gamma, const float* beta,
+                         float eps, float* out_f32, void* out_bf16, int batch, int p, int patch, int embed,
+                         void* stream);
+/* y = [residual +] LayerNorm(x) * gamma + beta over rows of c channels (c % 8 == 0, c <= 1024): Swin-V2's
+ * res-post-norm x = x + norm(f(x)) (SwinTransformerBlockV2.forward), PatchMergingV2.norm, and sViT's pre-norms.
+ * x: [rows][c] fp32 or bf16; residual: fp32 or NULL; the result is written as fp32 and/or bf16. */
+int stedm_layernorm(const void* x, int x_dtype, const float* residual, const float* gamma, const float* beta, float eps,
+                    float* out_f32, void* out_bf16, long long rows, int c, void* stream);
+/* ShiftedWindowAttentionV2 core (shifted_window_attention with logit_scale): per 8x8 window and head,
+ * softmax(normalize(q).normalize(k)^T * logit_scale[head] + rel_bias[head] + shift mask) . v, with the cyclic shift,
+ * window partition and their inverses folded into the indexing.  qkv: [batch, h, w, 3*heads*32] = [q | k | v] (the
+ * qkv Linear's output, k bias already zeroed by the caller as torchvision does); logit_scale: fp32 [heads] =
+ * exp(min(param, log 100)); rel_bias: fp32 [heads][64][64] = 16*sigmoid(cpb_mlp(table))[index] (input independent,
+ * computed at weight-pack time); out: [batch, h, w, heads*32].  A map that is not a whole number of windows is
+ * zero-padded as torchvision does (F.pad before the qkv Linear): padded tokens act as keys with q, k, v = qkv_bias
+ * (fp32 [3*heads*32], k part zero; NULL = no bias) and are dropped from the output; no shift along an axis one window wide. */
+int stedm_window_attention(const void* qkv, int dtype, const float* logit_scale, const float* rel_bias,
+                           const float* qkv_bias, void* out, int batch, int h, int w, int heads, int head_dim,
+                           int window, int shift, void* stream);
+/* PatchMergingV2's gather (_patch_merging_pad): [batch, h, w, c] -> [batch, h/2, w/2, 4c] in x0|x1|x2|x3 order. */
+int stedm_patch_merge_gather(const void* x, void* out, int dtype, int batch, int h, int w, int c, void* stream);
+/* SwinTransformer.forward tail: norm -> permute -> avgpool -> flatten: out[b][c] = mean_t LN(x[b][t])[c].
+ * x: fp32 [batch][tokens][c], c % 32 == 0, c <= 1024. */
+int stedm_ln_meanpool(const float* x, const float* gamma, const float* beta, float eps, float* out, int batch,
+                      int tokens, int c, void* stream);
+/* Agg_Mean (mode 0) / Agg_Max (mode 1) over the n style images of a sample: fp32 [b][n][f] -> [b][f]. */
+int stedm_set_reduce(const float* x, float* out, int b, int n, int f, int mode, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * K12  VQ nearest-code lookup (taming VectorQuantizer2.forward via ldm/models/autoencoder.py:277):

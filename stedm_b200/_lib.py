@@ -20,7 +20,8 @@ class ConvDesc(C.Structure):
                 ("stats_out", vp), ("workspace", vp), ("workspace_bytes", C.c_int64), ("c0", C.c_int32), ("c1", C.c_int32), ("in_dtype", C.c_int32), ("batch", C.c_int32),
                 ("in_h", C.c_int32), ("in_w", C.c_int32), ("x1_batch", C.c_int32), ("ksize", C.c_int32),
                 ("stride", C.c_int32), ("upsample", C.c_int32), ("emb_stride", C.c_int32), ("res_dtype", C.c_int32),
-                ("out_dtype", C.c_int32), ("out_nchw", C.c_int32), ("cout", C.c_int32), ("cout_store", C.c_int32), ("tap_mode", C.c_int32), ("phase", C.c_int32)]
+                ("out_dtype", C.c_int32), ("out_nchw", C.c_int32), ("cout", C.c_int32), ("cout_store", C.c_int32), ("tap_mode", C.c_int32), ("phase", C.c_int32),
+                ("act", C.c_int32)]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -49,6 +50,12 @@ SIGNATURES = {
     "stedm_vq_nearest": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "stedm_spatial_rescale": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_image_to_uint8": [vp, vp, i32, i32, i32, vp],
+    "stedm_patch_embed_ln": [vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
+    "stedm_layernorm": [vp, i32, vp, vp, vp, f32, vp, vp, i64, i32, vp],
+    "stedm_window_attention": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "stedm_patch_merge_gather": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "stedm_ln_meanpool": [vp, vp, vp, f32, vp, i32, i32, i32, vp],
+    "stedm_set_reduce": [vp, vp, i32, i32, i32, i32, vp],
 }
 _RESTYPES = {"stedm_last_error": C.c_char_p, "stedm_conv_tc_workspace_bytes": C.c_longlong}
 
@@ -68,7 +75,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.stedm_abi_version() != 1:
+    if lib.stedm_abi_version() != 2:
         raise RuntimeError("libstedm_b200.so ABI version mismatch")
     _lib = lib
     return lib

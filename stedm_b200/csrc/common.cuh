@@ -46,6 +46,8 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 // exact-ish SiLU for the fp32 parity mode (expf, true division)
 __device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
+// exact (erf) GELU, nn.GELU() default: the Swin-V2 / sViT MLP activation
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

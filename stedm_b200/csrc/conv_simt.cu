@@ -26,7 +26,7 @@ struct SimtConvParams {
   int c0, c1, ctot;
   int batch, x1_batch, in_h, in_w, out_h, out_w;
   int ksize, stride, upsample, pad;
-  int emb_stride, res_dtype, out_dtype, out_nchw, cout;
+  int emb_stride, res_dtype, out_dtype, out_nchw, cout, act;
   int M, K;
 };
 
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(const SimtConvParams
       float v = acc[i][j];
       if (p.bias) v += p.bias[n];
       if (p.emb) v += p.emb[static_cast<size_t>(b) * p.emb_stride + n];
+      if (p.act == STEDM_ACT_GELU) v = gelu_erf(v);
       if (p.residual) {
         const size_t ro = static_cast<size_t>(m) * p.cout + n;
         v += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[ro]
@@ -266,7 +267,7 @@ extern "C" int stedm_conv_simt(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(uh % d->stride == 0 && uw % d->stride == 0, "conv_simt: odd spatial size with stride 2");
   p.ksize = d->ksize; p.stride = d->stride; p.upsample = d->upsample; p.pad = d->ksize / 2;
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype; p.out_nchw = d->out_nchw;
-  p.cout = d->cout;
+  p.cout = d->cout; p.act = d->act;
   const long long M = static_cast<long long>(d->batch) * p.out_h * p.out_w;
   STEDM_REQUIRE(M < (1LL << 31), "conv_simt: too many output pixels");
   p.M = static_cast<int>(M);

@@ -71,6 +71,7 @@ struct TcParams {
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
+  int act;               // STEDM_ACT_*: applied to acc + bias + emb, before the residual
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -263,6 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int n = n_base + c;
+        if (n >= p.cout) break;  // partially filled last channel tile (cout % BN != 0): nothing to store
         if (p.ksplit > 1) {  // split-K: raw fp32 partial tile -> workspace; splitk_finish_kernel applies the epilogue
           float4* wp = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.m_pad + m) * p.cout + n);
 #pragma unroll
@@ -283,6 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
             v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
+        }
+        if (p.act == STEDM_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
         }
         size_t o = static_cast<size_t>(m) * p.cout + n;
         if (p.tap_mode == 1) {  // this phase's pixel (y, x) lands at (2y + py, 2x + px) of the [B, 2H, 2W, C] output
@@ -412,6 +418,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
   for (int j = 0; j < 8; ++j) {
     if (p.bias) v[j] += p.bias[n + j];
     if (p.emb) v[j] += p.emb[static_cast<size_t>(b) * p.emb_stride + n + j];
+    if (p.act == STEDM_ACT_GELU) v[j] = gelu_erf(v[j]);
   }
   size_t o = static_cast<size_t>(m) * p.cout + n;
   if (p.tap_mode == 1) {
@@ -507,11 +514,16 @@ struct TcPlan {
 TcPlan tc_plan(long long M, int cout, int num_kb, bool want_stats) {
   TcPlan t;
   t.bn = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 16));
+  if (t.bn == 16 && cout % 32 == 0 && cout > 64) {
+    // widths like 96 / 288 (Swin-V2-T stage 1): a partially filled last tile beats 16-wide tiles; least padding wins
+    const int pad128 = (cout + 127) / 128 * 128, pad64 = (cout + 63) / 64 * 64;
+    t.bn = pad128 <= pad64 ? 128 : 64;
+  }
   t.cl = (t.bn >= 128 && M > TC_BM && g_tc_cluster_enabled) ? 2 : 1;
   t.pair = t.cl == 2 && g_tc_pair_enabled;
   const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
   const int m_groups = (m_tiles + t.cl - 1) / t.cl;
-  const int tiles = m_groups * (cout / t.bn);
+  const int tiles = m_groups * ((cout + t.bn - 1) / t.bn);
   const int max_clusters = tc_num_sms() * (t.bn >= 256 ? 1 : 2) / t.cl;
   t.m_pad = m_groups * t.cl * TC_BM;
   t.ksplit = 1;
@@ -535,7 +547,7 @@ extern "C" long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d) {
   if (d == nullptr || d->cout < 16 || d->cout % 16 != 0 || d->batch <= 0) return 0;
   const long long M = static_cast<long long>(d->batch) * d->in_h * d->in_w;
   const int taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
-  const int num_kb = taps * ((d->c0 + d->c1) / TC_BK);
+  const int num_kb = taps * ((d->c0 + d->c1 + TC_BK - 1) / TC_BK);
   return static_cast<long long>(tc_plan(M, d->cout, num_kb, d->stats_out != nullptr).ws_bytes);
 }
 
@@ -550,9 +562,13 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d->tap_mode == 0 || (d->tap_mode == 1 && d->phase >= 0 && d->phase < 4 && d->residual == nullptr &&
                                      d->out_nchw == 0 && d->c1 == 0),
                 "conv_tc: sub-pixel phase convolution takes one source, no residual, NHWC output, phase in [0,4)");
-  STEDM_REQUIRE(d->c0 > 0 && d->c0 % TC_BK == 0 && d->c1 % TC_BK == 0 && (d->c1 == 0 || d->x1),
-                "conv_tc: channel counts must be multiples of 64 (%d, %d)", d->c0, d->c1);
+  // plain GEMM (1 tap, one source): the last K slab may be partial — TMA zero-fills both operands beyond c0
+  const bool plain_gemm = d->ksize == 1 && d->tap_mode == 0 && d->c1 == 0;
+  STEDM_REQUIRE(d->c0 > 0 && (d->c0 % TC_BK == 0 || (plain_gemm && d->c0 % 8 == 0)) && d->c1 % TC_BK == 0 &&
+                    (d->c1 == 0 || d->x1),
+                "conv_tc: channel counts must be multiples of 64 (8 for a plain GEMM) (%d, %d)", d->c0, d->c1);
   STEDM_REQUIRE(d->cout >= 16 && d->cout % 16 == 0, "conv_tc: cout %d must be a multiple of 16", d->cout);
+  STEDM_REQUIRE(d->act == STEDM_ACT_NONE || d->act == STEDM_ACT_GELU, "conv_tc: unknown activation %d", d->act);
   const int H = d->in_h, W = d->in_w, B = d->batch;
   STEDM_REQUIRE(B > 0 && H > 0 && W > 0, "conv_tc: bad shape");
   // tile geometry: 128 consecutive pixels of the flattened (b, y, x) index must form a TMA box
@@ -603,10 +619,11 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   }
   const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
   // channel tile, 2-CTA cluster (cta_group::2 pair or weight multicast) and split-K plan
-  TcPlan plan = tc_plan(M, d->cout, taps * (ctot / TC_BK), d->stats_out != nullptr);
+  const int c_blks = (ctot + TC_BK - 1) / TC_BK;
+  TcPlan plan = tc_plan(M, d->cout, taps * c_blks, d->stats_out != nullptr);
   if (plan.ksplit > 1 && (d->workspace == nullptr || static_cast<size_t>(d->workspace_bytes) < plan.ws_bytes)) {
     plan.ksplit = 1;                        // no (or too small a) workspace: single pass
-    plan.kb_per_split = taps * (ctot / TC_BK);
+    plan.kb_per_split = taps * c_blks;
   }
   const int bn = plan.bn, cl = plan.cl;
   const bool pair = plan.pair;
@@ -621,17 +638,20 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.bias = d->bias; p.emb = d->emb; p.residual = d->residual; p.out = d->out;
   p.M = static_cast<int>(M); p.H = H; p.W = W; p.HW = H * W; p.cout = d->cout;
   p.taps = taps; p.ksize = d->ksize;
-  p.c0_blks = d->c0 / TC_BK; p.c_blks = ctot / TC_BK;
+  p.c0_blks = (d->c0 + TC_BK - 1) / TC_BK; p.c_blks = c_blks;
   p.x1_batch = x1b;
-  p.n_tiles = d->cout / bn;
+  p.n_tiles = (d->cout + bn - 1) / bn;
+  STEDM_REQUIRE(d->cout % bn == 0 || (d->cout % 32 == 0 && d->out_nchw == 0),
+                "conv_tc: cout %d with a partial last channel tile needs cout %% 32 == 0 and NHWC output", d->cout);
   p.ksplit = plan.ksplit; p.kb_per_split = plan.kb_per_split; p.m_pad = plan.m_pad;
   p.ws = static_cast<float*>(d->workspace);
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
+  p.act = d->act;
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {
-    STEDM_REQUIRE(bn >= 64 && d->out_nchw == 0 && (H * W) % TC_BM == 0,
+    STEDM_REQUIRE(bn >= 64 && d->cout % bn == 0 && d->out_nchw == 0 && (H * W) % TC_BM == 0,
                   "conv_tc: fused GroupNorm statistics need cout %% 64 == 0, NHWC output and H*W %% 128 == 0");
     const int m_tiles = static_cast<int>((M + TC_BM - 1) / TC_BM);
     p.stats_out = d->stats_out;

@@ -264,13 +264,13 @@ extern "C" int stedm_timestep_embedding(const long long* t, float* out, int batc
 constexpr int LIN_BT = 8;
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ out,
-                                                     int batch, int k, int n, int silu_in) {
+                                                     int batch, int k, int n, int act) {
   extern __shared__ float s_in[];  // [LIN_BT][k]
   const int b0 = blockIdx.y * LIN_BT;
   const int nb = min(LIN_BT, batch - b0);
   for (int i = threadIdx.x; i < nb * k; i += blockDim.x) {
     float v = in[static_cast<size_t>(b0) * k + i];
-    s_in[i] = silu_in ? silu_precise(v) : v;
+    s_in[i] = (act & 1) ? silu_precise(v) : ((act & 2) ? fmaxf(v, 0.f) : v);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,17 +289,31 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
 #pragma unroll
   for (int j = 0; j < LIN_BT; ++j) {
     const float v = warp_sum(acc[j]);
-    if (lane == 0 && j < nb) out[static_cast<size_t>(b0 + j) * n + col] = v + (bias ? bias[col] : 0.f);
+    if (lane == 0 && j < nb) {
+      const float y = v + (bias ? bias[col] : 0.f);
+      out[static_cast<size_t>(b0 + j) * n + col] = (act & 4) ? fmaxf(y, 0.f) : y;
+    }
   }
 }
 
 extern "C" int stedm_linear(const float* in, const float* w, const float* bias, float* out, int batch, int k, int n,
-                            int silu_in, void* stream) {
+                            int act, void* stream) {
   STEDM_REQUIRE(in && w && out && batch > 0 && k > 0 && n > 0, "linear: bad argument");
-  STEDM_REQUIRE(static_cast<size_t>(LIN_BT) * k * 4 <= 48 * 1024, "linear: k too large for the staging buffer");
+  const size_t smem = static_cast<size_t>(LIN_BT) * k * 4;
+  STEDM_REQUIRE(smem <= 200 * 1024, "linear: k = %d too large for the staging buffer", k);
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        set_error("linear: cannot raise the dynamic shared memory limit");
+        return ERR_CUDA;
+      }
+      configured = true;
+    }
+  }
   dim3 grid((n + 7) / 8, (batch + LIN_BT - 1) / LIN_BT);
   linear_kernel<<<grid, 256, static_cast<size_t>(LIN_BT) * k * 4, static_cast<cudaStream_t>(stream)>>>(
-      in, w, bias, out, batch, k, n, silu_in);
+      in, w, bias, out, batch, k, n, act);
   return check_launch("linear");
 }
 

@@ -1,17 +1,15 @@
 """Style aggregation blocks, mirroring networks/agg_blocks.py of the reference (Agg_Linear :6-35, Agg_Max :38-54,
 Agg_Mean :57-75, Agg_None :78-85) with the same registered names (``_embedder`` and ``embedder``).
 
-The style encoder itself is torchvision's ``swin_v2_t`` (a library call in the reference too, s_zss_dm.py:19-20);
-it runs once per conditioning set, outside the DDIM loop (~0.1 % of the path's FLOPs) and is a
-"next" row of the scope table.  The (b n) h w c -> c h w shuffles and the reductions over n are plain torch views.
+The embedder module (torchvision ``swin_v2_t`` with a 768->512 head, s_zss_dm.py:19-20) only OWNS the parameters, so
+reference checkpoints load by name; its forward is executed natively by stedm_b200.style_engine.StyleEncoderRunner
+(patch embedding, window attention, LayerNorm kernels + tcgen05 GEMMs) straight from the ``b n h w c`` style tensor —
+the reference's ``(b n) c h w`` permute is folded into the patch-embedding kernel — and the reduction over the n
+style images of a sample is stedm_set_reduce.  No CPU or torchvision fallback: CUDA tensors only.
 """
 import torch
 
-
-def _embed(embedder, style_imgs):
-    b, n, h, w, c = style_imgs.shape
-    imgs = style_imgs.permute(0, 1, 4, 2, 3).reshape(b * n, c, h, w)
-    return embedder(imgs).reshape(b, n, -1)
+from .. import ops
 
 
 class _Agg(torch.nn.Module):
@@ -20,16 +18,56 @@ class _Agg(torch.nn.Module):
         self._sampling_cfg = sampling_cfg
         self._embedder = embedder
         self.register_module("embedder", self._embedder)
+        self.precision = "bf16"
+        self._runner = None
+
+    # ---- packed-weight lifecycle (same contract as UNetModel / VQModelInterface) -------------------------
+    def invalidate_packed(self):
+        self._runner = None
+
+    def _apply(self, fn, *a, **k):
+        self._runner = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._runner = None
+        return super().load_state_dict(*a, **k)
+
+    def set_precision(self, precision):
+        if precision != self.precision:
+            self.precision, self._runner = precision, None
+
+    def _versions(self):
+        return tuple(p._version for p in self._embedder.parameters())
+
+    def runner(self):
+        ver = self._versions()
+        if self._runner is None or self._runner_versions != ver:
+            from ..style_engine import StyleEncoderRunner
+            if not next(self._embedder.parameters()).is_cuda:
+                raise RuntimeError("the style encoder runs only on a CUDA (sm_100a) device: move the model with "
+                                   ".cuda() first — there is no CPU path")
+            self._runner = StyleEncoderRunner(self._embedder, self.precision)
+            self._runner_versions = ver
+        return self._runner
+
+    def embed(self, style_imgs):
+        """'b n h w c' style images -> per-image features [b, n, 512] (agg_blocks.py:26-30, 49-52, 68-72)."""
+        b, n, h, w, c = style_imgs.shape
+        if not style_imgs.is_cuda:
+            raise RuntimeError("stedm_b200 style encoder takes CUDA tensors only (no CPU fallback)")
+        feats = self.runner()(style_imgs.reshape(b * n, h, w, c))
+        return feats.view(b, n, -1)
 
 
 class Agg_Mean(_Agg):
     def forward(self, style_imgs):
-        return torch.mean(_embed(self._embedder, style_imgs), dim=1)
+        return ops.set_reduce(self.embed(style_imgs), "mean")
 
 
 class Agg_Max(_Agg):
     def forward(self, style_imgs):
-        return torch.max(_embed(self._embedder, style_imgs), dim=1)[0]
+        return ops.set_reduce(self.embed(style_imgs), "max")
 
 
 class Agg_Linear(_Agg):
@@ -41,8 +79,13 @@ class Agg_Linear(_Agg):
         self.register_module("linear_block", self._linear_block)
 
     def forward(self, style_imgs):
-        f = _embed(self._embedder, style_imgs)
-        return self._linear_block(f.reshape(f.shape[0], -1))
+        f = self.embed(style_imgs)
+        f = f.reshape(f.shape[0], -1)
+        l1, l3 = self._linear_block[1], self._linear_block[3]
+        # ReLU -> Linear -> ReLU -> Linear -> ReLU (agg_blocks.py:15-19) on the K8 linear kernel
+        h = ops.linear(f, l1.weight.detach().float().contiguous(), l1.bias.detach().float().contiguous(), act_in="relu")
+        return ops.linear(h, l3.weight.detach().float().contiguous(), l3.bias.detach().float().contiguous(),
+                          act_in="relu", relu_out=True)
 
 
 class Agg_None(torch.nn.Module):

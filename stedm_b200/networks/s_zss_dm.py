@@ -35,6 +35,13 @@ class S_ZSS_DM(LatentDiffusion):
             raise Exception("Unkown aggregation function!")
         self.register_module("agg_block", self._agg_block)
         self._agg_block.eval()
+        if hasattr(self._agg_block, "set_precision"):
+            self._agg_block.set_precision(self.precision)
+
+    def set_precision(self, precision):
+        super().set_precision(precision)
+        if hasattr(self._agg_block, "set_precision"):
+            self._agg_block.set_precision(precision)
 
     def _style_features(self, style_imgs):
         """Aggregated style vector.  predict_step's unconditional branch feeds a CONSTANT image (-2 everywhere,
@@ -42,7 +49,7 @@ class S_ZSS_DM(LatentDiffusion):
         sample's style set per (shape, weights) and the row is broadcast — identical values, no recomputation per batch."""
         first = style_imgs.reshape(-1)[0]
         if style_imgs.numel() > 0 and bool((style_imgs == first).all()):
-            key = (tuple(style_imgs.shape[1:]), float(first), self._agg_version())
+            key = (tuple(style_imgs.shape[1:]), float(first), self._agg_version(), self.precision)
             if getattr(self, "_const_style_cache", (None, None))[0] != key:
                 self._const_style_cache = (key, self._agg_block(style_imgs[:1]))
             return self._const_style_cache[1].expand(style_imgs.shape[0], -1).contiguous()

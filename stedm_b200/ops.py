@@ -136,7 +136,8 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
+         act=0):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
     _cuda(x0, x1, weight, bias, residual)
@@ -164,6 +165,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.out_dtype, d.out_nchw, d.cout = _DT[out.dtype], 1 if out_nchw else 0, cout
     d.cout_store = cout_store if out_nchw else 0
     d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
+    d.act = act
     out._stats_written = stats_out is not None
     if tensor_core and SPLIT_K[0] and b * h * w <= SPLITK_MAX_PIXELS:
         # small launches (few output tiles, deep K): split-K over the idle SMs through a caller-owned workspace.
@@ -289,14 +291,89 @@ def timestep_embedding(t, dim):
     return out
 
 
-def linear(x, weight, bias, silu_in=False):
+def linear(x, weight, bias, silu_in=False, act_in=None, relu_out=False):
+    """g(bias + f(x) @ weight.T): f = SiLU (``silu_in``) / ReLU (``act_in='relu'``), g = ReLU (``relu_out``)."""
     _cuda(x, weight, bias)
+    act = (1 if silu_in else 0) | (2 if act_in == "relu" else 0) | (4 if relu_out else 0)
     assert x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
     b, k = x.shape
     n = weight.shape[0]
     assert weight.shape[1] == k
     out = torch.empty((b, n), device=x.device, dtype=torch.float32)
-    _call("stedm_linear", _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), b, k, n, 1 if silu_in else 0, _stream())
+    _call("stedm_linear", _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), b, k, n, act, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ style encoder
+ACT_NONE, ACT_GELU = 0, 1
+
+
+def patch_embed_ln(img, w, bias, gamma, beta, eps, want_f32=True, want_bf16=False):
+    """features.0 of swin_v2_t on NHWC fp32 images [B, P, P, 3]; w fp32 [48][E].  Returns (fp32 | None, bf16 | None)."""
+    _cuda(img, w, bias, gamma, beta)
+    assert img.dtype == torch.float32 and img.dim() == 4 and img.shape[3] == 3 and img.shape[1] == img.shape[2]
+    b, p = img.shape[0], img.shape[1]
+    e = w.shape[1]
+    assert w.shape[0] == 48 and w.dtype == torch.float32
+    shape = (b, p // 4, p // 4, e)
+    of = torch.empty(shape, device=img.device, dtype=torch.float32) if want_f32 else None
+    ob = torch.empty(shape, device=img.device, dtype=torch.bfloat16) if want_bf16 else None
+    _call("stedm_patch_embed_ln", _ptr(img), _ptr(w), _ptr(bias), _ptr(gamma), _ptr(beta), float(eps), _ptr(of),
+          _ptr(ob), b, p, 4, e, _stream())
+    return of, ob
+
+
+def layernorm(x, residual, gamma, beta, eps, want_f32=True, want_bf16=False):
+    """[residual +] LayerNorm(x) over the last dim; x fp32/bf16, residual fp32.  Returns (fp32 | None, bf16 | None)."""
+    _cuda(x, residual, gamma, beta)
+    c = x.shape[-1]
+    rows = x.numel() // c
+    assert residual is None or (residual.dtype == torch.float32 and residual.shape == x.shape)
+    of = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
+    ob = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _call("stedm_layernorm", _ptr(x), _DT[x.dtype], _ptr(residual), _ptr(gamma), _ptr(beta), float(eps), _ptr(of),
+          _ptr(ob), rows, c, _stream())
+    return of, ob
+
+
+def window_attention(qkv, logit_scale, rel_bias, qkv_bias, heads, shift, window=8):
+    """ShiftedWindowAttentionV2 core on qkv [B, H, W, 3*heads*32] -> [B, H, W, heads*32] (same dtype)."""
+    _cuda(qkv, logit_scale, rel_bias, qkv_bias)
+    b, h, w, c3 = qkv.shape
+    hd = c3 // (3 * heads)
+    assert c3 == 3 * heads * hd and rel_bias.shape == (heads, window * window, window * window)
+    assert logit_scale.numel() == heads and logit_scale.dtype == torch.float32 and rel_bias.dtype == torch.float32
+    out = torch.empty((b, h, w, heads * hd), device=qkv.device, dtype=qkv.dtype)
+    _call("stedm_window_attention", _ptr(qkv), _DT[qkv.dtype], _ptr(logit_scale), _ptr(rel_bias), _ptr(qkv_bias),
+          _ptr(out), b, h, w, heads, hd, window, shift, _stream())
+    return out
+
+
+def patch_merge_gather(x):
+    _cuda(x)
+    b, h, w, c = x.shape
+    out = torch.empty((b, h // 2, w // 2, 4 * c), device=x.device, dtype=x.dtype)
+    _call("stedm_patch_merge_gather", _ptr(x), _ptr(out), _DT[x.dtype], b, h, w, c, _stream())
+    return out
+
+
+def ln_meanpool(x, gamma, beta, eps):
+    """mean over tokens of LayerNorm(x): fp32 [B, T, C] -> [B, C]."""
+    _cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.dim() == 3
+    b, t, c = x.shape
+    out = torch.empty((b, c), device=x.device, dtype=torch.float32)
+    _call("stedm_ln_meanpool", _ptr(x), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), b, t, c, _stream())
+    return out
+
+
+def set_reduce(x, mode):
+    """mean ('mean') or max ('max') over dim 1 of fp32 [B, N, F]."""
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 3
+    b, n, f = x.shape
+    out = torch.empty((b, f), device=x.device, dtype=torch.float32)
+    _call("stedm_set_reduce", _ptr(x), _ptr(out), b, n, f, {"mean": 0, "max": 1}[mode], _stream())
     return out
 
 

@@ -40,8 +40,10 @@ def timestep_embedding(t, dim):
     return torch.cat([torch.cos(a), torch.sin(a)], -1)
 
 
-def linear(x, w, b, silu_in=False):
-    return F.linear(F.silu(x) if silu_in else x, w, b)
+def linear(x, w, b, silu_in=False, act_in=None, relu_out=False):
+    x = F.silu(x) if silu_in else (F.relu(x) if act_in == "relu" else x)
+    y = F.linear(x, w, b)
+    return F.relu(y) if relu_out else y
 
 
 def gn_stats(x0, x1, stats=None):
@@ -69,7 +71,8 @@ def im2col_3x3_s2(x):
 
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
-         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None):
+         upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
+         act=0):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
     if up_phase is not None:   # one 2x2 sub-pixel phase: taps (a,b) read (y+a-1+py, x+b-1+px); write (2y+py, 2x+px)
@@ -89,6 +92,8 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     y = F.conv2d(xin, w, bias, stride=stride, padding=ksize // 2)
     if emb is not None:
         y = y + emb[:, :, None, None]        # (1, C) broadcasts like the kernel's row stride 0
+    if act == 1:
+        y = F.gelu(y)
     if residual is not None:
         y = y + _nchw(residual.float())
     if out_nchw:
@@ -121,3 +126,75 @@ def vq_nearest(z, codebook, return_indices=False):
     idx = torch.argmin(d, 1)
     zq = codebook[idx].reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
     return (zq, idx.int()) if return_indices else zq
+
+
+# ---------------------------------------------------------------------------------------------- style encoder
+ACT_NONE, ACT_GELU = 0, 1
+
+
+def _two(y, want_f32, want_bf16):
+    return (y.float() if want_f32 else None), (y.to(torch.bfloat16) if want_bf16 else None)
+
+
+def patch_embed_ln(img, w, bias, gamma, beta, eps, want_f32=True, want_bf16=False):
+    b, p = img.shape[0], img.shape[1]
+    t = p // 4
+    patches = img.reshape(b, t, 4, t, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(b, t, t, 48)     # (dy, dx, c) order
+    y = F.layer_norm(patches @ w + bias, (w.shape[1],), gamma, beta, eps)
+    return _two(y, want_f32, want_bf16)
+
+
+def layernorm(x, residual, gamma, beta, eps, want_f32=True, want_bf16=False):
+    y = F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps)
+    if residual is not None:
+        y = y + residual
+    return _two(y, want_f32, want_bf16)
+
+
+def window_attention(qkv, logit_scale, rel_bias, qkv_bias, heads, shift, window=8):
+    """Independent restatement (roll / partition / mask built the torchvision way) of what the kernel folds into indexing."""
+    b, h, w, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    x = qkv.float()
+    ph, pw = -(-h // window) * window, -(-w // window) * window
+    if (ph, pw) != (h, w):   # padded tokens carry the qkv bias (zero input through the Linear)
+        full = qkv_bias.float().expand(b, ph, pw, c3).clone()
+        full[:, :h, :w] = x
+        x = full
+    sy, sx = (0 if ph <= window else shift), (0 if pw <= window else shift)
+    if sy or sx:
+        x = torch.roll(x, (-sy, -sx), (1, 2))
+    nw = (ph // window) * (pw // window)
+    x = x.view(b, ph // window, window, pw // window, window, c3).permute(0, 1, 3, 2, 4, 5).reshape(b * nw, window * window, c3)
+    q, k, v = x.reshape(b * nw, window * window, 3, heads, d).permute(2, 0, 3, 1, 4)
+    attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1) * logit_scale.view(1, heads, 1, 1)
+    attn = attn + rel_bias[None]
+    if sy or sx:
+        m = torch.zeros(ph, pw)
+        cnt = 0
+        for hs in ((0, -window), (-window, -sy), (-sy, None)):
+            for ws_ in ((0, -window), (-window, -sx), (-sx, None)):
+                m[hs[0]:hs[1], ws_[0]:ws_[1]] = cnt
+                cnt += 1
+        m = m.view(ph // window, window, pw // window, window).permute(0, 2, 1, 3).reshape(nw, window * window)
+        m = m[:, None, :] - m[:, :, None]
+        m = torch.where(m != 0, torch.tensor(-100.0), torch.tensor(0.0))
+        attn = (attn.view(b, nw, heads, window * window, window * window) + m[None, :, None]).view(-1, heads, window * window, window * window)
+    o = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(b * nw, window * window, c)
+    o = o.view(b, ph // window, pw // window, window, window, c).permute(0, 1, 3, 2, 4, 5).reshape(b, ph, pw, c)
+    if sy or sx:
+        o = torch.roll(o, (sy, sx), (1, 2))
+    return o[:, :h, :w].contiguous().to(qkv.dtype)
+
+
+def patch_merge_gather(x):
+    return torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1).contiguous()
+
+
+def ln_meanpool(x, gamma, beta, eps):
+    return F.layer_norm(x, (x.shape[-1],), gamma, beta, eps).mean(1)
+
+
+def set_reduce(x, mode):
+    return x.mean(1) if mode == "mean" else x.max(1)[0]

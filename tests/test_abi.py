@@ -22,12 +22,12 @@ def test_library_exports_header_symbols():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
     lib.stedm_abi_version.restype = ctypes.c_int
-    assert lib.stedm_abi_version() == 1
+    assert lib.stedm_abi_version() == 2
 
 
 def test_conv_desc_layout_matches_header():
     from stedm_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 18 * 4  # 9 pointers, int64, 18 int32
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 20 * 4  # 9 pointers, int64, 19 int32 (+4 B tail padding)
 
 
 def test_sass_is_blackwell_native():

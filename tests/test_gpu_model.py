@@ -45,10 +45,10 @@ def test_conditioning_matches_reference():
     z, c = m._model.get_input(batch, "image")
     assert tuple(z.shape) == (2, 3, 32, 32)
     assert max_abs(c["c_concat"][0], g["c_concat"]) < 1e-6
-    assert max_abs(c["c_crossattn"][0], g["c_crossattn"]) < 2e-3     # torchvision Swin on GPU vs CPU (library code)
+    assert max_abs(c["c_crossattn"][0], g["c_crossattn"]) < FP32_EPS_BAR   # native fp32 style encoder vs the reference's
     unc = dict(batch, style_imgs=torch.zeros_like(batch["style_imgs"]) - 2)
     _, cu = m._model.get_input(unc, "image")
-    assert max_abs(cu["c_crossattn"][0], g["uc_crossattn"]) < 2e-3
+    assert max_abs(cu["c_crossattn"][0], g["uc_crossattn"]) < FP32_EPS_BAR
 
 
 @pytest.mark.parametrize("t", [981, 481, 1])
@@ -242,9 +242,11 @@ def test_latent128_eps_and_decode_vs_oracle():
     assert tuple(img.shape) == (1, 3, 512, 512) and p >= PSNR_BAR
 
 
-def test_multi_style_aggregation_her2_shape():
-    """BASELINE configs[2]: N = 10 style patches per sample aggregated by Agg_Mean (conf/style_sampling/mp.yaml)."""
-    m = build_model(32, n_style=10, precision="bf16")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_multi_style_aggregation_her2_shape(precision):
+    """BASELINE configs[2]: N = 10 style patches per sample aggregated by Agg_Mean (conf/style_sampling/mp.yaml); the
+    style encoder runs natively (stedm_b200.style_engine) and is compared with the oracle's torchvision swin_v2_t."""
+    m = build_model(32, n_style=10, precision=precision)
     model = m._model
     sd = oracle_state_dict(model)
     seg, style, _ = O.synthetic_batch(2, 128, 10, seed=3)
@@ -253,7 +255,13 @@ def test_multi_style_aggregation_her2_shape():
     with torch.no_grad():
         want = O.get_conditioning(sd, seg, style)
     assert tuple(c["c_crossattn"][0].shape) == (2, 512)
-    assert max_abs(c["c_crossattn"][0], want["c_crossattn"][0]) < 2e-3
+    err = max_abs(c["c_crossattn"][0], want["c_crossattn"][0])
+    if precision == "fp32":
+        assert err < FP32_EPS_BAR, err
+    else:
+        rel = err / float(want["c_crossattn"][0].abs().max())
+        print(f"bf16 style feature (N=10) rel err {rel:.3e}")
+        assert rel < BF16_EPS_BAR, rel
     assert max_abs(c["c_concat"][0], want["c_concat"][0]) < 1e-6
 
 

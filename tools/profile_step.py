@@ -1,7 +1,7 @@
 """Profiling driver: one guided DDIM step (or one VQ decode) at the bench workload, bracketed by
 cudaProfilerStart/Stop so that `ncu --profile-from-start off` sees exactly that step.
 
-    python tools/profile_step.py [--batch 64] [--latent 64] [--what unet|decode] [--precision bf16]
+    python tools/profile_step.py [--batch 64] [--latent 64] [--what unet|decode|style] [--precision bf16]
 """
 import argparse
 import os
@@ -35,7 +35,9 @@ def main():
         step = lambda: sampler.p_sample_ddim(x_T, c, ts, index=24, unconditional_guidance_scale=1.5,
                                              unconditional_conditioning=cu)
         dec = lambda: model.decode_first_stage(x_T * 60)
-        fn = step if a.what == "unet" else dec
+        sty_imgs = (torch.rand(a.batch, 1, 4 * a.latent, 4 * a.latent, 3, device=dev) * 2 - 1)
+        sty = lambda: model._agg_block(sty_imgs)      # the native style encoder + aggregation on `batch` images
+        fn = {"unet": step, "decode": dec, "style": sty}[a.what]
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
