@@ -143,16 +143,22 @@ int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_a, int dtyp
                     long long b_sb, long long b_sh, long long c_sb, long long c_sh, float alpha, void* stream);
 /* Row softmax of scale * x over the last dimension of a [rows][cols] fp32 matrix (openaimodel.py:392, model.py:189-190).
  * x is used as scratch; the probabilities go to `out` (fp32 or bf16 [rows][cols]); out == NULL => in place. */
-int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale, void* stream);
+/* mask_diag_period = T > 0: the rows are the queries of [.., T, T] score matrices and column row % T (the token itself)
+ * is excluded — sViT's LSA diagonal mask (networks/vit_set.py:52-54); 0 = plain softmax. */
+int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale,
+                       int mask_diag_period, void* stream);
 
 /* K5  Fused flash-style self-attention on tcgen05 (S and O accumulators in TMEM, online fp32 softmax, P staged as
  * bf16 in shared memory): the U-Net AttentionBlock, head_dim 64 or 128, any token count.
  * q, k, v: bf16, token-major: element (b, h, t, c) at base + b*stride_b + h*stride_h + t*stride_t + c (strides in
  * elements, multiples of 8).  out: bf16 [batch][tokens][heads*head_dim].  scale multiplies q.k (= ch^-1/2).
  * Replaces QKVAttentionLegacy.forward (openaimodel.py:378-394): (q*ch^-1/4).(k*ch^-1/4), fp32 softmax, .v */
+/* out_stride_b: elements between samples of `out` (0 => tokens*heads*head_dim, dense).  mask_diag != 0: a token does
+ * not attend to itself — sViT's LSA (networks/vit_set.py:44-60: softmax(q.k^T * exp(temperature) with the diagonal
+ * masked) . v), head_dim 64, scale = exp(temperature). */
 int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int tokens,
                        int head_dim, long long stride_b, long long stride_h, long long stride_t, float scale,
-                       void* stream);
+                       long long out_stride_b, int mask_diag, void* stream);
 
 
 /* ----------------------------------------------------------------------------------------------------
@@ -217,6 +223,20 @@ int stedm_ln_meanpool(const float* x, const float* gamma, const float* beta, flo
                       int tokens, int c, void* stream);
 /* Agg_Mean (mode 0) / Agg_Max (mode 1) over the n style images of a sample: fp32 [b][n][f] -> [b][f]. */
 int stedm_set_reduce(const float* x, float* out, int b, int n, int f, int mode, void* stream);
+
+/* style_agg=svit (networks/vit_set.py sViT, built by networks/s_zss_dm.py:31-38): its Linear layers run on
+ * stedm_conv_tc / stedm_conv_simt, the LayerNorms on stedm_layernorm, LSA on stedm_attention_tc (mask_diag) or
+ * stedm_gemm_simt + stedm_softmax_rows (mask_diag_period); these are the remaining pieces.
+ * SPT patch tokens (vit_set.py:82-107): img = style images NHWC fp32 [batch][ns][p_img][p_img][3]; out = fp32
+ * [batch][(p_img/patch)^2][patch*patch*3*ns], patch element (p1, p2, c*ns + s) = img[b][s][h*patch+p1][w*patch+p2][c]. */
+int stedm_spt_patchify(const float* img, float* out, int batch, int ns, int p_img, int patch, void* stream);
+/* Token sequence of sViT.forward (vit_set.py:176-190): out fp32 [batch][t_pad][dim], row 0 = cls + pos[0], row 1 =
+ * pos[1] (t_emb is None on the sampling path -> zeros), row 2+i = patches[b][i] + pos[2+i], rows >= n_patches+2 zero
+ * (t_pad rounds the sequence up to whole 128-row GEMM tiles).  patches: [batch][n_patches][dim] fp32 or bf16. */
+int stedm_svit_assemble(const void* patches, int dtype, const float* cls, const float* pos, float* out, int batch,
+                        int n_patches, int t_pad, int dim, void* stream);
+/* pool = 'mean' (vit_set.py:195-196): mean over the first `tokens` rows of each sample of fp32 [batch][t_pad][c]. */
+int stedm_token_mean(const float* x, float* out, int batch, int tokens, int t_pad, int c, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * K12  VQ nearest-code lookup (taming VectorQuantizer2.forward via ldm/models/autoencoder.py:277):

@@ -3,7 +3,7 @@ on fixture weights, and assert that oracle/stedm_oracle.py reproduces every tens
 
 Run once in the build container (the reference cannot travel to the GPU box):
 
-    python -m oracle.make_golden [--only small|c1|sched]
+    python -m oracle.make_golden [--only small|c1|sched|svit]
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -166,6 +166,37 @@ def gen_sched():
     print("[sched] wrote sched.npz; len(ts_128) =", len(out["ts_128"]))
 
 
+SVIT_CASES = {  # name -> (image size, style images per sample, pool, seed); conf/style_agg/svit.yaml otherwise
+    "svit_p64_n2_mean": (64, 2, "mean", 11),
+    "svit_p128_n1_cls": (128, 1, "cls", 12),
+}
+SVIT_KW = dict(patch_size=8, num_classes=512, dim=256, depth=6, heads=12, mlp_dim=256, channels=3, dropout=0.1,
+               emb_dropout=0.1, t_dim=256)
+
+
+@torch.no_grad()
+def gen_svit():
+    """style_agg=svit: the reference's networks/vit_set.py sViT (as networks/s_zss_dm.py:31-38 builds it) on fixture
+    weights; asserts oracle.svit_aggregate == reference and stores the [B, 512] style vectors."""
+    ref_shims.install()
+    from networks.vit_set import sViT
+    out = {}
+    for name, (P, ns, pool, seed) in SVIT_CASES.items():
+        holder = torch.nn.Module()
+        holder.agg_block = sViT(image_size=P, ns=ns, pool=pool, **SVIT_KW).eval()
+        apply_fixture_weights(holder, seed=0)
+        sd = {k: v.detach().float() for k, v in holder.state_dict().items()}
+        _, style, _ = O.synthetic_batch(2, P, ns, seed)
+        want = holder.agg_block(style)
+        got = O.svit_aggregate(sd, style, heads=SVIT_KW["heads"], patch=SVIT_KW["patch_size"], pool=pool)
+        d = maxdiff(want, got)
+        print(f"[{name}] oracle vs reference sViT: max|d| = {d:.3e} (|out|max {float(want.abs().max()):.3f})")
+        assert d < 1e-5
+        out[name] = want.numpy()
+    np.savez_compressed(os.path.join(GOLD, "svit.npz"), **out)
+    print("[svit] wrote svit.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -173,6 +204,8 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if a.only in ("all", "sched"):
         gen_sched()
+    if a.only in ("all", "svit"):
+        gen_svit()
     if a.only in ("all", "small"):
         # B=2, latent 32 (128^2 image), two style images per sample (exercises Agg_Mean), full DDIM-50
         gen_case("small_b2_l32", B=2, L=32, n_style=2, S=50, full_steps=True, seed=0, store_f16_image=False)

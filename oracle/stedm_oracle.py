@@ -242,6 +242,45 @@ def agg_mean(sd, style_bnhwc):
 
 
 @torch.no_grad()
+def svit_aggregate(sd, style_bnhwc, heads, patch=8, pool="mean", prefix="agg_block."):
+    """networks/vit_set.py sViT.forward (:163-208) with t_emb = None, c_old = None, eval mode (dropouts off), built by
+    networks/s_zss_dm.py:31-38 for ``style_agg=svit``.  SPT (:82-107): the ns images of a sample are stacked along
+    channels (channel c*ns + s), cut into patch x patch patches flattened as (p1 p2 c), LayerNorm, Linear.  Tokens
+    = [cls, zero time token, patches] + pos_embedding (:176-188).  Transformer (:67-80): x = LSA(LN(x)) + x;
+    x = FF(LN(x)) + x.  LSA (:44-60): softmax over (q k^T * exp(temperature)) with the diagonal masked out; dim_head 64.
+    Pooling (:195-205) and mlp_head = LayerNorm + Linear (:147-150)."""
+    g = lambda k: sd[prefix + k]
+    x = style_bnhwc.float().permute(0, 1, 4, 2, 3)                                  # b ns c H W   (:165)
+    b, ns, ch, H, W = x.shape
+    x = x.permute(0, 2, 1, 3, 4).reshape(b, ch * ns, H, W)                          # (:104-105)
+    hh, ww = H // patch, W // patch
+    x = x.reshape(b, ch * ns, hh, patch, ww, patch).permute(0, 2, 4, 3, 5, 1).reshape(b, hh * ww, patch * patch * ch * ns)
+    tp = "to_patch_embedding.to_patch_tokens."
+    x = F.layer_norm(x, (x.shape[-1],), g(tp + "1.weight"), g(tp + "1.bias"), 1e-5)
+    x = F.linear(x, g(tp + "2.weight"), g(tp + "2.bias"))
+    n, dim = x.shape[1], x.shape[2]
+    x = torch.cat([g("cls_token").expand(b, 1, dim), torch.zeros(b, 1, dim), x], 1) + g("pos_embedding")[:, :n + 2]
+    depth = 0
+    while (prefix + f"transformer.layers.{depth}.0.norm.weight") in sd:
+        depth += 1
+    for i in range(depth):
+        p = f"transformer.layers.{i}."
+        y = F.layer_norm(x, (dim,), g(p + "0.norm.weight"), g(p + "0.norm.bias"), 1e-5)
+        q, k, v = F.linear(y, g(p + "0.fn.to_qkv.weight")).chunk(3, dim=-1)
+        sp = lambda t: t.reshape(b, n + 2, heads, -1).permute(0, 2, 1, 3)
+        q, k, v = sp(q), sp(k), sp(v)
+        dots = q @ k.transpose(-1, -2) * g(p + "0.fn.temperature").exp()
+        dots = dots.masked_fill(torch.eye(n + 2, dtype=torch.bool), -torch.finfo(dots.dtype).max)
+        o = (torch.softmax(dots, -1) @ v).permute(0, 2, 1, 3).reshape(b, n + 2, -1)
+        x = F.linear(o, g(p + "0.fn.to_out.0.weight"), g(p + "0.fn.to_out.0.bias")) + x
+        y = F.layer_norm(x, (dim,), g(p + "1.norm.weight"), g(p + "1.norm.bias"), 1e-5)
+        y = F.gelu(F.linear(y, g(p + "1.fn.net.0.weight"), g(p + "1.fn.net.0.bias")))
+        x = F.linear(y, g(p + "1.fn.net.3.weight"), g(p + "1.fn.net.3.bias")) + x
+    x = x.mean(1) if pool == "mean" else x[:, 0]
+    x = F.layer_norm(x, (dim,), g("mlp_head.0.weight"), g("mlp_head.0.bias"), 1e-5)
+    return F.linear(x, g("mlp_head.1.weight"), g("mlp_head.1.bias"))
+
+
 def get_conditioning(sd, seg_bhwc, style_bnhwc):
     """S_ZSS_DM.get_input, networks/s_zss_dm.py:45-60, minus the discarded VAE encode of the image."""
     seg = seg_bhwc.permute(0, 3, 1, 2).contiguous().float()            # ddpm.py:332-338

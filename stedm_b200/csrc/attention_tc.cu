@@ -28,6 +28,8 @@ struct AttnParams {
   __nv_bfloat16* out;
   int tokens, heads, head_dim;
   float scale_log2e;  // scale * log2(e)
+  long long out_stride_b;  // elements between samples of `out`
+  int mask_diag;      // 1: a token does not attend to itself (sViT's LSA, networks/vit_set.py:52-54)
 };
 
 // smem descriptor for an MN-major SW128 operand whose K rows are 128 B apart (as TMA writes a [rows][64] bf16 box):
@@ -169,6 +171,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int valid_keys = min(AT_BN, p.tokens - j * AT_BN);
+      // LSA diagonal mask: column of this tile that holds the query's own key (out of range when not in the tile)
+      const int self_col = p.mask_diag ? (q0 + row - j * AT_BN) : -1;
       // pass 1: row max
       float m_tile = -INFINITY;
 #pragma unroll 1
@@ -178,10 +182,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c + i < valid_keys) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+          if (c + i < valid_keys && c + i != self_col) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
       }
       const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2e);   // exp2(-inf) = 0 on the first tile
+      // exp2(-inf) = 0 on the first tile; a tile whose only live key is the masked diagonal leaves m at -inf
+      const float alpha = m_new == -INFINITY ? 1.0f : exp2f((m_run - m_new) * p.scale_log2e);
       // previous P V must be complete before P is overwritten and O is rescaled
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -199,7 +204,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       // pass 2: P = exp2((S - m) * scale*log2e) -> bf16 -> shared memory (K-major SW128: 16 B chunk ^ (row % 8))
       float l_tile = 0.f;
-      const float mb = m_new * p.scale_log2e;
+      const float mb = m_new == -INFINITY ? 0.f : m_new * p.scale_log2e;
 #pragma unroll 1
       for (int c = 0; c < AT_BN; c += 32) {
         uint32_t r[32];
@@ -208,8 +213,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < valid_keys) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
-          float p1 = (c + i + 1 < valid_keys) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2e - mb) : 0.f;
+          float p0 = (c + i < valid_keys && c + i != self_col)
+                         ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
+          float p1 = (c + i + 1 < valid_keys && c + i + 1 != self_col)
+                         ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2e - mb) : 0.f;
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           // the row sum uses the bf16-rounded probabilities that the P V product actually consumes
           l_tile += __low2float(h2) + __high2float(h2);
@@ -233,7 +240,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tc_fence_after();
     const int t = q0 + row;
     const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.tokens + t) * (p.heads * HD) + head * HD;
+    __nv_bfloat16* dst = p.out + static_cast<size_t>(b) * p.out_stride_b + static_cast<size_t>(t) * (p.heads * HD) + head * HD;
 #pragma unroll 1
     for (int c = 0; c < HD; c += 32) {
       uint32_t r[32];
@@ -292,7 +299,8 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 
 extern "C" int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads,
                                   int tokens, int head_dim, long long stride_b, long long stride_h,
-                                  long long stride_t, float scale, void* stream) {
+                                  long long stride_t, float scale, long long out_stride_b, int mask_diag,
+                                  void* stream) {
   STEDM_REQUIRE(q && k && v && out, "attention_tc: null pointer");
   STEDM_REQUIRE(head_dim == 64 || head_dim == 128, "attention_tc: head_dim %d unsupported (64 or 128)", head_dim);
   STEDM_REQUIRE(batch > 0 && heads > 0 && tokens > 0 && batch <= 65535 && heads <= 65535, "attention_tc: bad shape");
@@ -307,6 +315,9 @@ extern "C" int stedm_attention_tc(const void* q, const void* k, const void* v, v
   p.out = static_cast<__nv_bfloat16*>(out);
   p.tokens = tokens; p.heads = heads; p.head_dim = head_dim;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.out_stride_b = out_stride_b > 0 ? out_stride_b : static_cast<long long>(tokens) * heads * head_dim;
+  p.mask_diag = mask_diag ? 1 : 0;
+  STEDM_REQUIRE(p.out_stride_b % 8 == 0 && !(mask_diag && tokens < 2), "attention_tc: bad out stride / diagonal mask");
   auto s = static_cast<cudaStream_t>(stream);
   return head_dim == 128 ? launch_attn<128>(mq, mk, mv, p, batch, s) : launch_attn<64>(mq, mk, mv, p, batch, s);
 }

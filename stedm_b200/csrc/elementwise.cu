@@ -466,18 +466,21 @@ extern "C" int stedm_image_to_uint8(const float* img, uint8_t* out, int batch, i
 // =====================================================================================================
 template <typename TO>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, TO* __restrict__ out, long long rows,
-                                                           int cols, float scale) {
+                                                           int cols, float scale, int mask_diag_period) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
   float* r = x + row * cols;
   TO* o = out + row * cols;
+  // mask_diag_period = T > 0: rows are queries of [.., T, cols = T] score matrices; a token does not attend to itself
+  const int self_col = mask_diag_period > 0 ? static_cast<int>(row % mask_diag_period) : -1;
   float m = -INFINITY;
-  for (int i = lane; i < cols; i += 32) m = fmaxf(m, r[i]);
+  for (int i = lane; i < cols; i += 32)
+    if (i != self_col) m = fmaxf(m, r[i]);
   m = warp_max(m) * scale;
   float s = 0.f;
   for (int i = lane; i < cols; i += 32) {
-    const float e = expf(r[i] * scale - m);
+    const float e = i == self_col ? 0.f : expf(r[i] * scale - m);
     r[i] = e;                      // each lane re-reads only what it wrote
     s += e;
   }
@@ -486,14 +489,16 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
 }
 
 extern "C" int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale,
-                                  void* stream) {
+                                  int mask_diag_period, void* stream) {
   STEDM_REQUIRE(x && rows > 0 && cols > 0 && scale > 0.f, "softmax_rows: bad argument");
   STEDM_REQUIRE((rows + 7) / 8 < 0x7fffffffLL, "softmax_rows: too many rows");
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   auto s = static_cast<cudaStream_t>(stream);
   if (out == nullptr || out_dtype == DT_F32)
-    softmax_rows_kernel<float><<<grid, 256, 0, s>>>(x, out ? static_cast<float*>(out) : x, rows, cols, scale);
+    softmax_rows_kernel<float><<<grid, 256, 0, s>>>(x, out ? static_cast<float*>(out) : x, rows, cols, scale,
+                                                    mask_diag_period);
   else
-    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), rows, cols, scale);
+    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out), rows, cols, scale,
+                                                            mask_diag_period);
   return check_launch("softmax_rows");
 }

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------ row LayerNorm
-// A row of C channels (C % 8 == 0, C <= 1024) is owned by G lanes (power of two <= 32); a lane holds up to four
+// A row of C channels (C % 8 == 0, C <= 2048) is owned by G lanes (power of two <= 32); a lane holds up to PER (4 or 8)
 // 8-channel items (item j of the row -> lane j % G), so every global access is a 16/32-byte vector.
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
@@ -117,7 +117,7 @@ __device__ __forceinline__ float group_sum(float v, int G) {
   return v;
 }
 
-template <typename TI>
+template <typename TI, int PER>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ residual,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float* __restrict__ out_f32,
@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x
   const long long row = warp_global * rows_per_warp + lane / G;
   const bool live = row < rows;
   const int items = C / 8;
-  float v[4][8];
+  float v[PER][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < PER; ++i) {
     const int it = sub + i * G;
     if (live && it < items) {
       load8<TI>(x + row * C + it * 8, v[i]);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x
   const float mean = group_sum(s, G) / static_cast<float>(C);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < PER; ++i) {
     if (sub + i * G < items) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x
   const float rstd = 1.0f / sqrtf(group_sum(q, G) / static_cast<float>(C) + eps);
   if (!live) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < PER; ++i) {
     const int it = sub + i * G;
     if (it >= items) continue;
     float g[8], b[8], y[8];
@@ -586,7 +586,103 @@ __global__ void __launch_bounds__(256) set_reduce_kernel(const float* __restrict
   out[idx] = mode == 1 ? a : a / static_cast<float>(n);
 }
 
+// ------------------------------------------------------------------------------------------ sViT (style_agg=svit)
+// SPT patch tokens (networks/vit_set.py:97-107): the ns style images of a sample are stacked along channels
+// (channel c*ns + s) and cut into p x p patches flattened as (p1 p2 c).  One thread per output element (coalesced
+// writes; the gathered reads are 12-byte pixel triples that stay in L1/L2).
+__global__ void __launch_bounds__(256) spt_patchify_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                           long long total, int ns, int P, int p) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cn = 3 * ns, pd = p * p * cn, g = P / p;
+  const int e = static_cast<int>(idx % pd);
+  const long long tokidx = idx / pd;
+  const int tok = static_cast<int>(tokidx % (g * g));
+  const long long b = tokidx / (g * g);
+  const int cs = e % cn, pp = e / cn;
+  const int c = cs / ns, s = cs % ns;
+  const int y = (tok / g) * p + pp / p, x = (tok % g) * p + pp % p;
+  out[idx] = img[(((b * ns + s) * P + y) * P + x) * 3 + c];
+}
+
+// x[b, 0] = cls + pos[0];  x[b, 1] = t_emb (zeros when None) + pos[1];  x[b, 2 + i] = patch_i + pos[2 + i]
+// (vit_set.py:182-190); rows >= T of the padded token buffer are zero.
+template <typename TI>
+__global__ void __launch_bounds__(256) svit_assemble_kernel(const TI* __restrict__ patches, const float* __restrict__ cls,
+                                                            const float* __restrict__ pos, float* __restrict__ out,
+                                                            long long total, int n_patches, int t_pad, int dim) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int d = static_cast<int>(idx % dim);
+  const long long r = idx / dim;
+  const int t = static_cast<int>(r % t_pad);
+  const long long b = r / t_pad;
+  float v = 0.f;
+  if (t < n_patches + 2) {
+    v = pos[static_cast<size_t>(t) * dim + d];
+    if (t == 0) v += cls[d];
+    else if (t >= 2) v += to_f32<TI>(patches[(b * n_patches + (t - 2)) * dim + d]);
+  }
+  out[idx] = v;
+}
+
+// mean over the first `tokens` rows of each sample of a [batch][t_pad][c] fp32 buffer (pool = 'mean', vit_set.py:196)
+__global__ void __launch_bounds__(256) token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int tokens,
+                                                         int t_pad, int C) {
+  __shared__ float part[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const float* xb = x + static_cast<size_t>(blockIdx.y) * t_pad * C;
+  float a = 0.f;
+  if (c < C)
+    for (int t = warp; t < tokens; t += 8) a += xb[static_cast<size_t>(t) * C + c];
+  part[warp][lane] = a;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][lane];
+    out[static_cast<size_t>(blockIdx.y) * C + c] = s / static_cast<float>(tokens);
+  }
+}
+
 }  // namespace
+
+extern "C" int stedm_spt_patchify(const float* img, float* out, int batch, int ns, int p_img, int patch, void* stream) {
+  STEDM_REQUIRE(img && out && batch > 0 && ns > 0 && patch > 0 && p_img > 0 && p_img % patch == 0,
+                "spt_patchify: bad argument");
+  const long long total = static_cast<long long>(batch) * ns * p_img * p_img * 3;
+  const long long blocks = (total + 255) / 256;
+  STEDM_REQUIRE(blocks < (1LL << 31), "spt_patchify: too large");
+  spt_patchify_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, out, total, ns,
+                                                                                                    p_img, patch);
+  return check_launch("spt_patchify");
+}
+
+extern "C" int stedm_svit_assemble(const void* patches, int dtype, const float* cls, const float* pos, float* out,
+                                   int batch, int n_patches, int t_pad, int dim, void* stream) {
+  STEDM_REQUIRE(patches && cls && pos && out && batch > 0 && n_patches > 0 && t_pad >= n_patches + 2 && dim > 0,
+                "svit_assemble: bad argument");
+  const long long total = static_cast<long long>(batch) * t_pad * dim;
+  const long long blocks = (total + 255) / 256;
+  STEDM_REQUIRE(blocks < (1LL << 31), "svit_assemble: too large");
+  auto s = static_cast<cudaStream_t>(stream);
+  if (dtype == DT_BF16)
+    svit_assemble_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(patches), cls, pos, out, total, n_patches, t_pad, dim);
+  else
+    svit_assemble_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const float*>(patches), cls,
+                                                                               pos, out, total, n_patches, t_pad, dim);
+  return check_launch("svit_assemble");
+}
+
+extern "C" int stedm_token_mean(const float* x, float* out, int batch, int tokens, int t_pad, int c, void* stream) {
+  STEDM_REQUIRE(x && out && batch > 0 && tokens > 0 && t_pad >= tokens && c > 0 && batch <= 65535,
+                "token_mean: bad argument");
+  dim3 grid((c + 31) / 32, batch);
+  token_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, tokens, t_pad, c);
+  return check_launch("token_mean");
+}
 
 extern "C" int stedm_patch_embed_ln(const float* img, const float* w, const float* bias, const float* gamma,
                                     const float* beta, float eps, float* out_f32, void* out_bf16, int batch, int p,
@@ -611,22 +707,27 @@ extern "C" int stedm_patch_embed_ln(const float* img, const float* w, const floa
 extern "C" int stedm_layernorm(const void* x, int x_dtype, const float* residual, const float* gamma, const float* beta,
                                float eps, float* out_f32, void* out_bf16, long long rows, int c, void* stream) {
   STEDM_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "layernorm: null pointer");
-  STEDM_REQUIRE(rows > 0 && c >= 8 && c % 8 == 0 && c <= 1024, "layernorm: C = %d must be a multiple of 8, <= 1024", c);
+  STEDM_REQUIRE(rows > 0 && c >= 8 && c % 8 == 0 && c <= 2048, "layernorm: C = %d must be a multiple of 8, <= 2048", c);
   const int items = c / 8;
+  const int per = items > 128 ? 8 : 4;      // items per lane
   int G = 1;
-  while (G < 32 && G * 4 < items) G <<= 1;  // <= 4 items per lane
+  while (G < 32 && G * per < items) G <<= 1;
   if (G < 4) G = 4;
   const int rows_per_block = 8 * (32 / G);
   const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
   STEDM_REQUIRE(blocks < (1LL << 31), "layernorm: too many rows");
   auto s = static_cast<cudaStream_t>(stream);
   auto ob = static_cast<__nv_bfloat16*>(out_bf16);
-  if (x_dtype == DT_BF16)
-    layernorm_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(x), residual, gamma, beta, eps, out_f32, ob, rows, c, G);
-  else
-    layernorm_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const float*>(x), residual, gamma,
-                                                                           beta, eps, out_f32, ob, rows, c, G);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  if (x_dtype == DT_BF16) {
+    auto xp = static_cast<const __nv_bfloat16*>(x);
+    if (per == 4) layernorm_kernel<__nv_bfloat16, 4><<<nb, 256, 0, s>>>(xp, residual, gamma, beta, eps, out_f32, ob, rows, c, G);
+    else layernorm_kernel<__nv_bfloat16, 8><<<nb, 256, 0, s>>>(xp, residual, gamma, beta, eps, out_f32, ob, rows, c, G);
+  } else {
+    auto xp = static_cast<const float*>(x);
+    if (per == 4) layernorm_kernel<float, 4><<<nb, 256, 0, s>>>(xp, residual, gamma, beta, eps, out_f32, ob, rows, c, G);
+    else layernorm_kernel<float, 8><<<nb, 256, 0, s>>>(xp, residual, gamma, beta, eps, out_f32, ob, rows, c, G);
+  }
   return check_launch("layernorm");
 }
 

@@ -5,6 +5,7 @@ import torchvision
 
 from ..ldm.models.diffusion.ddpm import LatentDiffusion
 from .agg_blocks import Agg_Linear, Agg_Max, Agg_Mean, Agg_None
+from .vit_set import sViT
 
 
 def _get(cfg, name, default=None):
@@ -30,7 +31,10 @@ class S_ZSS_DM(LatentDiffusion):
         elif a_name == "linear":
             self._agg_block = Agg_Linear(sampling_cfg, embedder)
         elif a_name == "svit":
-            raise NotImplementedError("style_agg=svit (networks/vit_set.py) is a 'next' row (SURVEY.md §8f rank 2)")
+            items = agg_cfg.items() if isinstance(agg_cfg, dict) else vars(agg_cfg).items()
+            args = {k: v for k, v in items if k != "name"}                    # s_zss_dm.py:32-38
+            self._agg_block = sViT(image_size=_get(_get(cfg, "data"), "patch_size"), num_classes=512,
+                                   ns=_get(sampling_cfg, "num_patches") if s_name == "mp" else 1, **args)
         else:
             raise Exception("Unkown aggregation function!")
         self.register_module("agg_block", self._agg_block)

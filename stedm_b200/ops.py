@@ -201,32 +201,34 @@ def gemm_simt(a, b, c, m, n, k, lda, ldb, ldc, b_is_nk, nb, nh, a_strides, b_str
           c_strides[1], float(alpha), _stream())
 
 
-def softmax_rows(x, scale=1.0, out=None):
-    """softmax(scale * x) over the last dim of fp32 ``x`` (used as scratch); result in ``out`` (fp32/bf16) or in place."""
+def softmax_rows(x, scale=1.0, out=None, mask_diag_period=0):
+    """softmax(scale * x) over the last dim of fp32 ``x`` (used as scratch); result in ``out`` (fp32/bf16) or in place.
+    ``mask_diag_period`` = T: rows are queries of [.., T, T] score matrices, the diagonal is excluded (sViT LSA)."""
     _cuda(x, out)
     assert x.dtype == torch.float32 and (out is None or out.shape == x.shape)
     cols = x.shape[-1]
     _call("stedm_softmax_rows", _ptr(x), _ptr(out), F32 if out is None else _DT[out.dtype], x.numel() // cols, cols,
-          float(scale), _stream())
+          float(scale), int(mask_diag_period), _stream())
     return x if out is None else out
 
 
 def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
-                   scale, out_dtype):
+                   scale, out_dtype, mask_diag=False, batch_tokens=None):
     """fp32-accumulate attention on CUDA cores with a materialised score matrix (parity mode).
     q/k/v live in [B, T, token_stride] buffers at channel offset ``*_off + head*head_stride``; for the U-Net's
     legacy head-major qkv layout head_stride = 3*head_dim, for separate q/k/v tensors head_stride = head_dim."""
     b = q_src.shape[0]
     hs = head_stride
+    bt = batch_tokens or tokens        # rows per sample in the q/k/v/out buffers (> tokens when padded)
     s = torch.empty((b, heads, tokens, tokens), device=q_src.device, dtype=torch.float32)
     gemm_simt(q_src, k_src, s, tokens, tokens, head_dim, token_stride, token_stride, tokens, True, b, heads,
-              (tokens * token_stride, hs), (tokens * token_stride, hs), (heads * tokens * tokens, tokens * tokens),
+              (bt * token_stride, hs), (bt * token_stride, hs), (heads * tokens * tokens, tokens * tokens),
               alpha=scale, a_off=q_off, b_off=k_off)
-    softmax_rows(s)
-    out = torch.empty((b, tokens, heads * head_dim), device=q_src.device, dtype=out_dtype)
+    softmax_rows(s, mask_diag_period=tokens if mask_diag else 0)
+    out = torch.zeros((b, bt, heads * head_dim), device=q_src.device, dtype=out_dtype)
     gemm_simt(s, v_src, out, tokens, head_dim, tokens, tokens, token_stride, heads * head_dim, False, b, heads,
-              (heads * tokens * tokens, tokens * tokens), (tokens * token_stride, hs),
-              (tokens * heads * head_dim, head_dim), b_off=v_off)
+              (heads * tokens * tokens, tokens * tokens), (bt * token_stride, hs),
+              (bt * heads * head_dim, head_dim), b_off=v_off)
     return out
 
 
@@ -235,14 +237,19 @@ def attention_tc_supported(head_dim, tokens):
     return head_dim in (64, 128)
 
 
-def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0):
-    """Fused tcgen05 flash attention; q/k/v are bf16 views described by element offsets and (b, h, t) strides."""
+def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0, mask_diag=False,
+                 batch_tokens=None):
+    """Fused tcgen05 flash attention; q/k/v are bf16 views described by element offsets and (b, h, t) strides.
+    ``batch_tokens`` > tokens: the output keeps that many (zero) rows per sample; ``mask_diag``: sViT's LSA mask."""
     _cuda(q, k, v)
     b = q.shape[0]
-    out = torch.empty((b, tokens, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    bt = batch_tokens or tokens
+    alloc = torch.empty if bt == tokens else torch.zeros
+    out = alloc((b, bt, heads * head_dim), device=q.device, dtype=torch.bfloat16)
     es = 2
     _call("stedm_attention_tc", _ptr(q) + q_off * es, _ptr(k) + k_off * es, _ptr(v) + v_off * es, _ptr(out), b, heads,
-          tokens, head_dim, strides[0], strides[1], strides[2], float(scale), _stream())
+          tokens, head_dim, strides[0], strides[1], strides[2], float(scale), bt * heads * head_dim,
+          1 if mask_diag else 0, _stream())
     return out
 
 
@@ -374,6 +381,38 @@ def set_reduce(x, mode):
     b, n, f = x.shape
     out = torch.empty((b, f), device=x.device, dtype=torch.float32)
     _call("stedm_set_reduce", _ptr(x), _ptr(out), b, n, f, {"mean": 0, "max": 1}[mode], _stream())
+    return out
+
+
+def spt_patchify(style_imgs, patch):
+    """SPT patch tokens of 'b n h w c' fp32 style images -> fp32 [b, (P/patch)^2, patch*patch*3*n]."""
+    _cuda(style_imgs)
+    assert style_imgs.dtype == torch.float32 and style_imgs.dim() == 5 and style_imgs.shape[-1] == 3
+    b, ns, p, p2, _ = style_imgs.shape
+    assert p == p2 and p % patch == 0
+    out = torch.empty((b, (p // patch) ** 2, patch * patch * 3 * ns), device=style_imgs.device, dtype=torch.float32)
+    _call("stedm_spt_patchify", _ptr(style_imgs), _ptr(out), b, ns, p, patch, _stream())
+    return out
+
+
+def svit_assemble(patches, cls, pos, t_pad):
+    """[cls | t_emb=0 | patches] + pos_embedding -> fp32 [b, t_pad, dim] (rows past the sequence are zero)."""
+    _cuda(patches, cls, pos)
+    b, n, dim = patches.shape
+    assert cls.numel() == dim and pos.shape[-1] == dim and pos.numel() >= (n + 2) * dim and pos.dtype == torch.float32
+    out = torch.empty((b, t_pad, dim), device=patches.device, dtype=torch.float32)
+    _call("stedm_svit_assemble", _ptr(patches), _DT[patches.dtype], _ptr(cls), _ptr(pos), _ptr(out), b, n, t_pad, dim,
+          _stream())
+    return out
+
+
+def token_mean(x, tokens):
+    """mean over the first ``tokens`` rows of fp32 [b, t_pad, c]."""
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 3
+    b, t_pad, c = x.shape
+    out = torch.empty((b, c), device=x.device, dtype=torch.float32)
+    _call("stedm_token_mean", _ptr(x), _ptr(out), b, tokens, t_pad, c, _stream())
     return out
 
 

@@ -14,6 +14,10 @@ SwinTransformer.forward (torchvision/models/swin_transformer.py) as C-ABI kernel
   PatchMergingV2        stedm_patch_merge_gather -> reduction GEMM -> stedm_layernorm
   norm, avgpool, head   stedm_ln_meanpool -> stedm_linear
 
+``SetViTRunner`` does the same for ``style_agg=svit`` (networks/vit_set.py sViT): stedm_spt_patchify -> LayerNorm ->
+patch GEMM -> stedm_svit_assemble -> depth x [LayerNorm, qkv GEMM, LSA on stedm_attention_tc (masked diagonal, learned
+temperature), to_out GEMM + residual, LayerNorm, GELU MLP + residual] -> token mean / cls -> LayerNorm -> Linear.
+
 What is input independent is folded at pack time: the continuous relative position bias
 16*sigmoid(cpb_mlp(relative_coords_table))[relative_position_index] per block, exp(clamp(logit_scale, max=log 100)),
 and the zeroed k-bias of the qkv Linear (ShiftedWindowAttentionV2.__init__ / shifted_window_attention).
@@ -37,8 +41,9 @@ class PackedLinear:
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.act_dtype = prec.act
 
-    def __call__(self, x, act=ops.ACT_NONE):
-        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=self.act_dtype, tensor_core=self.tc, act=act)
+    def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None):
+        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=out_dtype or self.act_dtype,
+                        tensor_core=self.tc, act=act, residual=residual)
 
 
 class PackedNormLN:
@@ -155,3 +160,89 @@ class StyleEncoderRunner:
         if imgs.shape[0] <= chunk:
             return self._forward(imgs)
         return torch.cat([self._forward(imgs[i:i + chunk]) for i in range(0, imgs.shape[0], chunk)], 0)
+
+
+def _gemm_view(x2d_rows, c, t):
+    """View a [rows, c] activation as the NHWC map [1, rows/128, 128, c] the implicit-GEMM kernel tiles over."""
+    if x2d_rows % 128 == 0:
+        return t.view(1, x2d_rows // 128, 128, c)
+    if 128 % x2d_rows == 0:
+        return t.view(1, 1, x2d_rows, c)
+    raise RuntimeError(f"style encoder: {x2d_rows} token rows do not tile into 128-row GEMM tiles")
+
+
+class SetViTRunner:
+    """sViT.forward (vit_set.py:163-208, t_emb = None) for the parameter container stedm_b200.networks.vit_set.sViT;
+    input 'b n h w c' fp32 style images -> [b, num_classes]."""
+
+    def __init__(self, svit, precision):
+        self.prec = prec = Precision(precision)
+        if svit.pool not in ("mean", "cls"):
+            raise NotImplementedError("native sViT: pool must be 'mean' or 'cls' (a [b, 512] context for ResBlockStyle)")
+        self.pool, self.patch, self.ns, self.np = svit.pool, svit.patch_size, svit.ns, svit.np
+        spt = svit.to_patch_embedding.to_patch_tokens
+        self.spt_norm = PackedNormLN(spt[1])
+        self.spt_lin = PackedLinear(spt[2].weight, spt[2].bias, prec)
+        self.dim = spt[2].weight.shape[0]
+        self.cls = svit.cls_token.detach().float().reshape(-1).contiguous()
+        self.pos = svit.pos_embedding.detach().float().reshape(-1, self.dim).contiguous()
+        self.layers = []
+        for attn, ff in svit.transformer.layers:
+            lsa = attn.fn
+            if lsa.dim_head != 64:
+                raise NotImplementedError("native sViT: dim_head must be 64 (the LSA default)")
+            self.layers.append(dict(
+                n1=PackedNormLN(attn.norm), qkv=PackedLinear(lsa.to_qkv.weight, None, prec), heads=lsa.heads,
+                scale=float(lsa.temperature.detach().float().exp()),                      # vit_set.py:50
+                out=PackedLinear(lsa.to_out[0].weight, lsa.to_out[0].bias, prec),
+                n2=PackedNormLN(ff.norm), fc1=PackedLinear(ff.fn.net[0].weight, ff.fn.net[0].bias, prec),
+                fc2=PackedLinear(ff.fn.net[3].weight, ff.fn.net[3].bias, prec)))
+        self.head_norm = PackedNormLN(svit.mlp_head[0])
+        self.head_w = svit.mlp_head[1].weight.detach().float().contiguous()
+        self.head_b = svit.mlp_head[1].bias.detach().float().contiguous()
+
+    def _ln(self, x, n):
+        tc = self.prec.tc
+        f32, b16 = ops.layernorm(x, None, n.gamma, n.beta, n.eps, want_f32=not tc, want_bf16=tc)
+        return b16 if tc else f32
+
+    def __call__(self, style_imgs):
+        if style_imgs.dim() != 5 or style_imgs.shape[1] != self.ns or style_imgs.shape[-1] != 3:
+            raise RuntimeError(f"sViT expects 'b n h w c' images with n = {self.ns}, got {tuple(style_imgs.shape)}")
+        tc, dim = self.prec.tc, self.dim
+        b = style_imgs.shape[0]
+        tok = ops.spt_patchify(style_imgs.float().contiguous(), self.patch)       # fp32 [b, np, patch_dim]
+        n_p, pd = tok.shape[1], tok.shape[2]
+        if n_p + 2 > self.pos.shape[0]:
+            raise RuntimeError("sViT: more patches than positional embeddings (image larger than image_size)")
+        a = self._ln(tok, self.spt_norm)
+        pe = self.spt_lin(_gemm_view(b * n_p, pd, a))                              # [.., dim]
+        T = n_p + 2
+        t_pad = (T + 127) // 128 * 128
+        x = ops.svit_assemble(pe.view(b, n_p, dim), self.cls, self.pos, t_pad)     # fp32 residual stream [b, t_pad, dim]
+        rows = b * t_pad
+        for L in self.layers:
+            inner = L["heads"] * 64
+            qkv = L["qkv"](_gemm_view(rows, dim, self._ln(x, L["n1"]))).view(b, t_pad, 3 * inner)
+            if tc:
+                o = ops.attention_tc(qkv, qkv, qkv, L["heads"], 64, T, (t_pad * 3 * inner, 64, 3 * inner), L["scale"],
+                                     q_off=0, k_off=inner, v_off=2 * inner, mask_diag=True, batch_tokens=t_pad)
+            else:
+                o = self._attention_fp32(qkv, L, T, t_pad, inner)
+            x = L["out"](_gemm_view(rows, inner, o), residual=_gemm_view(rows, dim, x),
+                         out_dtype=torch.float32).view(b, t_pad, dim)              # attn(x) + x
+            h = L["fc1"](_gemm_view(rows, dim, self._ln(x, L["n2"])), act=ops.ACT_GELU)
+            x = L["fc2"](h, residual=_gemm_view(rows, dim, x), out_dtype=torch.float32).view(b, t_pad, dim)
+        pooled = ops.token_mean(x, T) if self.pool == "mean" else x[:, 0].contiguous()
+        y, _ = ops.layernorm(pooled, None, self.head_norm.gamma, self.head_norm.beta, self.head_norm.eps)
+        return ops.linear(y, self.head_w, self.head_b)
+
+    @staticmethod
+    def _attention_fp32(qkv, L, T, t_pad, inner):
+        """Parity mode: materialised fp32 scores, at most ~1 GiB of them at a time."""
+        b = qkv.shape[0]
+        chunk = max(1, min(b, (1 << 28) // (L["heads"] * T * T)))
+        outs = [ops.attention_simt(qkv[s:s + chunk], qkv[s:s + chunk], qkv[s:s + chunk], L["heads"], 64, T, 0, inner,
+                                   2 * inner, 3 * inner, 64, L["scale"], torch.float32, mask_diag=True,
+                                   batch_tokens=t_pad) for s in range(0, b, chunk)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

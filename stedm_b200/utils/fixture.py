@@ -49,7 +49,8 @@ def is_fixture_key(key: str, tensor: torch.Tensor) -> bool:
         return False
     if key.startswith("model_ema.") or ".model_ema." in key:
         return False
-    return key.endswith(".weight") or key.endswith(".bias")
+    # sViT's free-standing parameters (vit_set.py:132-133) are torch.randn in the constructor: name-keyed too
+    return key.endswith((".weight", ".bias", "pos_embedding", "cls_token"))
 
 
 @torch.no_grad()

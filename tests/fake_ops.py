@@ -106,17 +106,30 @@ def attention_tc_supported(head_dim, tokens):
 
 
 def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
-                   scale, out_dtype):
+                   scale, out_dtype, mask_diag=False, batch_tokens=None):
     b = q_src.shape[0]
-    flat = lambda t: t.reshape(b, tokens, token_stride).float()
+    bt = batch_tokens or tokens
+    flat = lambda t: t.reshape(b, bt, token_stride).float()[:, :tokens]
     outs = []
     for h in range(heads):
         q = flat(q_src)[:, :, q_off + h * head_stride: q_off + h * head_stride + head_dim]
         k = flat(k_src)[:, :, k_off + h * head_stride: k_off + h * head_stride + head_dim]
         v = flat(v_src)[:, :, v_off + h * head_stride: v_off + h * head_stride + head_dim]
-        w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) * scale, -1)
-        outs.append(torch.einsum("bts,bsc->btc", w, v))
-    return torch.cat(outs, -1).to(out_dtype)
+        s = torch.einsum("btc,bsc->bts", q, k) * scale
+        if mask_diag:
+            s = s.masked_fill(torch.eye(tokens, dtype=torch.bool), float("-inf"))
+        outs.append(torch.einsum("bts,bsc->btc", torch.softmax(s, -1), v))
+    o = torch.cat(outs, -1)
+    if bt != tokens:
+        o = F.pad(o, (0, 0, 0, bt - tokens))
+    return o.to(out_dtype)
+
+
+def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0, mask_diag=False,
+                 batch_tokens=None):
+    assert strides[1] == head_dim and q is k and k is v
+    return attention_simt(q, k, v, heads, head_dim, tokens, q_off, k_off, v_off, strides[2], strides[1], scale,
+                          torch.bfloat16, mask_diag=mask_diag, batch_tokens=batch_tokens)
 
 
 def vq_nearest(z, codebook, return_indices=False):
@@ -198,3 +211,20 @@ def ln_meanpool(x, gamma, beta, eps):
 
 def set_reduce(x, mode):
     return x.mean(1) if mode == "mean" else x.max(1)[0]
+
+
+def spt_patchify(style_imgs, patch):
+    b, ns, p, _, _ = style_imgs.shape
+    x = style_imgs.permute(0, 4, 1, 2, 3).reshape(b, 3 * ns, p, p)                      # channel c*ns + s
+    g = p // patch
+    return x.reshape(b, 3 * ns, g, patch, g, patch).permute(0, 2, 4, 3, 5, 1).reshape(b, g * g, patch * patch * 3 * ns).contiguous()
+
+
+def svit_assemble(patches, cls, pos, t_pad):
+    b, n, dim = patches.shape
+    x = torch.cat([cls.view(1, 1, dim).expand(b, 1, dim), torch.zeros(b, 1, dim), patches.float()], 1) + pos[None, :n + 2]
+    return F.pad(x, (0, 0, 0, t_pad - (n + 2))).contiguous()
+
+
+def token_mean(x, tokens):
+    return x[:, :tokens].mean(1)

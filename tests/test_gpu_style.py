@@ -235,3 +235,85 @@ def test_agg_blocks_match_reference_formulas(agg):
                 "linear": lambda: blk._linear_block(f.reshape(2, -1))}[agg]()
         got = blk(style)
     assert max_abs(got, want) < 1e-4, max_abs(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- style_agg=svit
+def test_spt_patchify_assemble_token_mean(ops):
+    g = torch.Generator().manual_seed(3)
+    style = torch.rand(2, 3, 32, 32, 3, generator=g)
+    assert torch.equal(ops.spt_patchify(style.cuda(), 8).cpu(), fake_ops.spt_patchify(style, 8))
+    patches = torch.randn(2, 16, 64, generator=g)
+    cls, pos = torch.randn(64, generator=g), torch.randn(18, 64, generator=g)
+    for dt in (torch.float32, torch.bfloat16):
+        got = ops.svit_assemble(patches.to(dt).cuda(), cls.cuda(), pos.cuda(), 128)
+        assert max_abs(got, fake_ops.svit_assemble(patches.to(dt), cls, pos, 128)) < 1e-6
+    x = torch.randn(3, 128, 256, generator=g)
+    assert max_abs(ops.token_mean(x.cuda(), 66), fake_ops.token_mean(x, 66)) < 1e-6
+
+
+@pytest.mark.parametrize("T,heads", [(66, 12), (258, 2), (1026, 3)])
+def test_attention_tc_diagonal_mask_and_padded_rows(ops, T, heads):
+    """LSA on the tcgen05 flash kernel: masked diagonal, learned temperature as the scale, token buffer padded to
+    whole 128-row tiles (pad rows hold garbage on input and stay zero on output)."""
+    g = torch.Generator().manual_seed(T)
+    t_pad = (T + 127) // 128 * 128
+    inner = heads * 64
+    qkv = torch.randn(2, t_pad, 3 * inner, generator=g).to(torch.bfloat16)
+    qkv[:, T:] = 1000.0                                    # must not leak into real rows
+    want = fake_ops.attention_simt(qkv, qkv, qkv, heads, 64, T, 0, inner, 2 * inner, 3 * inner, 64, 0.21,
+                                   torch.float32, mask_diag=True, batch_tokens=t_pad)
+    q = qkv.cuda()
+    got = ops.attention_tc(q, q, q, heads, 64, T, (t_pad * 3 * inner, 64, 3 * inner), 0.21, q_off=0, k_off=inner,
+                           v_off=2 * inner, mask_diag=True, batch_tokens=t_pad)
+    assert tuple(got.shape) == (2, t_pad, inner) and float(got[:, T:].abs().max()) == 0.0
+    assert max_abs(got.float(), want) < 2e-2
+    s = ops.attention_simt(q.float(), q.float(), q.float(), heads, 64, T, 0, inner, 2 * inner, 3 * inner, 64, 0.21,
+                           torch.float32, mask_diag=True, batch_tokens=t_pad)
+    assert max_abs(s, want) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["svit_p64_n2_mean", "svit_p128_n1_cls"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_svit_matches_reference_golden(name, precision):
+    """Native sViT vs the reference's own networks/vit_set.py output on fixture weights (tests/golden/svit.npz)."""
+    from oracle import stedm_oracle as O
+    from tests.test_style_engine_glue import SVIT_CASES, build_svit
+    from tests.util import load_golden
+    P, ns, pool, seed = SVIT_CASES[name]
+    blk = build_svit(P, ns, pool).agg_block.cuda()
+    blk.set_precision(precision)
+    _, style, _ = O.synthetic_batch(2, P, ns, seed)
+    got = blk(style.cuda())
+    want = load_golden("svit")[name]
+    err = max_abs(got, want)
+    if precision == "fp32":
+        assert err < 1e-4, err
+    else:
+        rel = err / float(abs(want).max())
+        print(f"sViT bf16 rel err {name}: {rel:.3e}")
+        assert rel < 2e-2, rel
+
+
+def test_svit_full_size_vs_oracle_and_model_wiring():
+    """style_agg=svit at the path's real shape (256^2, 1026 tokens, N = 10 'mp' patches) through S_ZSS_DM.get_input."""
+    from oracle import stedm_oracle as O
+    from stedm_b200.modules.ldm_diffusion import LDM_Diffusion
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    from tests.util import build_config, oracle_state_dict
+    cfg = build_config(64, n_style=10, agg="svit")
+    m = LDM_Diffusion(cfg, precision="bf16", load_first_stage_ckpt=False)
+    apply_fixture_weights(m._model, seed=0)
+    m = m.cuda().eval()
+    seg, style, _ = O.synthetic_batch(2, 256, 10, seed=4)
+    batch = {"image": torch.zeros(2, 256, 256, 3).cuda(), "segmentation": seg.cuda(), "style_imgs": style.cuda()}
+    _, c = m._model.get_input(batch, "image")
+    sd = {k: v for k, v in oracle_state_dict(m._model).items() if k.startswith("agg_block.")}
+    with torch.no_grad():
+        want = O.svit_aggregate(sd, style, heads=12, patch=8, pool="mean")
+    got = c["c_crossattn"][0]
+    rel = max_abs(got, want) / float(want.abs().max())
+    print(f"sViT 256^2 N=10 bf16 rel err {rel:.3e}")
+    assert tuple(got.shape) == (2, 512) and rel < 2e-2, rel
+    m._model.set_precision("fp32")
+    _, c = m._model.get_input(batch, "image")
+    assert max_abs(c["c_crossattn"][0], want) < 1e-4

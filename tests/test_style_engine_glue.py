@@ -65,3 +65,48 @@ def test_relative_position_bias_matches_torchvision():
     at = m.features[3][1].attn
     with torch.no_grad():
         assert max_abs(relative_position_bias(at), at.get_relative_position_bias()[0]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- style_agg=svit
+SVIT_KW = dict(patch_size=8, num_classes=512, dim=256, depth=6, heads=12, mlp_dim=256, channels=3, dropout=0.1,
+               emb_dropout=0.1, t_dim=256)
+SVIT_CASES = {"svit_p64_n2_mean": (64, 2, "mean", 11), "svit_p128_n1_cls": (128, 1, "cls", 12)}   # as oracle/make_golden.py
+
+
+def build_svit(P, ns, pool):
+    """Product parameter container with name-keyed fixture weights (same tensors make_golden gave the reference)."""
+    from stedm_b200.networks.vit_set import sViT
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    holder = torch.nn.Module()
+    holder.agg_block = sViT(image_size=P, ns=ns, pool=pool, **SVIT_KW).eval()
+    apply_fixture_weights(holder, seed=0)
+    return holder
+
+
+@pytest.mark.parametrize("name", sorted(SVIT_CASES))
+def test_svit_oracle_matches_reference_golden(name):
+    """oracle.svit_aggregate on fixture weights == the reference's own sViT output (tests/golden/svit.npz)."""
+    from oracle import stedm_oracle as O
+    from tests.util import load_golden
+    P, ns, pool, seed = SVIT_CASES[name]
+    holder = build_svit(P, ns, pool)
+    sd = {k: v.detach().float() for k, v in holder.state_dict().items()}
+    _, style, _ = O.synthetic_batch(2, P, ns, seed)
+    with torch.no_grad():
+        got = O.svit_aggregate(sd, style, heads=12, patch=8, pool=pool)
+    assert max_abs(got, load_golden("svit")[name]) < 1e-5
+
+
+@pytest.mark.parametrize("name", sorted(SVIT_CASES))
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_svit_runner_glue(patched, name, precision, bar):
+    from oracle import stedm_oracle as O
+    from tests.util import load_golden
+    P, ns, pool, seed = SVIT_CASES[name]
+    holder = build_svit(P, ns, pool)
+    _, style, _ = O.synthetic_batch(2, P, ns, seed)
+    with torch.no_grad():
+        got = patched.SetViTRunner(holder.agg_block, precision)(style)
+    want = load_golden("svit")[name]
+    assert tuple(got.shape) == (2, 512)
+    assert max_abs(got, want) < bar * (float(abs(want).max()) if precision == "bf16" else 1.0), max_abs(got, want)
