@@ -48,6 +48,25 @@ __device__ __forceinline__ float silu_f(float x) {
 __device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
 // exact (erf) GELU, nn.GELU() default: the Swin-V2 / sViT MLP activation
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// The same function for the tensor-core epilogue, where erff's ~45 instructions per element made the whole SM
+// issue-bound on the MLP GEMMs (403 M activations per launch at stage 1 of the style encoder): erf by Abramowitz-Stegun
+// 7.1.26, |abs error| <= 1.5e-7 (+ ~1e-6 from the two approximate MUFU ops), i.e. far below the bf16 rounding of the
+// stored result: 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z = |x| / sqrt(2).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);            // erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return fmaf(h, copysignf(erf_abs, x), h);              // 0.5 x (1 + erf(x / sqrt 2))
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -91,7 +91,9 @@ struct TcCfg {
   static constexpr int ACC_COLS = BN;  // fp32 columns per accumulator
   static constexpr int TMEM_COLS = (ACC * BN) < 32 ? 32 : ACC * BN;  // 32 / 128 / 256 / 512: powers of two
   static constexpr int STATS_BYTES = 4 * BN * 2 * 4;  // [4 epilogue warps][BN][sum, sumsq] fp32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES;
+  static constexpr int OUT_STAGE_BYTES = 4 * 32 * 64;  // [4 epilogue warps][32 rows][64 B]: output transpose staging
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES + OUT_STAGE_BYTES;
   static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
 };
 
@@ -109,6 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
   float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  uint8_t* s_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::STATS_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -247,55 +250,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
+      // NHWC offset (elements) of output row mm at channel 0 (tap_mode 1: pixel (y, x) of this sub-pixel phase lands at
+      // (2y + py, 2x + px) of the [B, 2H, 2W, C] output)
+      auto row_offset = [&](int mm) -> size_t {
+        if (p.tap_mode != 1) return static_cast<size_t>(mm) * p.cout;
+        const int bb = mm / p.HW, pix = mm - bb * p.HW, y = pix / p.W, x = pix - y * p.W;
+        return ((static_cast<size_t>(bb) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout;
+      };
+      const size_t o_row = valid ? row_offset(m) : 0;
+      uint8_t* stg = s_out + quad * (32 * 64);  // this warp's staging rows
+      // rows this lane stores after the transpose: (lane / 4) + 8 i of the warp's 32, i < 4
+      size_t roff[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mm = m - lane + (lane >> 2) + 8 * i;
+        rok[i] = mm < p.M;
+        roff[i] = rok[i] ? row_offset(mm) : 0;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += CH) {
-        float v[CH];
+        const int n = n_base + c;
+        if (n >= p.cout) break;  // partially filled last channel tile (cout % BN != 0): nothing to store
+        float v[CH], add[CH];
         if constexpr (CH == 32) {
           uint32_t r[32];
           tmem_ld32(tmem_acc + c, r);
+          // bias / embedding rows are fetched while the TMEM load is in flight (they were the epilogue's longest stall)
+#pragma unroll
+          for (int j = 0; j < CH; ++j) add[j] = 0.f;
+          if (p.ksplit == 1) {
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                add[j] = t.x; add[j + 1] = t.y; add[j + 2] = t.z; add[j + 3] = t.w;
+              }
+            }
+            if (emb_row) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
+                add[j] += t.x; add[j + 1] += t.y; add[j + 2] += t.z; add[j + 3] += t.w;
+              }
+            }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         } else {
           uint32_t r[16];
           tmem_ld16(tmem_acc + c, r);
+#pragma unroll
+          for (int j = 0; j < CH; ++j) add[j] = 0.f;
+          if (p.ksplit == 1) {
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                add[j] = t.x; add[j + 1] = t.y; add[j + 2] = t.z; add[j + 3] = t.w;
+              }
+            }
+            if (emb_row) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
+                add[j] += t.x; add[j + 1] += t.y; add[j + 2] += t.z; add[j + 3] += t.w;
+              }
+            }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        const int n = n_base + c;
-        if (n >= p.cout) break;  // partially filled last channel tile (cout % BN != 0): nothing to store
         if (p.ksplit > 1) {  // split-K: raw fp32 partial tile -> workspace; splitk_finish_kernel applies the epilogue
           float4* wp = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.m_pad + m) * p.cout + n);
 #pragma unroll
           for (int j = 0; j < CH; j += 4) wp[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           continue;
         }
-        if (valid) {
-        if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-          }
-        }
-        if (emb_row) {
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(emb_row + n + j));
-            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-          }
-        }
+        for (int j = 0; j < CH; ++j) v[j] += add[j];
         if (p.act == STEDM_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf_fast(v[j]);
         }
-        size_t o = static_cast<size_t>(m) * p.cout + n;
-        if (p.tap_mode == 1) {  // this phase's pixel (y, x) lands at (2y + py, 2x + px) of the [B, 2H, 2W, C] output
-          const int pix = m - b * p.HW, y = pix / p.W, x = pix - y * p.W;
-          o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
-        }
-        if (p.residual) {
+        const size_t o = o_row + n;
+        if (valid && p.residual) {
           if (p.res_dtype == DT_BF16) {
             const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
 #pragma unroll
@@ -317,37 +358,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
         if (p.out_nchw) {
-          // channel-major output (eps / image heads in fp32; V^T for the decoder attention in bf16): consecutive
-          // lanes = consecutive pixels -> coalesced per channel plane
-          const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
-          if (p.out_dtype == DT_F32) {
-            float* op = static_cast<float*>(p.out) + base;
+          if (valid) {
+            // channel-major output (eps / image heads in fp32; V^T for the decoder attention in bf16): consecutive
+            // lanes = consecutive pixels -> coalesced per channel plane
+            const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+            if (p.out_dtype == DT_F32) {
+              float* op = static_cast<float*>(p.out) + base;
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+              for (int j = 0; j < CH; ++j)
+                if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = v[j];
+            } else {
+              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + base;
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        } else if constexpr (CH == 32) {
+          // NHWC output through a per-warp shared-memory transpose: a thread owns one pixel row of the accumulator,
+          // so direct stores are 32 half-written sectors per instruction; staged, 4 lanes write one row's 64
+          // contiguous bytes (2 whole sectors).  16-byte slots are XOR-swizzled: 4 wavefronts per access, the minimum.
+          const int jj = lane & 3;
+          if (p.out_dtype == DT_BF16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i;
+              if (rok[i])
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + roff[i] + n + jj * 8) =
+                    *reinterpret_cast<const uint4*>(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+            }
+            __syncwarp();
           } else {
-            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + base;
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n + j < p.cout_store) op[static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+            for (int h = 0; h < 2; ++h) {  // 16 fp32 channels = 64 B per pass
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                if (rok[i])
+                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + roff[i] + n + 16 * h + jj * 4) =
+                      *reinterpret_cast<const float4*>(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+              }
+              __syncwarp();
+            }
           }
-        } else if (p.out_dtype == DT_BF16) {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
+        } else if (valid) {
+          if (p.out_dtype == DT_BF16) {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o);
 #pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(v[j], v[j + 1]);
-            u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            op[j / 8] = u;
+            for (int j = 0; j < CH; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[j], v[j + 1]);
+              u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              op[j / 8] = u;
+            }
+          } else {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
-        } else {
-          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) op[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
-        }  // valid
         if constexpr (CH == 32) {
           if (p.stats_out != nullptr) {
             // GroupNorm statistics of the tensor being written (K7's statistics pass folded into its producer):

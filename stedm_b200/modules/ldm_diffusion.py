@@ -41,6 +41,7 @@ class LDM_Diffusion(torch.nn.Module):
                                precision=precision, **ldm_dict)
         self.register_module("model", self._model)
         self.predict_dir = None
+        self.writer = None      # optional stedm_b200.utils.image_writer.AsyncImageWriter (overlapped D2H + PNG encode)
 
     def prepare_batch(self, batch):
         """(img (B,3,P,P), seg_oh (B,K,P,P), seg, style (B,N,3,P,P), idx) -> channels-last dict; classes 1..K-1 are
@@ -77,6 +78,10 @@ class LDM_Diffusion(torch.nn.Module):
     def predict_step(self, batch, batch_idx):
         from PIL import Image
         ldm_batch = self.prepare_batch(batch)
+        if self.writer is not None:
+            # asynchronous tail: the copy to pinned memory and the PNG encodes overlap the next batch's sampling
+            segs = torch.argmax(ldm_batch["segmentation"], dim=-1).to(torch.uint8)
+            return self.writer.submit(self.generate(ldm_batch), segs, batch[4])
         out_imgs = self.generate(ldm_batch).cpu().numpy()
         segs = torch.argmax(ldm_batch["segmentation"], dim=-1).cpu().numpy().astype(np.uint8)
         for img, seg, num in zip(out_imgs, segs, batch[4].cpu().numpy()):

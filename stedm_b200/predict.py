@@ -39,7 +39,7 @@ class SyntheticPredictSet(torch.utils.data.Dataset):
         return torch.zeros(3, self.p, self.p), seg_oh, lab, style, i
 
 
-def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None):
+def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None, async_io=True):
     """Generate and save images for every batch tuple of ``batches`` on this rank's GPU."""
     rank, world, local = parallel.env_rank_world()
     device = device or torch.device("cuda", local)
@@ -59,10 +59,16 @@ def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None):
     module = module.to(device).eval()
     os.makedirs(predict_dir, exist_ok=True)
     module.predict_dir = predict_dir
+    if async_io:
+        from .utils.image_writer import AsyncImageWriter
+        module.writer = AsyncImageWriter(predict_dir)
     n = 0
     for idx, batch in enumerate(batches):
-        batch = tuple(t.to(device) if torch.is_tensor(t) else t for t in batch)
+        batch = tuple(t.to(device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
         n += len(module.predict_step(batch, idx))
+    if module.writer is not None:
+        module.writer.close()
+        module.writer = None
     return n
 
 
@@ -75,7 +81,11 @@ def main(argv=None):
     ds = SyntheticPredictSet(n, cfg.data.patch_size, cfg.data.num_classes,
                              cfg.style_sampling.get("num_patches", 1) if cfg.style_sampling.name == "mp" else 1)
     mine = torch.utils.data.Subset(ds, list(range(rank, n, world)))          # Lightning's distributed predict sampler
-    loader = torch.utils.data.DataLoader(mine, batch_size=batch_size, shuffle=False, num_workers=0)
+    # input side of the plumbing: worker processes build the next batches into pinned memory while the GPU samples
+    # (the reference's datamodule does the same through Lightning, data/dm.py:82-87)
+    workers = int(cfg.get("num_workers", min(4, os.cpu_count() or 1)))
+    loader = torch.utils.data.DataLoader(mine, batch_size=batch_size, shuffle=False, num_workers=workers,
+                                         pin_memory=True, persistent_workers=workers > 0)
     out = cfg.get("predict_dir", os.path.join(os.getcwd(), "stedm_predict"))
     done = run(cfg, loader, out, ckpt_path=cfg.get("ckpt_path_full"))
     print(f"[rank {rank}/{world}] wrote {done} images to {out}")
