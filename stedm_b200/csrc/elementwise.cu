@@ -488,12 +488,71 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   for (int i = lane; i < cols; i += 32) o[i] = from_f32<TO>(__fdiv_rn(r[i], s));
 }
 
+// Long rows (the VAE decoder's T = L^2 = 4096+ keys, model.py:189-190): one 256-thread block per row keeps the row
+// in registers — one global read, one write — instead of the warp kernel's three passes over global memory.
+template <typename TO, int PER>
+__global__ void __launch_bounds__(256) softmax_rows_block_kernel(const float* __restrict__ x, TO* __restrict__ out,
+                                                                 int cols, float scale, int mask_diag_period) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const float* r = x + row * cols;
+  const int self_col = mask_diag_period > 0 ? static_cast<int>(row % mask_diag_period) : -1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float v[PER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = threadIdx.x + i * 256;
+    v[i] = (c < cols && c != self_col) ? r[c] * scale : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = expf(v[i] - m);   // exp(-inf) = 0 for masked / out-of-range columns
+    s += v[i];
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  TO* o = out + row * cols;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < cols) o[c] = from_f32<TO>(__fdiv_rn(v[i], s));
+  }
+}
+
 extern "C" int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale,
                                   int mask_diag_period, void* stream) {
   STEDM_REQUIRE(x && rows > 0 && cols > 0 && scale > 0.f, "softmax_rows: bad argument");
   STEDM_REQUIRE((rows + 7) / 8 < 0x7fffffffLL, "softmax_rows: too many rows");
-  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   auto s = static_cast<cudaStream_t>(stream);
+  if (cols >= 2048 && cols <= 8192 && rows < 0x7fffffffLL) {
+    const unsigned g = static_cast<unsigned>(rows);
+    const bool f32 = out == nullptr || out_dtype == DT_F32;
+    float* of = out ? static_cast<float*>(out) : x;
+    auto ob = static_cast<__nv_bfloat16*>(out);
+    if (cols <= 4096) {
+      if (f32) softmax_rows_block_kernel<float, 16><<<g, 256, 0, s>>>(x, of, cols, scale, mask_diag_period);
+      else softmax_rows_block_kernel<__nv_bfloat16, 16><<<g, 256, 0, s>>>(x, ob, cols, scale, mask_diag_period);
+    } else {
+      if (f32) softmax_rows_block_kernel<float, 32><<<g, 256, 0, s>>>(x, of, cols, scale, mask_diag_period);
+      else softmax_rows_block_kernel<__nv_bfloat16, 32><<<g, 256, 0, s>>>(x, ob, cols, scale, mask_diag_period);
+    }
+    return check_launch("softmax_rows");
+  }
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   if (out == nullptr || out_dtype == DT_F32)
     softmax_rows_kernel<float><<<grid, 256, 0, s>>>(x, out ? static_cast<float*>(out) : x, rows, cols, scale,
                                                     mask_diag_period);

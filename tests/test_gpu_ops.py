@@ -218,3 +218,24 @@ def test_movement_kernels(ops):
 def test_no_cpu_fallback(ops):
     with pytest.raises(RuntimeError):
         ops.linear(torch.zeros(1, 8), torch.zeros(4, 8), None)
+
+
+@pytest.mark.parametrize("cols", [256, 1026, 4096, 5000])
+@pytest.mark.parametrize("mask", [False, True])
+def test_softmax_rows_warp_and_block_kernels(cols, mask):
+    """Row softmax (openaimodel.py:392, model.py:189-190) on both kernels (warp per row; block per row for >= 2048
+    columns), fp32 in place and bf16 out, with sViT's diagonal mask (vit_set.py:52-54)."""
+    from stedm_b200 import ops
+    g = torch.Generator().manual_seed(cols)
+    rows = 2 * cols if mask else 77
+    x = torch.randn(rows, cols, generator=g) * 3
+    ref_in = x * 0.37
+    if mask:
+        ref_in = ref_in.view(2, cols, cols).masked_fill(torch.eye(cols, dtype=torch.bool), float("-inf")).view(rows, cols)
+    want = torch.softmax(ref_in, -1)
+    period = cols if mask else 0
+    got16 = ops.softmax_rows(x.clone().cuda(), 0.37, out=torch.empty(rows, cols, device="cuda", dtype=torch.bfloat16),
+                             mask_diag_period=period)
+    got32 = ops.softmax_rows(x.clone().cuda(), 0.37, mask_diag_period=period)
+    assert float((got32.cpu() - want).abs().max()) < 1e-6
+    assert float((got16.float().cpu() - want).abs().max()) < 4e-3
