@@ -233,7 +233,7 @@ def main():
     dev = torch.device("cuda", local)
     B, L, P = args.batch, args.latent, 4 * args.latent
 
-    torch.set_float32_matmul_precision("high")                    # as predict_diff.py:68 (TF32 for the library-run Swin)
+    torch.set_float32_matmul_precision("high")                    # as predict_diff.py:68 (no library GEMM is on the path)
     m = build_model(L, args.n_style, args.precision).to(dev).eval()
     m._model.use_cuda_graph = not args.no_graph                   # captured once per shape, replayed every step
     first = rank * B                                              # global sample index of this rank's shard

@@ -19,74 +19,7 @@ using namespace stedm;
 
 namespace {
 
-// ------------------------------------------------------------------------------------------ patch embedding
-// One warp per token: the 4x4x3 patch (48 floats, 4 runs of 12 contiguous NHWC floats) is staged in shared memory,
-// lane l computes channels l, l+32, ... against the [48][E] weight held in shared memory, then LayerNorm over E.
-template <int EPL>
-__global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                             const float* __restrict__ bias,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float eps,
-                                                             float* __restrict__ out_f32,
-                                                             __nv_bfloat16* __restrict__ out_bf16, int batch, int P) {
-  constexpr int E = EPL * 32, K = 48;
-  __shared__ float ws[K * E];
-  __shared__ float patch[8][K];
-  for (int i = threadIdx.x; i < K * E; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = P / 4;
-  const long long tokens = static_cast<long long>(batch) * T * T;
-  float bi[EPL], ga[EPL], be[EPL];
-#pragma unroll
-  for (int i = 0; i < EPL; ++i) {
-    bi[i] = bias ? bias[lane + 32 * i] : 0.f;
-    ga[i] = gamma[lane + 32 * i];
-    be[i] = beta[lane + 32 * i];
-  }
-  for (long long tok = static_cast<long long>(blockIdx.x) * 8 + warp; tok < tokens;
-       tok += static_cast<long long>(gridDim.x) * 8) {
-    const int tx = static_cast<int>(tok % T), ty = static_cast<int>((tok / T) % T);
-    const long long b = tok / (static_cast<long long>(T) * T);
-    const float* src = img + ((b * P + 4 * ty) * P + 4 * tx) * 3;
-    __syncwarp();
-    for (int l = lane; l < K; l += 32) patch[warp][l] = src[static_cast<long long>(l / 12) * P * 3 + (l % 12)];
-    __syncwarp();
-    float acc[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-      const float pk = patch[warp][k];
-#pragma unroll
-      for (int i = 0; i < EPL; ++i) acc[i] = fmaf(pk, ws[k * E + lane + 32 * i], acc[i]);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      acc[i] += bi[i];
-      s += acc[i];
-    }
-    const float mean = warp_sum(s) * (1.0f / E);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const float d = acc[i] - mean;
-      q = fmaf(d, d, q);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / E) + eps);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const float y = (acc[i] - mean) * rstd * ga[i] + be[i];
-      if (out_f32) out_f32[tok * E + lane + 32 * i] = y;
-      if (out_bf16) out_bf16[tok * E + lane + 32 * i] = __float2bfloat16_rn(y);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ row LayerNorm
-// A row of C channels (C % 8 == 0, C <= 2048) is owned by G lanes (power of two <= 32); a lane holds up to PER (4 or 8)
-// 8-channel items (item j of the row -> lane j % G), so every global access is a 16/32-byte vector.
+// ------------------------------------------------------------------------------------------ 8-wide vector access
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
 template <>
@@ -112,6 +45,86 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
       make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
+// ------------------------------------------------------------------------------------------ patch embedding
+// One LANE per token: the lane keeps its 4x4x3 patch (48 floats, 12 16-byte loads: consecutive lanes = consecutive
+// 48-byte runs of an image row) and all E accumulators in registers; the [48][E] weight sits in shared memory and is
+// read as broadcast float4s (one LDS.128 per 4 FMAs), and the LayerNorm over E is thread-local.  (The first version
+// used a warp per token with a lane per channel: 7 instructions per FMA-triple and a shuffle tree per token made it
+// issue-bound at 15 % of the HBM roofline.)
+template <int E>
+__global__ void __launch_bounds__(128) patch_embed_ln_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                             const float* __restrict__ bias,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             float* __restrict__ out_f32,
+                                                             __nv_bfloat16* __restrict__ out_bf16, long long tokens,
+                                                             int P) {
+  constexpr int K = 48;
+  __shared__ __align__(16) float ws[K * E];
+  __shared__ __align__(16) float s_bias[E], s_gamma[E], s_beta[E];
+  for (int i = threadIdx.x; i < K * E; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    s_bias[i] = bias ? bias[i] : 0.f;
+    s_gamma[i] = gamma[i];
+    s_beta[i] = beta[i];
+  }
+  __syncthreads();
+  const int T = P / 4;
+  for (long long tok = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; tok < tokens;
+       tok += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tx = static_cast<int>(tok % T), ty = static_cast<int>((tok / T) % T);
+    const long long b = tok / (static_cast<long long>(T) * T);
+    const float4* src = reinterpret_cast<const float4*>(img + ((b * P + 4 * ty) * P + 4 * tx) * 3);
+    float x[K];
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 v = __ldg(src + static_cast<long long>(dy) * (P * 3 / 4) + q);
+        x[dy * 12 + q * 4] = v.x; x[dy * 12 + q * 4 + 1] = v.y; x[dy * 12 + q * 4 + 2] = v.z; x[dy * 12 + q * 4 + 3] = v.w;
+      }
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; e += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(&s_bias[e]);
+      acc[e] = bv.x; acc[e + 1] = bv.y; acc[e + 2] = bv.z; acc[e + 3] = bv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int e = 0; e < E; e += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[k * E + e]);
+        acc[e] = fmaf(x[k], wv.x, acc[e]);
+        acc[e + 1] = fmaf(x[k], wv.y, acc[e + 1]);
+        acc[e + 2] = fmaf(x[k], wv.z, acc[e + 2]);
+        acc[e + 3] = fmaf(x[k], wv.w, acc[e + 3]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += acc[e];
+    const float mean = s * (1.0f / E);
+    float q2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float d = acc[e] - mean;
+      q2 = fmaf(d, d, q2);
+    }
+    const float rstd = 1.0f / sqrtf(q2 * (1.0f / E) + eps);
+#pragma unroll
+    for (int e = 0; e < E; e += 8) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (acc[e + j] - mean) * rstd * s_gamma[e + j] + s_beta[e + j];
+      if (out_f32) store8(out_f32 + tok * E + e, y);
+      if (out_bf16) store8(out_bf16 + tok * E + e, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ row LayerNorm
+// A row of C channels (C % 8 == 0, C <= 2048) is owned by G lanes (power of two <= 32); a lane holds up to PER (4 or 8)
+// 8-channel items (item j of the row -> lane j % G), so every global access is a 16/32-byte vector.
 __device__ __forceinline__ float group_sum(float v, int G) {
   for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -349,161 +362,203 @@ __device__ __forceinline__ void store16_smem(__nv_bfloat16* p, const float (&v)[
   store8(p + 8, b);
 }
 
-__global__ void __launch_bounds__(128) window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                   const float* __restrict__ logit_scale,
-                                                                   const float* __restrict__ rel_bias,
-                                                                   const float* __restrict__ qkv_bias,
-                                                                   __nv_bfloat16* __restrict__ out, int H, int W, int PH,
-                                                                   int PW, int heads, int shift_y, int shift_x) {
+constexpr int WM_WPB = 4;  // windows per block: the head's bias fragments (32 registers) are loaded once per block
+
+struct WinRaw {  // one thread's share of a window: 16 dims of token (tid / 2)'s q, k, v, still bf16
+  uint4 q0, q1, k0, k1, v0, v1;
+  long long tok;  // token index in the stored map, -1 for a padded cell
+  int region;
+};
+
+__global__ void __launch_bounds__(128, 4) window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                      const float* __restrict__ logit_scale,
+                                                                      const float* __restrict__ rel_bias,
+                                                                      const float* __restrict__ qkv_bias,
+                                                                      __nv_bfloat16* __restrict__ out, int H, int W,
+                                                                      int PH, int PW, int heads, int shift_y,
+                                                                      int shift_x, int num_windows) {
   __shared__ __align__(16) __nv_bfloat16 qs[WA_TOK * WM_LD];
   __shared__ __align__(16) __nv_bfloat16 ks[WA_TOK * WM_LD];
   __shared__ __align__(16) __nv_bfloat16 vs[WA_TOK * WM_LD];
   __shared__ int region[WA_TOK];
-  __shared__ long long tok_of[WA_TOK];  // token index in the stored map, -1 for a padded cell
+  __shared__ long long tok_of[WA_TOK];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
   const int C = heads * WA_D;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = warp * 16, i0 = r0 + g, i1 = i0 + 8;
+  const bool masked = (shift_y | shift_x) != 0;
+  const float lscale = logit_scale[head];
+  // relative position bias of this thread's accumulator cells: rows i0 / i1, columns nt*8 + 2t (+1)
+  float bf[8][4];
   {
-    // ---- stage: thread pair (2i, 2i+1) loads the two 16-dim halves of token i's q, k, v
-    const int i = tid >> 1, half = tid & 1;
-    const int wpr = PW / 8, wpi = wpr * (PH / 8);
-    const int b = blockIdx.x / wpi, wrem = blockIdx.x % wpi;
-    const int ys = (wrem / wpr) * 8 + (i >> 3), xs = (wrem % wpr) * 8 + (i & 7);
+    const float* bias0 = rel_bias + (static_cast<size_t>(head) * WA_TOK + i0) * WA_TOK;
+    const float* bias1 = bias0 + 8 * WA_TOK;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 b0 = __ldg(reinterpret_cast<const float2*>(bias0 + nt * 8 + 2 * t));
+      const float2 b1 = __ldg(reinterpret_cast<const float2*>(bias1 + nt * 8 + 2 * t));
+      bf[nt][0] = b0.x; bf[nt][1] = b0.y; bf[nt][2] = b1.x; bf[nt][3] = b1.y;
+    }
+  }
+  const int ti = tid >> 1, half = tid & 1;  // staging role: thread pair (2i, 2i+1) = the two halves of token i
+  const int wpr = PW / 8, wpi = wpr * (PH / 8);
+  auto fetch = [&](int win, WinRaw& r) {
+    const int b = win / wpi, wrem = win % wpi;
+    const int ys = (wrem / wpr) * 8 + (ti >> 3), xs = (wrem % wpr) * 8 + (ti & 7);
     const int y = (ys + shift_y) % PH, x = (xs + shift_x) % PW;
     const bool pad = y >= H || x >= W;
-    const long long tok = pad ? -1 : (static_cast<long long>(b) * H + y) * W + x;
-    if (half == 0) {
-      int ry = 0, rx = 0;
-      if (shift_y > 0) ry = ys < PH - 8 ? 0 : (ys < PH - shift_y ? 1 : 2);
-      if (shift_x > 0) rx = xs < PW - 8 ? 0 : (xs < PW - shift_x ? 1 : 2);
-      region[i] = ry * 3 + rx;
-      tok_of[i] = tok;
-    }
-    float q[16], k[16], v[16];
+    r.tok = pad ? -1 : (static_cast<long long>(b) * H + y) * W + x;
+    int ry = 0, rx = 0;
+    if (shift_y > 0) ry = ys < PH - 8 ? 0 : (ys < PH - shift_y ? 1 : 2);
+    if (shift_x > 0) rx = xs < PW - 8 ? 0 : (xs < PW - shift_x ? 1 : 2);
+    r.region = ry * 3 + rx;
     if (!pad) {
-      const __nv_bfloat16* src = qkv + tok * 3 * C + head * WA_D + half * 16;
-      load16(src, q);
-      load16(src + C, k);
-      load16(src + 2 * C, v);
-    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(qkv + r.tok * 3 * C + head * WA_D + half * 16);
+      const int cs = C / 8;  // uint4 per C channels
+      r.q0 = __ldg(src); r.q1 = __ldg(src + 1);
+      r.k0 = __ldg(src + cs); r.k1 = __ldg(src + cs + 1);
+      r.v0 = __ldg(src + 2 * cs); r.v1 = __ldg(src + 2 * cs + 1);
+    }
+  };
+  auto unpack16 = [](const uint4& a, const uint4& b, float (&v)[16]) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  };
+  const int win0 = blockIdx.x * WM_WPB;
+  WinRaw raw;
+  fetch(win0, raw);
+  for (int w = 0; w < WM_WPB && win0 + w < num_windows; ++w) {
+    {
+      // ---- stage the fetched window: normalise q (logit scale folded in) and k in fp32, round to bf16
+      float q[16], k[16], v[16];
+      if (raw.tok >= 0) {
+        unpack16(raw.q0, raw.q1, q);
+        unpack16(raw.k0, raw.k1, k);
+        unpack16(raw.v0, raw.v1, v);
+      } else {  // padded cell: q, k, v = the qkv biases (k bias is zero); its own output row is dropped
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          q[d] = 0.f;
+          k[d] = 0.f;
+          v[d] = qkv_bias ? qkv_bias[2 * C + head * WA_D + half * 16 + d] : 0.f;
+        }
+      }
+      float q2 = 0.f, k2 = 0.f;
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
-        q[d] = 0.f;
-        k[d] = 0.f;
-        v[d] = qkv_bias ? qkv_bias[2 * C + head * WA_D + half * 16 + d] : 0.f;
+        q2 = fmaf(q[d], q[d], q2);
+        k2 = fmaf(k[d], k[d], k2);
+      }
+      q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+      k2 += __shfl_xor_sync(0xffffffffu, k2, 1);
+      const float qmul = lscale / fmaxf(sqrtf(q2), 1e-12f);  // F.normalize
+      const float kmul = 1.0f / fmaxf(sqrtf(k2), 1e-12f);
+      store16_smem(&qs[ti * WM_LD + half * 16], q, qmul);
+      store16_smem(&ks[ti * WM_LD + half * 16], k, kmul);
+      store16_smem(&vs[ti * WM_LD + half * 16], v, 1.0f);
+      if (half == 0) {
+        region[ti] = raw.region;
+        tok_of[ti] = raw.tok;
       }
     }
-    float q2 = 0.f, k2 = 0.f;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      q2 = fmaf(q[d], q[d], q2);
-      k2 = fmaf(k[d], k[d], k2);
-    }
-    q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
-    k2 += __shfl_xor_sync(0xffffffffu, k2, 1);
-    const float qmul = logit_scale[head] / fmaxf(sqrtf(q2), 1e-12f);  // F.normalize, logit scale folded into q
-    const float kmul = 1.0f / fmaxf(sqrtf(k2), 1e-12f);
-    store16_smem(&qs[i * WM_LD + half * 16], q, qmul);
-    store16_smem(&ks[i * WM_LD + half * 16], k, kmul);
-    store16_smem(&vs[i * WM_LD + half * 16], v, 1.0f);
-  }
-  __syncthreads();
-  const int g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16;
-  uint32_t a[2][4];
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    a[kk][0] = *reinterpret_cast<const uint32_t*>(&qs[(r0 + g) * WM_LD + kk * 16 + 2 * t]);
-    a[kk][1] = *reinterpret_cast<const uint32_t*>(&qs[(r0 + g + 8) * WM_LD + kk * 16 + 2 * t]);
-    a[kk][2] = *reinterpret_cast<const uint32_t*>(&qs[(r0 + g) * WM_LD + kk * 16 + 2 * t + 8]);
-    a[kk][3] = *reinterpret_cast<const uint32_t*>(&qs[(r0 + g + 8) * WM_LD + kk * 16 + 2 * t + 8]);
-  }
-  float s[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    __syncthreads();
+    if (w + 1 < WM_WPB && win0 + w + 1 < num_windows) fetch(win0 + w + 1, raw);  // in flight during the MMAs below
+    uint32_t a[2][4];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&ks[(nt * 8 + g) * WM_LD + kk * 16 + 2 * t]);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&ks[(nt * 8 + g) * WM_LD + kk * 16 + 2 * t + 8]);
-      mma_bf16_16816(s[nt], a[kk], b0, b1);
+      a[kk][0] = *reinterpret_cast<const uint32_t*>(&qs[i0 * WM_LD + kk * 16 + 2 * t]);
+      a[kk][1] = *reinterpret_cast<const uint32_t*>(&qs[i1 * WM_LD + kk * 16 + 2 * t]);
+      a[kk][2] = *reinterpret_cast<const uint32_t*>(&qs[i0 * WM_LD + kk * 16 + 2 * t + 8]);
+      a[kk][3] = *reinterpret_cast<const uint32_t*>(&qs[i1 * WM_LD + kk * 16 + 2 * t + 8]);
     }
-  }
-  // ---- + relative position bias + shift mask; fp32 softmax on the accumulator fragments
-  const int i0 = r0 + g, i1 = i0 + 8;
-  const float* bias0 = rel_bias + (static_cast<size_t>(head) * WA_TOK + i0) * WA_TOK;
-  const float* bias1 = bias0 + 8 * WA_TOK;
-  const bool masked = (shift_y | shift_x) != 0;
-  const int reg0 = region[i0], reg1 = region[i1];
-  float m0 = -INFINITY, m1 = -INFINITY;
+    float s[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int j = nt * 8 + 2 * t;
-    const float2 b0 = __ldg(reinterpret_cast<const float2*>(bias0 + j));
-    const float2 b1 = __ldg(reinterpret_cast<const float2*>(bias1 + j));
-    s[nt][0] += b0.x; s[nt][1] += b0.y; s[nt][2] += b1.x; s[nt][3] += b1.y;
-    if (masked) {
-      const int rj0 = region[j], rj1 = region[j + 1];
-      if (rj0 != reg0) s[nt][0] -= 100.0f;
-      if (rj1 != reg0) s[nt][1] -= 100.0f;
-      if (rj0 != reg1) s[nt][2] -= 100.0f;
-      if (rj1 != reg1) s[nt][3] -= 100.0f;
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = bf[nt][e];  // accumulate on top of the position bias
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&ks[(nt * 8 + g) * WM_LD + kk * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&ks[(nt * 8 + g) * WM_LD + kk * 16 + 2 * t + 8]);
+        mma_bf16_16816(s[nt], a[kk], b0, b1);
+      }
     }
-    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float sum0 = 0.f, sum1 = 0.f;
+    // ---- shift mask; fp32 softmax on the accumulator fragments (a row lives in the 4 lanes of a quad)
+    const int reg0 = region[i0], reg1 = region[i1];
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = __expf(s[nt][0] - m0);
-    s[nt][1] = __expf(s[nt][1] - m0);
-    s[nt][2] = __expf(s[nt][2] - m1);
-    s[nt][3] = __expf(s[nt][3] - m1);
-    sum0 += s[nt][0] + s[nt][1];
-    sum1 += s[nt][2] + s[nt][3];
-  }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-  // ---- O = P.V: the S accumulator fragments of key tiles (2kk, 2kk+1) are the A fragment of key step kk
-  float o[4][4];
+    for (int nt = 0; nt < 8; ++nt) {
+      if (masked) {
+        const int j = nt * 8 + 2 * t;
+        const int rj0 = region[j], rj1 = region[j + 1];
+        if (rj0 != reg0) s[nt][0] -= 100.0f;
+        if (rj1 != reg0) s[nt][1] -= 100.0f;
+        if (rj0 != reg1) s[nt][2] -= 100.0f;
+        if (rj1 != reg1) s[nt][3] -= 100.0f;
+      }
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = __expf(s[nt][0] - m0);
+      s[nt][1] = __expf(s[nt][1] - m0);
+      s[nt][2] = __expf(s[nt][2] - m1);
+      s[nt][3] = __expf(s[nt][3] - m1);
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // ---- O = P.V: the S accumulator fragments of key tiles (2kk, 2kk+1) are the A fragment of key step kk
+    float o[4][4];
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, smem_u32(&vs[(kk * 16 + (lane & 15)) * WM_LD + nt * 8]));
+        mma_bf16_16816(o[nt], pa, b0, b1);
+      }
+    }
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    // ---- stage the warp's 16 x 32 output rows in its own (already consumed) rows of qs, then 16-byte global stores
+    __syncwarp();
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      uint32_t b0, b1;
-      ldmatrix_x2_trans(b0, b1, smem_u32(&vs[(kk * 16 + (lane & 15)) * WM_LD + nt * 8]));
-      mma_bf16_16816(o[nt], pa, b0, b1);
+      *reinterpret_cast<uint32_t*>(&qs[i0 * WM_LD + nt * 8 + 2 * t]) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+      *reinterpret_cast<uint32_t*>(&qs[i1 * WM_LD + nt * 8 + 2 * t]) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
-  }
-  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-  // ---- stage the warp's 16 x 32 output rows in its own (already consumed) rows of qs, then 16-byte global stores
-  __syncwarp();
+    __syncwarp();
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    *reinterpret_cast<uint32_t*>(&qs[i0 * WM_LD + nt * 8 + 2 * t]) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-    *reinterpret_cast<uint32_t*>(&qs[i1 * WM_LD + nt * 8 + 2 * t]) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int c = lane; c < 64; c += 32) {
-    const int row = r0 + (c >> 2), part = c & 3;
-    const long long tok = tok_of[row];
-    if (tok >= 0)
-      *reinterpret_cast<uint4*>(out + tok * C + head * WA_D + part * 8) =
-          *reinterpret_cast<const uint4*>(&qs[row * WM_LD + part * 8]);
+    for (int c = lane; c < 64; c += 32) {
+      const int row = r0 + (c >> 2), part = c & 3;
+      const long long tok = tok_of[row];
+      if (tok >= 0)
+        *reinterpret_cast<uint4*>(out + tok * C + head * WA_D + part * 8) =
+            *reinterpret_cast<const uint4*>(&qs[row * WM_LD + part * 8]);
+    }
+    __syncthreads();  // every warp is done with this window's K / V / region before the next one is staged
   }
 }
 
@@ -690,16 +745,17 @@ extern "C" int stedm_patch_embed_ln(const float* img, const float* w, const floa
   STEDM_REQUIRE(img && w && gamma && beta && (out_f32 || out_bf16), "patch_embed_ln: null pointer");
   STEDM_REQUIRE(patch == 4 && p > 0 && p % 4 == 0 && batch > 0, "patch_embed_ln: patch must be 4 and divide the image");
   STEDM_REQUIRE(embed == 32 || embed == 64 || embed == 96 || embed == 128, "patch_embed_ln: embed %d unsupported", embed);
+  STEDM_REQUIRE(p % 16 == 0 || (p * 3) % 4 == 0, "patch_embed_ln: image rows must be 16-byte aligned");
   const long long tokens = static_cast<long long>(batch) * (p / 4) * (p / 4);
-  const long long want = (tokens + 7) / 8;
-  const int grid = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  const long long want = (tokens + 127) / 128;
+  const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
   auto s = static_cast<cudaStream_t>(stream);
   auto ob = static_cast<__nv_bfloat16*>(out_bf16);
-  switch (embed / 32) {
-    case 1: patch_embed_ln_kernel<1><<<grid, 256, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, batch, p); break;
-    case 2: patch_embed_ln_kernel<2><<<grid, 256, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, batch, p); break;
-    case 3: patch_embed_ln_kernel<3><<<grid, 256, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, batch, p); break;
-    default: patch_embed_ln_kernel<4><<<grid, 256, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, batch, p); break;
+  switch (embed) {
+    case 32: patch_embed_ln_kernel<32><<<grid, 128, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, tokens, p); break;
+    case 64: patch_embed_ln_kernel<64><<<grid, 128, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, tokens, p); break;
+    case 96: patch_embed_ln_kernel<96><<<grid, 128, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, tokens, p); break;
+    default: patch_embed_ln_kernel<128><<<grid, 128, 0, s>>>(img, w, bias, gamma, beta, eps, out_f32, ob, tokens, p); break;
   }
   return check_launch("patch_embed_ln");
 }
@@ -744,15 +800,16 @@ extern "C" int stedm_window_attention(const void* qkv, int dtype, const float* l
   const long long windows = static_cast<long long>(batch) * (ph / 8) * (pw / 8);
   STEDM_REQUIRE(windows < (1LL << 31) && heads <= 65535, "window_attention: grid too large");
   dim3 grid(static_cast<unsigned>(windows), static_cast<unsigned>(heads));
+  dim3 grid_mma(static_cast<unsigned>((windows + WM_WPB - 1) / WM_WPB), static_cast<unsigned>(heads));
   auto s = static_cast<cudaStream_t>(stream);
   static const bool simt_bf16 = [] {  // STEDM_WINATTN_SIMT=1: CUDA-core kernel for bf16 too (A/B measurements)
     const char* e = getenv("STEDM_WINATTN_SIMT");
     return e && e[0] == '1';
   }();
   if (dtype == DT_BF16 && !simt_bf16)
-    window_attention_mma_kernel<<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), logit_scale, rel_bias,
-                                                     qkv_bias, static_cast<__nv_bfloat16*>(out), h, w, ph, pw, heads,
-                                                     sy, sx);
+    window_attention_mma_kernel<<<grid_mma, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), logit_scale, rel_bias,
+                                                         qkv_bias, static_cast<__nv_bfloat16*>(out), h, w, ph, pw,
+                                                         heads, sy, sx, static_cast<int>(windows));
   else if (dtype == DT_BF16)
     window_attention_kernel<__nv_bfloat16><<<grid, WA_TOK, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), logit_scale,
                                                                    rel_bias, qkv_bias, static_cast<__nv_bfloat16*>(out),
