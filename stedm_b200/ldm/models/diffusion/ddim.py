@@ -45,7 +45,7 @@ class DDIMSampler(object):
         ac = self.model.alphas_cumprod
         assert ac.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
         to_torch = lambda x: torch.as_tensor(x).clone().detach().to(torch.float32).to(self.model.device)
-        ac_cpu = ac.detach().cpu()
+        ac_cpu = ac.detach().cpu().numpy()           # fp32 ndarray: the reference's np.sqrt(alphas_cumprod.cpu())
         self.register_buffer("betas", to_torch(self.model.betas))
         self.register_buffer("alphas_cumprod", to_torch(ac))
         self.register_buffer("alphas_cumprod_prev", to_torch(self.model.alphas_cumprod_prev))
@@ -81,19 +81,19 @@ class DDIMSampler(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None):
         """ddim.py:112-162."""
-        if ddim_use_original_steps or score_corrector is not None or quantize_denoised:
-            raise NotImplementedError("original-step sampling / score correctors / quantize_x0 are not on STEDM's path")
+        if score_corrector is not None:
+            raise NotImplementedError("score correctors are not on STEDM's path")
         device = self.model.betas.device
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device).float()
         if timesteps is None:
-            timesteps = self.ddim_timesteps
-        else:
+            timesteps = self.ddpm_num_timesteps if ddim_use_original_steps else self.ddim_timesteps
+        elif not ddim_use_original_steps:
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
             timesteps = self.ddim_timesteps[:subset_end]
         intermediates = {"x_inter": [img], "pred_x0": [img]}
-        time_range = np.flip(timesteps)
-        total_steps = timesteps.shape[0]
+        time_range = list(reversed(range(0, timesteps))) if ddim_use_original_steps else np.flip(timesteps)
+        total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
         stepper = _GuidedStepper(self, cond, unconditional_conditioning, unconditional_guidance_scale, shape)
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
@@ -103,7 +103,8 @@ class DDIMSampler(object):
                 img = self.model.q_sample(x0, ts) * mask + (1. - mask) * img
             # ts is torch.full(step): one timestep for the whole batch -> embeddings are computed for one row
             img, pred_x0 = stepper.step(img, ts, index, temperature=temperature, noise_dropout=noise_dropout,
-                                        uniform_t=True)
+                                        uniform_t=True, use_original_steps=ddim_use_original_steps,
+                                        quantize_denoised=quantize_denoised)
             if callback:
                 callback(i)
             if img_callback:
@@ -118,12 +119,13 @@ class DDIMSampler(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, rescale_phi=0.7):
         """ddim.py:164-210, one step (kept for callers that drive the loop themselves)."""
-        if use_original_steps or score_corrector is not None or quantize_denoised:
-            raise NotImplementedError("original-step sampling / score correctors / quantize_x0 are not on STEDM's path")
+        if score_corrector is not None:
+            raise NotImplementedError("score correctors are not on STEDM's path")
         stepper = _GuidedStepper(self, c, unconditional_conditioning, unconditional_guidance_scale, tuple(x.shape),
                                  rescale_phi=rescale_phi, allow_graph=False)
         return stepper.step(x, t, index, temperature=temperature, noise_dropout=noise_dropout,
-                            repeat_noise=repeat_noise)
+                            repeat_noise=repeat_noise, use_original_steps=use_original_steps,
+                            quantize_denoised=quantize_denoised)
 
 
 class _GuidedStepper:
@@ -196,16 +198,28 @@ class _GuidedStepper:
         ops.LAUNCHES[0] += ent["launches"]
         return ent["eps"].clone()
 
-    def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False, uniform_t=False):
+    def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False, uniform_t=False,
+             use_original_steps=False, quantize_denoised=False):
         s = self.s
         x = x.float().contiguous()
         eps = self._eps(x, t, uniform_t)
         e_c, e_u = (eps[:self.b], eps[self.b:]) if self.guided else (eps, None)
-        sigma = _f32(s.ddim_sigmas[index])
+        if use_original_steps:          # the 1000-step DDPM tables instead of the DDIM subsequence (ddim.py:188-191)
+            m = self.model
+            a_t, a_prev = float(m.alphas_cumprod[index]), float(m.alphas_cumprod_prev[index])
+            sigma = float(s.ddim_sigmas_for_original_num_steps[index])
+            sq1m = float(m.sqrt_one_minus_alphas_cumprod[index])
+        else:
+            a_t, a_prev = _f32(s.ddim_alphas[index]), _f32(s.ddim_alphas_prev[index])
+            sigma, sq1m = _f32(s.ddim_sigmas[index]), _f32(s.ddim_sqrt_one_minus_alphas[index])
         # the reference draws randn every step, also when sigma == 0 (ddim.py:206): keep the RNG stream aligned
         noise = noise_like(x.shape, x.device, repeat_noise) * temperature
         if noise_dropout > 0.:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
-        return ops.cfg_ddim_step(e_c, e_u, x, _f32(s.ddim_alphas[index]), _f32(s.ddim_alphas_prev[index]), sigma,
-                                 _f32(s.ddim_sqrt_one_minus_alphas[index]), cfg_scale=self.scale, phi=self.phi,
-                                 noise=noise.contiguous() if sigma != 0.0 else None)
+        x_prev, pred_x0 = ops.cfg_ddim_step(e_c, e_u, x, a_t, a_prev, sigma, sq1m, cfg_scale=self.scale, phi=self.phi,
+                                            noise=noise.contiguous() if sigma != 0.0 else None)
+        if quantize_denoised:           # ddim.py:200-201: pred_x0 snapped to the VQ codebook before it enters x_prev
+            pq = ops.vq_nearest(pred_x0, self.model.first_stage_model.quantize.embedding.weight.detach().float().contiguous())
+            x_prev = x_prev + (a_prev ** 0.5) * (pq - pred_x0)     # x_prev = sqrt(a_prev) pred_x0 + dir_xt + noise
+            pred_x0 = pq
+        return x_prev, pred_x0

@@ -350,3 +350,63 @@ def test_config0_flowers_b4_256_full_path_vs_reference_golden(precision, z_bar, 
     print(f"config0 {precision}: eps rel {r_e:.2e}  DDIM-50 latent rel {r_z:.2e}  decode PSNR {p_dec:.1f} dB  "
           f"end-to-end PSNR {p_e2e:.1f} dB")
     assert r_z < z_bar and p_dec >= PSNR_BAR and p_e2e >= psnr_bar
+
+
+def test_ddim_eta_mask_original_steps_and_quantize_branches():
+    """The optional branches of ddim.py around the same U-Net call: eta > 0 (sigma*noise, :206-209),
+    mask / x0 in-painting (:143-146), use_original_steps (:188-191) and quantize_denoised (:200-201), each against the
+    oracle's restatement of the step tail fed with the engine's own eps."""
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    model = m._model
+    cond, unc = _cond(g, "c_crossattn"), _cond(g, "uc_crossattn")
+    x = x_T.cuda()
+    s = DDIMSampler(model)
+    s.make_schedule(ddim_num_steps=50, ddim_eta=0.7, verbose=False)
+    ts = torch.full((2,), int(s.ddim_timesteps[30]), device="cuda", dtype=torch.long)
+    e = O.cfg_combine(model.apply_model(x, ts, cond).cpu(), model.apply_model(x, ts, unc).cpu(), 1.5)
+    # eta > 0: same RNG stream as the reference (one randn per step)
+    torch.manual_seed(5)
+    xp, p0 = s.p_sample_ddim(x, cond, ts, index=30, unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
+    torch.manual_seed(5)
+    noise = torch.randn(x.shape, device="cuda").cpu()
+    sig = float(s.ddim_sigmas[30])
+    assert sig > 0
+    wx, wp = O.ddim_update(x_T, e, s.ddim_alphas[30], s.ddim_alphas_prev[30], sig, s.ddim_sqrt_one_minus_alphas[30], noise)
+    assert max_abs(xp, wx) < 2e-4 and max_abs(p0, wp) < 2e-4
+    # original 1000-step tables: index = t
+    t_idx = 481
+    ts2 = torch.full((2,), t_idx, device="cuda", dtype=torch.long)
+    e2 = O.cfg_combine(model.apply_model(x, ts2, cond).cpu(), model.apply_model(x, ts2, unc).cpu(), 1.5)
+    torch.manual_seed(6)
+    xp, p0 = s.p_sample_ddim(x, cond, ts2, index=t_idx, use_original_steps=True, unconditional_guidance_scale=1.5,
+                             unconditional_conditioning=unc)
+    torch.manual_seed(6)
+    noise = torch.randn(x.shape, device="cuda").cpu()
+    wx, wp = O.ddim_update(x_T, e2, model.alphas_cumprod[t_idx].cpu(), model.alphas_cumprod_prev[t_idx].cpu(),
+                           s.ddim_sigmas_for_original_num_steps[t_idx].cpu(),
+                           model.sqrt_one_minus_alphas_cumprod[t_idx].cpu(), noise)
+    assert max_abs(xp, wx) < 2e-4 and max_abs(p0, wp) < 2e-4
+    # quantize_denoised: pred_x0 snapped to the codebook, x_prev rebuilt from it
+    s0 = DDIMSampler(model)
+    s0.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    xq, pq = s0.p_sample_ddim(x * 40, cond, ts, index=30, quantize_denoised=True, unconditional_guidance_scale=1.5,
+                              unconditional_conditioning=unc)
+    eq = O.cfg_combine(model.apply_model(x * 40, ts, cond).cpu(), model.apply_model(x * 40, ts, unc).cpu(), 1.5)
+    _, wp = O.ddim_update(x_T * 40, eq, s0.ddim_alphas[30], s0.ddim_alphas_prev[30], 0.0, s0.ddim_sqrt_one_minus_alphas[30])
+    cb = model.first_stage_model.quantize.embedding.weight.detach().cpu().float()
+    wq, _ = O.vq_quantize(wp, cb)
+    a_prev = torch.tensor(float(s0.ddim_alphas_prev[30]))
+    wxq = a_prev.sqrt() * wq + (1.0 - a_prev).sqrt() * eq
+    assert float((pq.cpu() != wq).float().mean()) < 0.01          # a code flips only when two codes are ~equidistant
+    assert max_abs(xq.cpu() - a_prev.sqrt() * pq.cpu(), wxq - a_prev.sqrt() * wq) < 2e-3
+    # in-painting: masked region follows q_sample(x0, t), the sampler runs and returns the right shapes
+    mask = torch.zeros(2, 1, 32, 32, device="cuda")
+    mask[..., :16] = 1
+    z, inter = s0.sample(4, 2, (3, 32, 32), conditioning=cond, verbose=False, x_T=x, mask=mask, x0=torch.zeros_like(x),
+                         eta=0.0, unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
+    assert tuple(z.shape) == (2, 3, 32, 32) and bool(torch.isfinite(z).all())
+    z2, _ = s0.ddim_sampling(cond, (2, 3, 32, 32), x_T=x, ddim_use_original_steps=True, timesteps=3,
+                             unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
+    assert bool(torch.isfinite(z2).all())
