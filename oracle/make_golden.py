@@ -3,7 +3,7 @@ on fixture weights, and assert that oracle/stedm_oracle.py reproduces every tens
 
 Run once in the build container (the reference cannot travel to the GPU box):
 
-    python -m oracle.make_golden [--only small|c1|sched|svit]
+    python -m oracle.make_golden [--only small|c1|sched|svit|plms]
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -197,6 +197,55 @@ def gen_svit():
     print("[svit] wrote svit.npz")
 
 
+class _StandInModel:
+    """The minimum a reference sampler touches (plms.py:12-56, 177-191), with a deterministic non-linear eps so that the
+    sampler arithmetic — timestep sequence, multistep coefficients, guidance combine, x_prev update — can be run through
+    the REFERENCE PLMSSampler, which cannot take STEDM's dict conditioning (torch.cat of conditionings, plms.py:179)."""
+
+    def __init__(self):
+        ac, _ = O.alphas_cumprod_linear()
+        self.num_timesteps = 1000
+        self.alphas_cumprod = torch.from_numpy(ac)
+        self.alphas_cumprod_prev = torch.cat([torch.ones(1), self.alphas_cumprod[:-1]])
+        self.betas = torch.from_numpy(np.linspace(0.0015 ** 0.5, 0.0205 ** 0.5, 1000, dtype=np.float64) ** 2).float()
+        self.device = torch.device("cpu")
+
+    @staticmethod
+    def eps(x, t, c):
+        return torch.tanh(0.3 * x + c) * (1.0 + t.float().view(-1, 1, 1, 1) / 1000.0)
+
+    def apply_model(self, x, t, c):
+        return self.eps(x, t, c)
+
+
+@torch.no_grad()
+def gen_plms():
+    """PLMS sampler arithmetic: reference PLMSSampler on the stand-in model == oracle.plms_sample; stores the result."""
+    ref_shims.install()
+    import contextlib
+    import io
+    from ldm.models.diffusion.plms import PLMSSampler
+    PLMSSampler.register_buffer = lambda self, n, a: setattr(self, n, a)        # the original hard-codes .to("cuda")
+    model = _StandInModel()
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(2, 3, 8, 8, generator=g)
+    c, uc = torch.randn(2, 3, 8, 8, generator=g) * 0.5, torch.zeros(2, 3, 8, 8)
+    out = {}
+    for name, scale in (("plms_s20_cfg1", 1.0), ("plms_s20_cfg3", 3.0)):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            want, _ = PLMSSampler(model).sample(20, 2, (3, 8, 8), conditioning=c, verbose=False, x_T=x_T, eta=0.0,
+                                                unconditional_guidance_scale=scale,
+                                                unconditional_conditioning=None if scale == 1.0 else uc)
+        got = O.plms_sample(lambda x, t: model.eps(x, t, c), x_T, S=20, cfg_scale=scale,
+                            uncond_eps_fn=None if scale == 1.0 else (lambda x, t: model.eps(x, t, uc)))
+        d = maxdiff(want, got)
+        print(f"[{name}] oracle vs reference PLMSSampler: max|d| = {d:.3e}")
+        assert d < 1e-5
+        out[name] = want.numpy()
+    np.savez_compressed(os.path.join(GOLD, "plms.npz"), **out)
+    print("[plms] wrote plms.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -206,6 +255,8 @@ if __name__ == "__main__":
         gen_sched()
     if a.only in ("all", "svit"):
         gen_svit()
+    if a.only in ("all", "plms"):
+        gen_plms()
     if a.only in ("all", "small"):
         # B=2, latent 32 (128^2 image), two style images per sample (exercises Agg_Mean), full DDIM-50
         gen_case("small_b2_l32", B=2, L=32, n_style=2, S=50, full_steps=True, seed=0, store_f16_image=False)

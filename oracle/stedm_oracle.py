@@ -203,6 +203,51 @@ def ddim_sample(sd, cond, uncond, x_T, S=50, eta=0.0, cfg_scale=1.5, num_heads=8
     return img, inter
 
 
+def plms_sample(eps_fn, x_T, S=50, cfg_scale=1.0, uncond_eps_fn=None, max_steps=None):
+    """PLMSSampler.sample / plms_sampling / p_sample_plms, ldm/models/diffusion/plms.py:113-236, eta = 0:
+    e_t = e_u + w (e_c - e_u) (plain guidance, :184); first step = pseudo improved Euler (:219-223), then
+    Adams-Bashforth orders 2-4 over the kept eps history (:224-232); x_prev from e_t_prime (:198-216).
+    ``eps_fn(x, t)`` / ``uncond_eps_fn(x, t)`` stand for apply_model with the (un)conditional conditioning."""
+    tab = ddim_tables(S, 0.0)
+    ts = tab["timesteps"]
+    total = ts.shape[0]
+    time_range = np.flip(ts)
+    img = x_T
+    old_eps = []
+
+    def model_output(x, t):
+        e = eps_fn(x, t)
+        if uncond_eps_fn is not None and cfg_scale != 1.0:
+            e_u = uncond_eps_fn(x, t)
+            e = e_u + cfg_scale * (e - e_u)
+        return e
+
+    def x_prev_of(x, e, index):
+        return ddim_update(x, e, tab["a_t"][index], tab["a_prev"][index], 0.0, tab["sqrt_one_minus_a"][index])
+
+    for i, step in enumerate(time_range):
+        if max_steps is not None and i >= max_steps:
+            break
+        index = total - i - 1
+        t = torch.full((img.shape[0],), int(step), dtype=torch.long)
+        t_next = torch.full((img.shape[0],), int(time_range[min(i + 1, len(time_range) - 1)]), dtype=torch.long)
+        e_t = model_output(img, t)
+        if len(old_eps) == 0:
+            x_prev, _ = x_prev_of(img, e_t, index)
+            e_prime = (e_t + model_output(x_prev, t_next)) / 2
+        elif len(old_eps) == 1:
+            e_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img, _ = x_prev_of(img, e_prime, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+    return img
+
+
 # --------------------------------------------------------------------------------------------------
 # conditioning: SpatialRescaler (encoders/modules.py:104-133) and Agg_Mean (networks/agg_blocks.py:57-75)
 # --------------------------------------------------------------------------------------------------

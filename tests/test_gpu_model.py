@@ -410,3 +410,37 @@ def test_ddim_eta_mask_original_steps_and_quantize_branches():
     z2, _ = s0.ddim_sampling(cond, (2, 3, 32, 32), x_T=x, ddim_use_original_steps=True, timesteps=3,
                              unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
     assert bool(torch.isfinite(z2).all())
+
+
+def test_plms_sampler_matches_oracle():
+    """PLMSSampler (plms.py) on the native U-Net: first five steps (improved Euler, then Adams-Bashforth orders 2-4)
+    against oracle.plms_sample — itself bit-equal to the reference's sampler class — with the oracle U-Net as eps."""
+    from stedm_b200.ldm.models.diffusion.plms import PLMSSampler
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision="fp32")
+    model = m._model
+    sd = oracle_state_dict(model)
+    cond, unc = _cond(g, "c_crossattn"), _cond(g, "uc_crossattn")
+    s = PLMSSampler(model)
+    s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    tr = np.flip(s.ddim_timesteps)
+    img, old = x_T.cuda(), []
+    n_steps = 5
+    for i in range(n_steps):
+        ts = torch.full((2,), int(tr[i]), device="cuda", dtype=torch.long)
+        tn = torch.full((2,), int(tr[i + 1]), device="cuda", dtype=torch.long)
+        img, p0, e_t = s.p_sample_plms(img, cond, ts, index=50 - i - 1, unconditional_guidance_scale=1.5,
+                                       unconditional_conditioning=unc, old_eps=old, t_next=tn)
+        old.append(e_t)
+        if len(old) >= 4:
+            old.pop(0)
+    oc, ou = _cond(g, "c_crossattn", "cpu"), _cond(g, "uc_crossattn", "cpu")
+    with torch.no_grad():
+        want = O.plms_sample(lambda x, t: O.apply_model(sd, x, t, oc), x_T, S=50, cfg_scale=1.5,
+                             uncond_eps_fn=lambda x, t: O.apply_model(sd, x, t, ou), max_steps=n_steps)
+    assert max_abs(img, want) < 5e-4, max_abs(img, want)
+    z, inter = s.sample(50, 2, (3, 32, 32), conditioning=cond, verbose=False, x_T=x_T.cuda(), timesteps=None,
+                        unconditional_guidance_scale=1.5, unconditional_conditioning=unc, log_every_t=10)
+    assert tuple(z.shape) == (2, 3, 32, 32) and bool(torch.isfinite(z).all()) and len(inter["x_inter"]) == 7
+    with pytest.raises(ValueError):
+        s.make_schedule(ddim_num_steps=50, ddim_eta=0.5, verbose=False)

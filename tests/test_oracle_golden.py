@@ -71,3 +71,18 @@ def test_oracle_conditioning_small(fixture_sd):
     c = O.get_conditioning(fixture_sd, seg, style)
     assert max_abs(c["c_concat"][0], g["c_concat"]) < 1e-6
     assert max_abs(c["c_crossattn"][0], g["c_crossattn"]) < 1e-4
+
+
+def test_oracle_plms_matches_reference_sampler_golden():
+    """oracle.plms_sample == the reference's PLMSSampler run on the stand-in model of oracle/make_golden.py
+    (tests/golden/plms.npz): pins timestep order, multistep coefficients, plain CFG and the x_prev update."""
+    import torch
+    from oracle import stedm_oracle as O
+    eps = lambda x, t, c: torch.tanh(0.3 * x + c) * (1.0 + t.float().view(-1, 1, 1, 1) / 1000.0)
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(2, 3, 8, 8, generator=g)
+    c, uc = torch.randn(2, 3, 8, 8, generator=g) * 0.5, torch.zeros(2, 3, 8, 8)
+    gold = load_golden("plms")
+    got1 = O.plms_sample(lambda x, t: eps(x, t, c), x_T, S=20)
+    got3 = O.plms_sample(lambda x, t: eps(x, t, c), x_T, S=20, cfg_scale=3.0, uncond_eps_fn=lambda x, t: eps(x, t, uc))
+    assert max_abs(got1, gold["plms_s20_cfg1"]) < 1e-6 and max_abs(got3, gold["plms_s20_cfg3"]) < 1e-6
