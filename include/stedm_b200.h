@@ -121,6 +121,15 @@ typedef struct stedm_conv_desc {
   int32_t phase;       /* tap_mode 1: py*2 + px */
   int32_t act;         /* activation applied to (acc + bias + emb) before the residual add: STEDM_ACT_NONE, or
                           STEDM_ACT_GELU = exact erf GELU (the Swin-V2 MLP, torchvision swin_transformer.py MLP/nn.GELU) */
+  int32_t skip_c0, skip_c1;  /* tensor-core path: channels of the fused skip input (see skip_x0) */
+  int32_t skip_x1_batch;     /* 0 => batch; otherwise skip_x1 is broadcast as b % skip_x1_batch */
+  const void* skip_x0; /* tensor-core path, optional: ResBlock.skip_connection / ResnetBlock.nin_shortcut (the 1x1 conv
+                          on the block INPUT, openaimodel.py:246-256, model.py:104-119) fused into the block's last 3x3
+                          conv: out = conv_kxk([x0 | x1]) + conv_1x1([skip_x0 | skip_x1]) accumulated in the same TMEM
+                          tile.  skip inputs are NHWC [batch, in_h, in_w, skip_c*]; `weight` = bf16
+                          [cout][k*k*(c0+c1) + skip_c0 + skip_c1] (the 1x1 weights appended along K), `bias` = the sum
+                          of both biases.  NULL => no fused skip. */
+  const void* skip_x1; /* second skip source (channel concat) or NULL */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(const SimtGemmParams
 extern "C" int stedm_conv_simt(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_simt: null pointer");
   STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_simt: ksize %d unsupported", d->ksize);
+  STEDM_REQUIRE(d->skip_x0 == nullptr, "conv_simt: the fused skip input is a tensor-core path feature");
   STEDM_REQUIRE(d->stride == 1 || d->stride == 2, "conv_simt: stride %d unsupported", d->stride);
   STEDM_REQUIRE(!(d->upsample && d->stride != 1), "conv_simt: upsample with stride");
   STEDM_REQUIRE(d->c0 > 0 && d->c0 % 4 == 0 && d->c1 % 4 == 0 && (d->c1 == 0 || d->x1),

@@ -72,6 +72,9 @@ struct TcParams {
   int out_nchw, cout_store;
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
   int act;               // STEDM_ACT_*: applied to acc + bias + emb, before the residual
+  // fused 1x1 skip convolution (ResBlock skip_connection / nin_shortcut): extra K slabs after the k x k taps, read at
+  // the output pixel itself from a second input [skip0 | skip1]; its weights are appended along K
+  int skip_c0_blks, skip_blks, skip_x1_batch;
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -100,7 +103,8 @@ struct TcCfg {
 template <int BN, int CL, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, PAIR>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_s0,
+               const __grid_constant__ CUtensorMap map_s1, const TcParams p) {
   static_assert(!PAIR || CL == 2, "cta_group::2 needs a 2-CTA cluster");
   using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -116,12 +120,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
-  const int num_kb = p.taps * p.c_blks;
+  const int main_kb = p.taps * p.c_blks;
+  const int num_kb = main_kb + p.skip_blks;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_w);
+    if (p.skip_blks > 0) {
+      tma_prefetch_desc(&map_s0);
+      tma_prefetch_desc(&map_s1);
+    }
     for (int i = 0; i < Cfg::STAGES; ++i) {
       // PAIR: the leader's full barrier collects both CTAs' producers; its single commit frees the slab in both
       mbar_init(&full_bar[i], PAIR ? 2 : 1);
@@ -164,29 +173,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(&empty_bar[s], ph ^ 1);
           if constexpr (PAIR) mbar_arrive_expect_tx_cluster(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES, 0);
           else mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-          const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
-          int dy = 0, dx = 0;
-          if (p.tap_mode == 1) {        // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
-            dy = (tap >> 1) - 1 + p.py;
-            dx = (tap & 1) - 1 + p.px;
-          } else if (p.ksize == 3) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+          // which activation slab: tap (r, s) x 64-channel block of [x0 | x1], or a block of the fused skip input
+          const CUtensorMap* amap;
+          int ach, ab, dy = 0, dx = 0;
+          if (kb < main_kb) {
+            const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
+            if (p.tap_mode == 1) {      // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
+              dy = (tap >> 1) - 1 + p.py;
+              dx = (tap & 1) - 1 + p.px;
+            } else if (p.ksize == 3) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+            const bool first = cb < p.c0_blks;
+            amap = first ? &map_a0 : &map_a1;
+            ach = (first ? cb : cb - p.c0_blks) * TC_BK;
+            ab = first ? b0 : b1;
+          } else {
+            const int sb = kb - main_kb;
+            const bool first = sb < p.skip_c0_blks;
+            amap = first ? &map_s0 : &map_s1;
+            ach = (first ? sb : sb - p.skip_c0_blks) * TC_BK;
+            ab = (first || p.skip_x1_batch <= 0) ? b0 : (b0 % p.skip_x1_batch);
           }
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           if constexpr (PAIR) {
-            if (cb < p.c0_blks)
-              tma_load_4d_2sm(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
-            else
-              tma_load_4d_2sm(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
+            tma_load_4d_2sm(sa, amap, &full_bar[s], ach, x0 + dx, y0 + dy, ab);
             // this CTA's half of the weight slab: rows [rank*BN/2, +BN/2)
             tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
             continue;
           }
-          if (cb < p.c0_blks)
-            tma_load_4d(sa, &map_a0, &full_bar[s], cb * TC_BK, x0 + dx, y0 + dy, b0);
-          else
-            tma_load_4d(sa, &map_a1, &full_bar[s], (cb - p.c0_blks) * TC_BK, x0 + dx, y0 + dy, b1);
+          tma_load_4d(sa, amap, &full_bar[s], ach, x0 + dx, y0 + dy, ab);
           if (CL == 1) {
             tma_load_2d(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0);
           } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
@@ -542,7 +559,8 @@ int tc_num_sms() {
 }
 
 template <int BN, int CL, bool PAIR = false>
-int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, TcParams p, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
+              const CUtensorMap& ms1, TcParams p, cudaStream_t stream) {
   using Cfg = TcCfg<BN, PAIR>;
   static bool configured = false;  // per-process; the attribute is per-function and idempotent
   if (!configured) {
@@ -570,7 +588,7 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR>, ma0, ma1, mw, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR>, ma0, ma1, mw, ms0, ms1, p);
   if (e != cudaSuccess) {
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
@@ -629,7 +647,7 @@ extern "C" long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d) {
   if (d == nullptr || d->cout < 16 || d->cout % 16 != 0 || d->batch <= 0) return 0;
   const long long M = static_cast<long long>(d->batch) * d->in_h * d->in_w;
   const int taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
-  const int num_kb = taps * ((d->c0 + d->c1 + TC_BK - 1) / TC_BK);
+  const int num_kb = taps * ((d->c0 + d->c1 + TC_BK - 1) / TC_BK) + (d->skip_x0 ? (d->skip_c0 + d->skip_c1) / TC_BK : 0);
   return static_cast<long long>(tc_plan(M, d->cout, num_kb, d->stats_out != nullptr).ws_bytes);
 }
 
@@ -702,16 +720,52 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
   // channel tile, 2-CTA cluster (cta_group::2 pair or weight multicast) and split-K plan
   const int c_blks = (ctot + TC_BK - 1) / TC_BK;
-  TcPlan plan = tc_plan(M, d->cout, taps * c_blks, d->stats_out != nullptr);
+  // fused 1x1 skip convolution: a second input [skip_x0 | skip_x1] of the output's spatial size, extra K slabs
+  const int skip_c = d->skip_x0 ? d->skip_c0 + d->skip_c1 : 0;
+  const int skip_blks = skip_c / TC_BK;
+  if (d->skip_x0) {
+    STEDM_REQUIRE(d->tap_mode == 0 && ctot % TC_BK == 0 && d->skip_c0 > 0 && d->skip_c0 % TC_BK == 0 &&
+                      d->skip_c1 % TC_BK == 0 && (d->skip_c1 == 0 || d->skip_x1),
+                  "conv_tc: fused skip input needs dense taps and channel counts that are multiples of 64 (%d, %d)",
+                  d->skip_c0, d->skip_c1);
+  }
+  const int skip_x1b = (skip_c > 0 && d->skip_c1 > 0 && d->skip_x1_batch > 0 && d->skip_x1_batch != B) ? d->skip_x1_batch : 0;
+  if (skip_x1b > 0)
+    STEDM_REQUIRE((static_cast<long long>(skip_x1b) * H * W) % TC_BM == 0 || tb == 1,
+                  "conv_tc: broadcast skip batch %d not tile aligned", skip_x1b);
+  CUtensorMap ms0 = ma0, ms1 = ma0;
+  if (skip_c > 0) {
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    {
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->skip_c0), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                static_cast<uint64_t>(B)};
+      const uint64_t str[3] = {static_cast<uint64_t>(d->skip_c0) * 2, static_cast<uint64_t>(W) * d->skip_c0 * 2,
+                               static_cast<uint64_t>(H) * W * d->skip_c0 * 2};
+      int rc = make_tmap_bf16(&ms0, d->skip_x0, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    ms1 = ms0;
+    if (d->skip_c1 > 0) {
+      const int bs1 = skip_x1b > 0 ? skip_x1b : B;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d->skip_c1), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                static_cast<uint64_t>(bs1)};
+      const uint64_t str[3] = {static_cast<uint64_t>(d->skip_c1) * 2, static_cast<uint64_t>(W) * d->skip_c1 * 2,
+                               static_cast<uint64_t>(H) * W * d->skip_c1 * 2};
+      int rc = make_tmap_bf16(&ms1, d->skip_x1, 4, dims, str, box);
+      if (rc) return rc;
+    }
+  }
+  TcPlan plan = tc_plan(M, d->cout, taps * c_blks + skip_blks, d->stats_out != nullptr);
   if (plan.ksplit > 1 && (d->workspace == nullptr || static_cast<size_t>(d->workspace_bytes) < plan.ws_bytes)) {
     plan.ksplit = 1;                        // no (or too small a) workspace: single pass
-    plan.kb_per_split = taps * c_blks;
+    plan.kb_per_split = taps * c_blks + skip_blks;
   }
   const int bn = plan.bn, cl = plan.cl;
   const bool pair = plan.pair;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(d->cout)};
-    const uint64_t str[1] = {static_cast<uint64_t>(taps) * ctot * 2};
+    const uint64_t ktot = static_cast<uint64_t>(taps) * ctot + skip_c;
+    const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->cout)};
+    const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {TC_BK, static_cast<uint32_t>(bn / cl)};  // multicast half / pair half / whole slab
     int rc = make_tmap_bf16(&mw, d->weight, 2, dims, str, box);
     if (rc) return rc;
@@ -731,6 +785,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
   p.act = d->act;
+  p.skip_blks = skip_blks; p.skip_c0_blks = skip_c > 0 ? d->skip_c0 / TC_BK : 0; p.skip_x1_batch = skip_x1b;
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {
     STEDM_REQUIRE(bn >= 64 && d->cout % bn == 0 && d->out_nchw == 0 && (H * W) % TC_BM == 0,
@@ -742,12 +797,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256:
-      if (pair) return launch_tc<256, 2, true>(ma0, ma1, mw, p, s);
-      return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, p, s) : launch_tc<256, 1>(ma0, ma1, mw, p, s);
+      if (pair) return launch_tc<256, 2, true>(ma0, ma1, mw, ms0, ms1, p, s);
+      return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, ms0, ms1, p, s) : launch_tc<256, 1>(ma0, ma1, mw, ms0, ms1, p, s);
     case 128:
-      if (pair) return launch_tc<128, 2, true>(ma0, ma1, mw, p, s);
-      return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, p, s) : launch_tc<128, 1>(ma0, ma1, mw, p, s);
-    case 64: return launch_tc<64, 1>(ma0, ma1, mw, p, s);
-    default: return launch_tc<16, 1>(ma0, ma1, mw, p, s);
+      if (pair) return launch_tc<128, 2, true>(ma0, ma1, mw, ms0, ms1, p, s);
+      return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, ms0, ms1, p, s) : launch_tc<128, 1>(ma0, ma1, mw, ms0, ms1, p, s);
+    case 64: return launch_tc<64, 1>(ma0, ma1, mw, ms0, ms1, p, s);
+    default: return launch_tc<16, 1>(ma0, ma1, mw, ms0, ms1, p, s);
   }
 }

@@ -16,6 +16,7 @@ import torch
 from . import ops
 
 PAD_TC = 64   # channel padding granularity of the tensor-core path (one 128-byte K slab of bf16)
+FUSE_SKIP = [True]   # fold ResBlock 1x1 skip convolutions into the second 3x3 conv (A/B switch for measurements)
 PAD_SIMT = 4
 
 
@@ -111,9 +112,27 @@ class PackedConv:
         tiles = torch.empty((reps * m_tiles, self.cout, 2), device=x.device, dtype=torch.float32)
         return tiles, (tiles, self.cout, reps, m_tiles, h * w_ // 128, b)
 
+    def fuse_skip(self, skip):
+        """Fold a 1x1 skip convolution on the block input (ResBlock.skip_connection, openaimodel.py:246-256;
+        ResnetBlock.nin_shortcut, model.py:104-119) into this convolution: its [Cout][Cin_skip] weights are appended
+        along K and its bias added, so out = conv(a) + skip(x) accumulates in one TMEM tile — no separate launch, no
+        skip tensor written and re-read as a residual.  Tensor-core path only."""
+        assert self.tc and skip.tc and skip.ksize == 1 and skip.cout == self.cout and self.stride == 1
+        self.weight = torch.cat([self.weight, skip.weight], dim=1).contiguous()
+        if skip.bias is not None:
+            self.bias = skip.bias.clone() if self.bias is None else (self.bias + skip.bias).contiguous()
+        self.has_skip = True
+
     def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False,
-                 want_stats=False):
+                 want_stats=False, skip=None):
         out_dtype = out_dtype or self.prec.act
+        if skip is not None:
+            assert self.tc and getattr(self, "has_skip", False) and not upsample and self.stride == 1
+            tiles, meta = self._tile_stats(x0, want_stats)
+            out = ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
+                           out_dtype=out_dtype, tensor_core=True, stats_out=tiles, skip_x0=skip[0], skip_x1=skip[1])
+            out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
+            return out
         if self.tc:
             if self.stride == 2:
                 assert x1 is None and self.ksize == 3
@@ -183,12 +202,18 @@ class PackedResBlock:
         self.c1 = PackedConv(conv1.weight, conv1.bias, prec, cin_split=cin_split)
         self.c2 = PackedConv(conv2.weight, conv2.bias, prec)
         self.skip = None if skip is None else PackedConv(skip.weight, skip.bias, prec, cin_split=cin_split)
+        self.fused_skip = False
+        if self.skip is not None and prec.tc and FUSE_SKIP[0]:
+            self.c2.fuse_skip(self.skip)          # the skip GEMM rides along the second 3x3 conv's K loop
+            self.fused_skip = True
         self.prec = prec
 
     def __call__(self, x0, x1, emb, pool):
         a = self.n1(x0, x1, True, self.prec.act, pool.next())
         h = self.c1(a, emb=emb, want_stats=True)
         a = self.n2(h, None, True, self.prec.act, pool.next())
+        if self.fused_skip:
+            return self.c2(a, want_stats=True, skip=(x0, x1))
         if self.skip is not None:
             xs = self.skip(x0, x1)
         else:

@@ -137,10 +137,10 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0):
+         act=0, skip_x0=None, skip_x1=None):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
-    _cuda(x0, x1, weight, bias, residual)
+    _cuda(x0, x1, weight, bias, residual, skip_x0, skip_x1)
     if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
         assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] == cout
         assert emb.shape[0] in (1, x0.shape[0])          # one row per sample, or one row broadcast to all samples
@@ -166,6 +166,13 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.cout_store = cout_store if out_nchw else 0
     d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
     d.act = act
+    skip_c = 0
+    if skip_x0 is not None:     # fused 1x1 skip convolution over [skip_x0 | skip_x1] (weights appended along K)
+        assert tensor_core and skip_x0.shape[1:3] == (h, w) and skip_x0.shape[0] == b and skip_x0.dtype == x0.dtype
+        d.skip_x0, d.skip_x1 = _ptr(skip_x0), _ptr(skip_x1)
+        d.skip_c0, d.skip_c1 = skip_x0.shape[-1], 0 if skip_x1 is None else skip_x1.shape[-1]
+        d.skip_x1_batch = 0 if skip_x1 is None or skip_x1.shape[0] == b else skip_x1.shape[0]
+        skip_c = d.skip_c0 + d.skip_c1
     out._stats_written = stats_out is not None
     if tensor_core and SPLIT_K[0] and b * h * w <= SPLITK_MAX_PIXELS:
         # small launches (few output tiles, deep K): split-K over the idle SMs through a caller-owned workspace.
@@ -181,8 +188,8 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
             d.stats_out = _ptr(stats_out)
     if tensor_core:
         ntaps = 4 if up_phase is not None else ksize * ksize
-        assert weight.dtype == torch.bfloat16 and weight.numel() == cout * ntaps * (c0 + c1), \
-            (weight.shape, cout, ksize, c0, c1)
+        assert weight.dtype == torch.bfloat16 and weight.numel() == cout * (ntaps * (c0 + c1) + skip_c), \
+            (weight.shape, cout, ksize, c0, c1, skip_c)
         _call("stedm_conv_tc", C.byref(d), _stream())
     else:
         assert weight.dtype == torch.float32 and weight.numel() == cout * ksize * ksize * (c0 + c1), \

@@ -72,9 +72,16 @@ def im2col_3x3_s2(x):
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0):
+         act=0, skip_x0=None, skip_x1=None):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
+    y_skip = None
+    if skip_x0 is not None:    # fused 1x1 skip conv: its weights are the trailing K columns
+        sk = skip_x0 if skip_x1 is None else torch.cat([skip_x0, _bcast(skip_x1, skip_x0.shape[0])], -1)
+        kmain = ksize * ksize * cin
+        wfull = weight.float().reshape(cout, -1)
+        y_skip = F.conv2d(_nchw(sk.float()), wfull[:, kmain:].reshape(cout, sk.shape[-1], 1, 1))
+        weight = wfull[:, :kmain]
     if up_phase is not None:   # one 2x2 sub-pixel phase: taps (a,b) read (y+a-1+py, x+b-1+px); write (2y+py, 2x+px)
         py, px = up_phase >> 1, up_phase & 1
         w = weight.float().reshape(cout, 2, 2, cin).permute(0, 3, 1, 2)
@@ -90,6 +97,8 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     if upsample:
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
     y = F.conv2d(xin, w, bias, stride=stride, padding=ksize // 2)
+    if y_skip is not None:
+        y = y + y_skip
     if emb is not None:
         y = y + emb[:, :, None, None]        # (1, C) broadcasts like the kernel's row stride 0
     if act == 1:

@@ -27,7 +27,7 @@ def test_library_exports_header_symbols():
 
 def test_conv_desc_layout_matches_header():
     from stedm_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 20 * 4  # 9 pointers, int64, 19 int32 (+4 B tail padding)
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 22 * 4 + 2 * 8  # 9 pointers, int64, 22 int32, 2 pointers
 
 
 def test_sass_is_blackwell_native():

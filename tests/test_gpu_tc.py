@@ -226,3 +226,31 @@ def test_conv_tc_split_k_small_batch(ops, B, hw, cin, cout, k):
     if (hw * hw) % 128 == 0:
         got2 = ops.conv(xd, wd, b.cuda(), cout, k, out_dtype=torch.float32, tensor_core=True, stats_out=tiles)
         assert max_abs(nchw(got2.cpu()), F.conv2d(x, w, b, padding=k // 2)) < 3e-3
+
+
+@pytest.mark.parametrize("B,hw,cmid,cs0,cs1,co,sb", [
+    (4, 16, 128, 128, 64, 256, 2),     # two-source skip, second source broadcast (b % 2), BN=256 pair
+    (2, 32, 128, 256, 0, 128, 0),      # one skip source, BN=128
+    (3, 8, 64, 64, 64, 64, 0),         # several samples per tile, partial last tile, BN=64
+])
+def test_conv_tc_fused_skip_connection(ops, B, hw, cmid, cs0, cs1, co, sb):
+    """ResBlock tail in one launch: conv3x3(a) + bias + skip_1x1([x0 | x1]) + skip bias, the skip GEMM's weights appended
+    along K (openaimodel.py:246-256, 288); with emb and fused GroupNorm statistics of the sum."""
+    g = torch.Generator().manual_seed(B * 10 + hw)
+    a = bf(torch.randn(B, cmid, hw, hw, generator=g))
+    s0 = bf(torch.randn(B, cs0, hw, hw, generator=g))
+    s1 = bf(torch.randn(sb or B, cs1, hw, hw, generator=g)) if cs1 else None
+    w3 = bf(torch.randn(co, cmid, 3, 3, generator=g) / math.sqrt(9 * cmid))
+    w1 = bf(torch.randn(co, cs0 + cs1, 1, 1, generator=g) / math.sqrt(cs0 + cs1))
+    b3, b1 = torch.randn(co, generator=g), torch.randn(co, generator=g)
+    skip_in = s0 if s1 is None else torch.cat([s0, s1.repeat(B // s1.shape[0], 1, 1, 1)], 1)
+    want = F.conv2d(a, w3, b3, padding=1) + F.conv2d(skip_in, w1, b1)
+    wcat = torch.cat([tc_w(w3), tc_w(w1)], 1).contiguous()
+    dev = lambda t: None if t is None else nhwc(t).to(torch.bfloat16).cuda()
+    stats = torch.empty((B * hw * hw // 128, co, 2), device="cuda") if (hw * hw) % 128 == 0 and co % 64 == 0 else None
+    got = ops.conv(dev(a), wcat.cuda(), (b3 + b1).cuda(), co, 3, out_dtype=torch.float32, tensor_core=True,
+                   skip_x0=dev(s0), skip_x1=dev(s1), stats_out=stats)
+    assert max_abs(nchw(got.cpu()), want) < 3e-3, max_abs(nchw(got.cpu()), want)
+    if stats is not None:
+        tiles = nhwc(want).reshape(-1, 128, co)
+        assert max_abs(stats[..., 0].cpu(), tiles.sum(1)) < 0.05 and max_abs(stats[..., 1].cpu(), (tiles ** 2).sum(1)) < 0.5
