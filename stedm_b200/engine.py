@@ -319,7 +319,24 @@ class UNetRunner:
         emb_style = ops.linear(context.float().contiguous(), *self.style_emb, silu_in=True)
         return emb_all, emb_style
 
-    def __call__(self, x, c_concat, t, context, uniform_t=False):
+    def time_embedding_row(self, t_value, device):
+        """All 17 emb_layers outputs for ONE timestep value, cached: they depend on the weights and t only, so a DDIM
+        loop (the same 50 timesteps for every batch) pays the three embedding launches once per timestep per model,
+        not once per step.  The cache lives and dies with this runner (rebuilt whenever the weights change)."""
+        cache = self.__dict__.setdefault("_temb_cache", {})
+        row = cache.get(t_value)
+        if row is None or row.device != device:
+            t = torch.full((1,), int(t_value), dtype=torch.int64, device=device)
+            e = ops.linear(ops.timestep_embedding(t, self.mc), *self.te0)
+            e = ops.linear(e, *self.te2, silu_in=True)
+            row = cache[t_value] = ops.linear(e, self.emb_w, self.emb_b, silu_in=True)
+        return row
+
+    def style_embedding(self, context):
+        """ResBlockStyle's emb_layers on the style vectors (openaimodel.py:291-297): constant over a sampling loop."""
+        return ops.linear(context.float().contiguous(), *self.style_emb, silu_in=True)
+
+    def __call__(self, x, c_concat, t, context, uniform_t=False, emb=None):
         """x (B,3,L,L) and c_concat (B,3,L,L) NCHW fp32 (the 'hybrid' concat of ddpm.py:1414 is fused into the
         packing kernel), t (B,) int64, context (B,512) -> eps (B,3,L,L) NCHW fp32.
 
@@ -333,7 +350,8 @@ class UNetRunner:
         B = x.shape[0]
         G = context.shape[0] // B
         assert context.shape[0] == G * B and G >= 1
-        emb_all, emb_style = self.embeddings(t, context, uniform_t)
+        # emb = (time_embedding_row(t), style_embedding(context)) precomputed by the sampling loop
+        emb_all, emb_style = emb if emb is not None else self.embeddings(t, context, uniform_t)
         pool = StatsPool(self.n_norms, G * B, x.device)
         h = ops.pack_nchw_to_nhwc(x.contiguous(), c_concat, self.stem.cin_pad, prec.act)
         hs = []

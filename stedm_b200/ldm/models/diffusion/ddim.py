@@ -104,7 +104,7 @@ class DDIMSampler(object):
             # ts is torch.full(step): one timestep for the whole batch -> embeddings are computed for one row
             img, pred_x0 = stepper.step(img, ts, index, temperature=temperature, noise_dropout=noise_dropout,
                                         uniform_t=True, use_original_steps=ddim_use_original_steps,
-                                        quantize_denoised=quantize_denoised)
+                                        quantize_denoised=quantize_denoised, t_value=int(step))
             if callback:
                 callback(i)
             if img_callback:
@@ -159,50 +159,68 @@ class _GuidedStepper:
             self.context = ca(cond).float().contiguous()
         self.use_graph = allow_graph and sampler.use_cuda_graph
         self._graph_inputs_stale = True
+        self._emb_style = None
 
-    def _eps(self, x, t, uniform_t=False):
-        """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,)."""
+    def _eps(self, x, t, uniform_t=False, t_value=None):
+        """eps for the (cond ‖ uncond) batch.  x (B,3,L,L), t (B,).  ``t_value``: the loop's python timestep when the
+        whole batch shares it: the timestep embeddings then come from the runner's per-timestep cache and the style
+        embedding is computed once per loop — no embedding launch is left in the step (or in its CUDA graph)."""
         if self.guided and not self.shared:
             x2 = torch.cat([x, x], 0)
             t2 = torch.cat([t, t], 0)
         else:
             x2, t2 = x, t
+        emb = None
+        if uniform_t and t_value is not None:
+            runner = self.unet.runner()
+            if self._emb_style is None:
+                self._emb_style = runner.style_embedding(self.context)
+            emb = (runner.time_embedding_row(t_value, x.device), self._emb_style)
         if not self.use_graph:
-            return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t)
+            return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t, emb=emb)
         # CUDA graph of the U-Net pass (worth it only when a pass is launch-bound, i.e. small batches): captured
         # once per shape signature and cached on the U-Net module, with static input buffers, so later sampler
         # objects (sample_log builds a new DDIMSampler per call, like the reference) replay instead of re-capturing.
         cache = self.unet.__dict__.setdefault("_graph_cache", {})
-        key = (tuple(x2.shape), tuple(self.c_concat.shape), tuple(self.context.shape), self.unet.precision, uniform_t)
+        key = (tuple(x2.shape), tuple(self.c_concat.shape), tuple(self.context.shape), self.unet.precision, uniform_t,
+               emb is not None)
         ent = cache.get(key)
         if ent is None:
             warm = cache.setdefault(("warm",) + key, [0])
             if warm[0] < 1:   # one eager pass first: lazy kernel attribute setup must not happen under capture
                 warm[0] += 1
-                return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t)
+                return self.unet.forward_split(x2, self.c_concat, t2, self.context, uniform_t=uniform_t, emb=emb)
             ent = {"x": x2.clone(), "t": t2.clone(), "cc": self.c_concat.clone(), "ctx": self.context.clone(),
                    "graph": torch.cuda.CUDAGraph()}
+            if emb is not None:
+                ent["emb"] = (emb[0].clone(), emb[1].clone())
             n0 = ops.LAUNCHES[0]
             with torch.cuda.graph(ent["graph"]):
-                ent["eps"] = self.unet.forward_split(ent["x"], ent["cc"], ent["t"], ent["ctx"], uniform_t=uniform_t)
+                ent["eps"] = self.unet.forward_split(ent["x"], ent["cc"], ent["t"], ent["ctx"], uniform_t=uniform_t,
+                                                     emb=ent.get("emb"))
             ent["launches"] = ops.LAUNCHES[0] - n0
             ops.LAUNCHES[0] = n0                      # capture enqueued nothing; replays are counted below
             cache[key] = ent
         if self._graph_inputs_stale:
             ent["cc"].copy_(self.c_concat)
             ent["ctx"].copy_(self.context)
+            if emb is not None:
+                ent["emb"][1].copy_(emb[1])
             self._graph_inputs_stale = False
         ent["x"].copy_(x2)
-        ent["t"].copy_(t2)
+        if emb is not None:
+            ent["emb"][0].copy_(emb[0])
+        else:
+            ent["t"].copy_(t2)
         ent["graph"].replay()
         ops.LAUNCHES[0] += ent["launches"]
         return ent["eps"].clone()
 
     def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False, uniform_t=False,
-             use_original_steps=False, quantize_denoised=False):
+             use_original_steps=False, quantize_denoised=False, t_value=None):
         s = self.s
         x = x.float().contiguous()
-        eps = self._eps(x, t, uniform_t)
+        eps = self._eps(x, t, uniform_t, t_value)
         e_c, e_u = (eps[:self.b], eps[self.b:]) if self.guided else (eps, None)
         if use_original_steps:          # the 1000-step DDPM tables instead of the DDIM subsequence (ddim.py:188-191)
             m = self.model

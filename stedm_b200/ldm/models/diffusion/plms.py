@@ -68,7 +68,7 @@ class PLMSSampler(DDIMSampler):
                 assert x0 is not None
                 img = self.model.q_sample(x0, ts) * mask + (1. - mask) * img
             img, pred_x0, e_t = self._plms_step(stepper, img, ts, index, old_eps, ts_next, temperature, noise_dropout,
-                                                False)
+                                                False, t_values=(int(step), int(time_range[min(i + 1, len(time_range) - 1)])))
             old_eps.append(e_t)
             if len(old_eps) >= 4:
                 old_eps.pop(0)
@@ -93,9 +93,11 @@ class PLMSSampler(DDIMSampler):
         return self._plms_step(stepper, x, t, index, old_eps or [], t_next, temperature, noise_dropout, repeat_noise)
 
     # -------------------------------------------------------------------------------------------------------------
-    def _model_output(self, stepper, x, t):
-        """get_model_output, plms.py:177-191: plain classifier-free guidance."""
-        eps = stepper._eps(x.float().contiguous(), t, uniform_t=bool((t == t[0]).all()))
+    def _model_output(self, stepper, x, t, t_value=None):
+        """get_model_output, plms.py:177-191: plain classifier-free guidance.  ``t_value``: the loop's python timestep
+        (whole batch at one t: cached embeddings, no device sync); None: check the tensor."""
+        uniform = True if t_value is not None else bool((t == t[0]).all())
+        eps = stepper._eps(x.float().contiguous(), t, uniform_t=uniform, t_value=t_value)
         if not stepper.guided:
             return eps
         e_c, e_u = eps[:stepper.b], eps[stepper.b:]
@@ -111,11 +113,12 @@ class PLMSSampler(DDIMSampler):
                                  _f32(self.ddim_alphas_prev[index]), sigma, _f32(self.ddim_sqrt_one_minus_alphas[index]),
                                  noise=noise.contiguous() if sigma != 0.0 else None)
 
-    def _plms_step(self, stepper, x, t, index, old_eps, t_next, temperature, noise_dropout, repeat_noise):
-        e_t = self._model_output(stepper, x, t)
+    def _plms_step(self, stepper, x, t, index, old_eps, t_next, temperature, noise_dropout, repeat_noise,
+                   t_values=(None, None)):
+        e_t = self._model_output(stepper, x, t, t_values[0])
         if len(old_eps) == 0:       # pseudo improved Euler (2nd order), plms.py:219-223
             x_prev, _ = self._x_prev(x, e_t, index, temperature, noise_dropout, repeat_noise)
-            e_t_next = self._model_output(stepper, x_prev, t_next)
+            e_t_next = self._model_output(stepper, x_prev, t_next, t_values[1])
             e_t_prime = (e_t + e_t_next) / 2
         elif len(old_eps) == 1:     # Adams-Bashforth 2nd .. 4th order, plms.py:224-232
             e_t_prime = (3 * e_t - old_eps[-1]) / 2

@@ -185,12 +185,12 @@ class UNetModel(nn.Module):
             raise RuntimeError("the native U-Net is inference-only (no autograd)")
         return self.runner()(x.float(), None, timesteps.to(torch.int64), context)
 
-    def forward_split(self, x, c_concat, timesteps, context, uniform_t=False):
+    def forward_split(self, x, c_concat, timesteps, context, uniform_t=False, emb=None):
         """Same as forward(cat([x, c_concat], 1), ...) with the concat fused into the input packing kernel.
         ``context`` may hold G*B rows for B inputs (guided sampling with a shared encoder trunk, see
         engine.UNetRunner.__call__); eps then has G*B rows."""
         return self.runner()(x.float(), c_concat.float().contiguous(), timesteps.to(torch.int64), context,
-                             uniform_t=uniform_t)
+                             uniform_t=uniform_t, emb=emb)
 
     def shared_trunk_ok(self, batch, latent_hw):
         return self.runner().shared_trunk_ok(batch, latent_hw)
