@@ -157,6 +157,10 @@ int stedm_gemm_simt(const void* a, const void* b, void* c, int dtype_a, int dtyp
 int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int cols, float scale,
                        int mask_diag_period, void* stream);
 
+/* GEGLU of the SpatialTransformer feed-forward (ldm/modules/attention.py:37-44): in = [rows][2f] = [x | gate] (the
+ * proj Linear's output), out = [rows][f] = x * gelu(gate) (exact erf), fp32 or bf16. */
+int stedm_geglu(const void* in, void* out, int dtype, long long rows, int f, void* stream);
+
 /* K5  Fused flash-style self-attention on tcgen05 (S and O accumulators in TMEM, online fp32 softmax, P staged as
  * bf16 in shared memory): the U-Net AttentionBlock, head_dim 64 or 128, any token count.
  * q, k, v: bf16, token-major: element (b, h, t, c) at base + b*stride_b + h*stride_h + t*stride_t + c (strides in
@@ -165,9 +169,12 @@ int stedm_softmax_rows(float* x, void* out, int out_dtype, long long rows, int c
 /* out_stride_b: elements between samples of `out` (0 => tokens*heads*head_dim, dense).  mask_diag != 0: a token does
  * not attend to itself — sViT's LSA (networks/vit_set.py:44-60: softmax(q.k^T * exp(temperature) with the diagonal
  * masked) . v), head_dim 64, scale = exp(temperature). */
+/* Cross-attention (CrossAttention.forward with a context, ldm/modules/attention.py:169-193): tokens_kv > 0 keys /
+ * values per sample with their own strides kv_stride_*; tokens_kv == 0 => self-attention (k, v use q's strides). */
 int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads, int tokens,
                        int head_dim, long long stride_b, long long stride_h, long long stride_t, float scale,
-                       long long out_stride_b, int mask_diag, void* stream);
+                       long long out_stride_b, int mask_diag, int tokens_kv, long long kv_stride_b,
+                       long long kv_stride_h, long long kv_stride_t, void* stream);
 
 
 /* ----------------------------------------------------------------------------------------------------

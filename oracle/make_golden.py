@@ -3,7 +3,7 @@ on fixture weights, and assert that oracle/stedm_oracle.py reproduces every tens
 
 Run once in the build container (the reference cannot travel to the GPU box):
 
-    python -m oracle.make_golden [--only small|c1|sched|svit|plms]
+    python -m oracle.make_golden [--only small|c1|sched|svit|plms|st]
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -197,6 +197,53 @@ def gen_svit():
     print("[svit] wrote svit.npz")
 
 
+ST_UNET_KW = dict(image_size=32, in_channels=6, out_channels=3, model_channels=128, attention_resolutions=[32, 16, 8],
+                  num_res_blocks=2, channel_mult=[1, 4, 8], num_heads=8, use_spatial_transformer=True, context_dim=1024)
+
+
+@torch.no_grad()
+def gen_spatial_transformer():
+    """use_spatial_transformer=True: (1) the reference UNetModel with a SpatialTransformer in middle_block[2]
+    (openaimodel.py:648-652; context_dim = block width, the only value the reference can run, since the block is called
+    without a context) and (2) the stand-alone reference SpatialTransformer with a (B, N, 512) context — cross-attention
+    over style tokens (attention.py:245-261).  Asserts oracle == reference; stores eps / outputs."""
+    ref_shims.install()
+    from ldm.modules.attention import SpatialTransformer
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    out = {}
+    holder = torch.nn.Module()
+    holder.model = torch.nn.Module()
+    holder.model.diffusion_model = UNetModel(**ST_UNET_KW).eval()
+    apply_fixture_weights(holder, seed=0)
+    sd = {k: v.detach().float() for k, v in holder.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 6, 32, 32, generator=g)
+    ctx = torch.randn(2, 512, generator=g) * 0.5
+    for t in (981, 1):
+        tt = torch.full((2,), t, dtype=torch.long)
+        want = holder.model.diffusion_model(x, tt, ctx)
+        got = O.unet_forward(sd, x, tt, ctx)
+        d = maxdiff(want, got)
+        print(f"[st_unet t={t}] oracle vs reference: max|d| = {d:.3e} (|eps|max {float(want.abs().max()):.3f})")
+        assert d < 2e-4
+        out[f"unet_eps_{t}"] = want.numpy()
+    h2 = torch.nn.Module()
+    h2.st = SpatialTransformer(256, 4, 64, depth=2, context_dim=512).eval()
+    apply_fixture_weights(h2, seed=0)
+    sd2 = {k: v.detach().float() for k, v in h2.state_dict().items()}
+    xs = torch.randn(2, 256, 16, 16, generator=g)
+    for name, n_tok in (("st_ctx10", 10), ("st_ctx1", 1)):
+        c = torch.randn(2, n_tok, 512, generator=g)
+        want = h2.st(xs, c)
+        got = O.spatial_transformer(xs, sd2, "st.", 4, c)
+        d = maxdiff(want, got)
+        print(f"[{name}] oracle vs reference SpatialTransformer: max|d| = {d:.3e} (|out|max {float(want.abs().max()):.3f})")
+        assert d < 1e-4
+        out[name] = want.numpy()
+    np.savez_compressed(os.path.join(GOLD, "spatial_transformer.npz"), **out)
+    print("[st] wrote spatial_transformer.npz")
+
+
 class _StandInModel:
     """The minimum a reference sampler touches (plms.py:12-56, 177-191), with a deterministic non-linear eps so that the
     sampler arithmetic — timestep sequence, multistep coefficients, guidance combine, x_prev update — can be run through
@@ -257,6 +304,8 @@ if __name__ == "__main__":
         gen_svit()
     if a.only in ("all", "plms"):
         gen_plms()
+    if a.only in ("all", "st"):
+        gen_spatial_transformer()
     if a.only in ("all", "small"):
         # B=2, latent 32 (128^2 image), two style images per sample (exercises Agg_Mean), full DDIM-50
         gen_case("small_b2_l32", B=2, L=32, n_style=2, S=50, full_steps=True, seed=0, store_f16_image=False)

@@ -105,6 +105,42 @@ def attention_block(x, sd, p, num_heads):
     return (xf + h).reshape(b, c, hh, ww)
 
 
+def spatial_transformer(x, sd, p, n_heads, context=None):
+    """SpatialTransformer.forward, ldm/modules/attention.py:245-261, eval mode: GroupNorm(32, eps 1e-6) -> proj_in 1x1 ->
+    'b c h w -> b (h w) c' -> BasicTransformerBlock._forward per block (:211-215) -> back -> proj_out 1x1 -> + x_in.
+    CrossAttention (:169-193): q = to_q(x), k, v = to_k / to_v(context or x), heads split 'b n (h d)', softmax(q k^T *
+    d^-1/2) v, to_out.  FeedForward with GEGLU (:37-63): proj -> x * gelu(gate) -> Linear."""
+    b, c, hh, ww = x.shape
+    g = lambda k: sd[p + k]
+
+    def attn(y, q, ctx):
+        cx = y if ctx is None else ctx
+        qq, kk, vv = F.linear(y, g(q + "to_q.weight")), F.linear(cx, g(q + "to_k.weight")), F.linear(cx, g(q + "to_v.weight"))
+        sp = lambda t: t.reshape(t.shape[0], t.shape[1], n_heads, -1).permute(0, 2, 1, 3)
+        qq, kk, vv = sp(qq), sp(kk), sp(vv)
+        sim = torch.softmax(qq @ kk.transpose(-1, -2) * (qq.shape[-1] ** -0.5), dim=-1)
+        o = (sim @ vv).permute(0, 2, 1, 3).reshape(y.shape[0], y.shape[1], -1)
+        return F.linear(o, g(q + "to_out.0.weight"), g(q + "to_out.0.bias"))
+
+    h = F.group_norm(x, 32, g("norm.weight"), g("norm.bias"), 1e-6)
+    h = F.conv2d(h, g("proj_in.weight"), g("proj_in.bias"))
+    inner = h.shape[1]
+    h = h.reshape(b, inner, -1).permute(0, 2, 1)
+    if context is not None and context.dim() == 2:
+        context = context[:, None, :]
+    i = 0
+    while (p + f"transformer_blocks.{i}.norm1.weight") in sd:
+        q = f"transformer_blocks.{i}."
+        ln = lambda y, n: F.layer_norm(y, (inner,), g(q + n + ".weight"), g(q + n + ".bias"), 1e-5)
+        h = attn(ln(h, "norm1"), q + "attn1.", None) + h
+        h = attn(ln(h, "norm2"), q + "attn2.", context) + h
+        a, gate = F.linear(ln(h, "norm3"), g(q + "ff.net.0.proj.weight"), g(q + "ff.net.0.proj.bias")).chunk(2, dim=-1)
+        h = F.linear(a * F.gelu(gate), g(q + "ff.net.2.weight"), g(q + "ff.net.2.bias")) + h
+        i += 1
+    h = h.permute(0, 2, 1).reshape(b, inner, hh, ww)
+    return F.conv2d(h, g("proj_out.weight"), g("proj_out.bias")) + x
+
+
 def unet_structure(sd, prefix=UNET):
     """Recover the block list from the state-dict keys (UNetModel.__init__, openaimodel.py:536-733)."""
     n_in = 1 + max(int(k[len(prefix) + 13:].split(".")[0]) for k in sd if k.startswith(prefix + "input_blocks."))
@@ -135,7 +171,11 @@ def unet_forward(sd, x, t, context, num_heads=8, prefix=UNET):
     p = P + "middle_block."
     h = resblock(h, emb, sd, p + "0.")
     h = resblock(h, context.float(), sd, p + "1.block.")  # ResBlockStyle (:291-297; dispatch :93-101)
-    h = attention_block(h, sd, p + "2.", num_heads)
+    if (p + "2.transformer_blocks.0.norm1.weight") in sd:
+        # use_spatial_transformer=True (:648-652): TimestepEmbedSequential passes NO context to it (:93-101)
+        h = spatial_transformer(h, sd, p + "2.", num_heads, None)
+    else:
+        h = attention_block(h, sd, p + "2.", num_heads)
     h = resblock(h, emb, sd, p + "3.")
     for i in range(n_out):
         p = f"{P}output_blocks.{i}."

@@ -41,7 +41,7 @@ SIGNATURES = {
     "stedm_gemm_simt": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64,
                         i64, i64, f32, vp],
     "stedm_softmax_rows": [vp, vp, i32, i64, i32, f32, i32, vp],
-    "stedm_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, f32, i64, i32, vp],
+    "stedm_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, f32, i64, i32, i32, i64, i64, i64, vp],
     "stedm_upsample_nearest2x": [vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_im2col_3x3_s2": [vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_pack_nchw_to_nhwc": [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp],
@@ -57,6 +57,7 @@ SIGNATURES = {
     "stedm_patch_merge_gather": [vp, vp, i32, i32, i32, i32, i32, vp],
     "stedm_ln_meanpool": [vp, vp, vp, f32, vp, i32, i32, i32, vp],
     "stedm_set_reduce": [vp, vp, i32, i32, i32, i32, vp],
+    "stedm_geglu": [vp, vp, i32, i64, i32, vp],
     "stedm_spt_patchify": [vp, vp, i32, i32, i32, i32, vp],
     "stedm_svit_assemble": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],
     "stedm_token_mean": [vp, vp, i32, i32, i32, i32, vp],

@@ -30,6 +30,7 @@ struct AttnParams {
   float scale_log2e;  // scale * log2(e)
   long long out_stride_b;  // elements between samples of `out`
   int mask_diag;      // 1: a token does not attend to itself (sViT's LSA, networks/vit_set.py:52-54)
+  int tokens_kv;      // keys / values per sample (== tokens for self-attention; the context length for cross-attention)
 };
 
 // smem descriptor for an MN-major SW128 operand whose K rows are 128 B apart (as TMA writes a [rows][64] bf16 box):
@@ -81,7 +82,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BM, head = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.tokens + AT_BN - 1) / AT_BN;
+  const int n_kv = (p.tokens_kv + AT_BN - 1) / AT_BN;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q);
@@ -170,7 +171,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int valid_keys = min(AT_BN, p.tokens - j * AT_BN);
+      const int valid_keys = min(AT_BN, p.tokens_kv - j * AT_BN);
       // LSA diagonal mask: column of this tile that holds the query's own key (out of range when not in the tile)
       const int self_col = p.mask_diag ? (q0 + row - j * AT_BN) : -1;
       // pass 1: row max
@@ -300,6 +301,7 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 extern "C" int stedm_attention_tc(const void* q, const void* k, const void* v, void* out, int batch, int heads,
                                   int tokens, int head_dim, long long stride_b, long long stride_h,
                                   long long stride_t, float scale, long long out_stride_b, int mask_diag,
+                                  int tokens_kv, long long kv_stride_b, long long kv_stride_h, long long kv_stride_t,
                                   void* stream) {
   STEDM_REQUIRE(q && k && v && out, "attention_tc: null pointer");
   STEDM_REQUIRE(head_dim == 64 || head_dim == 128, "attention_tc: head_dim %d unsupported (64 or 128)", head_dim);
@@ -309,14 +311,21 @@ extern "C" int stedm_attention_tc(const void* q, const void* k, const void* v, v
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_qkv_map(&mq, q, batch, heads, tokens, head_dim, stride_b, stride_h, stride_t))) return rc;
-  if ((rc = make_qkv_map(&mk, k, batch, heads, tokens, head_dim, stride_b, stride_h, stride_t))) return rc;
-  if ((rc = make_qkv_map(&mv, v, batch, heads, tokens, head_dim, stride_b, stride_h, stride_t))) return rc;
+  // cross-attention: keys / values come from a context of tokens_kv tokens with its own strides (0 => self-attention)
+  if (tokens_kv <= 0) {
+    tokens_kv = tokens; kv_stride_b = stride_b; kv_stride_h = stride_h; kv_stride_t = stride_t;
+  }
+  STEDM_REQUIRE(kv_stride_t % 8 == 0 && kv_stride_h % 8 == 0 && kv_stride_b % 8 == 0 && !(mask_diag && tokens_kv != tokens),
+                "attention_tc: bad key/value strides or a diagonal mask on cross-attention");
+  if ((rc = make_qkv_map(&mk, k, batch, heads, tokens_kv, head_dim, kv_stride_b, kv_stride_h, kv_stride_t))) return rc;
+  if ((rc = make_qkv_map(&mv, v, batch, heads, tokens_kv, head_dim, kv_stride_b, kv_stride_h, kv_stride_t))) return rc;
   AttnParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.tokens = tokens; p.heads = heads; p.head_dim = head_dim;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out_stride_b = out_stride_b > 0 ? out_stride_b : static_cast<long long>(tokens) * heads * head_dim;
   p.mask_diag = mask_diag ? 1 : 0;
+  p.tokens_kv = tokens_kv;
   STEDM_REQUIRE(p.out_stride_b % 8 == 0 && !(mask_diag && tokens < 2), "attention_tc: bad out stride / diagonal mask");
   auto s = static_cast<cudaStream_t>(stream);
   return head_dim == 128 ? launch_attn<128>(mq, mk, mv, p, batch, s) : launch_attn<64>(mq, mk, mv, p, batch, s);

@@ -280,10 +280,14 @@ class UNetRunner:
         self.mid0 = pack_res(mb[0], ("mid", 0))
         self.mid1 = pack_res(mb[1].block, None, style=True)
         att = mb[2]
-        self.att_norm = PackedNorm(att.norm, 1e-5)
         self.n_norms += 1
-        self.att_qkv = PackedConv(att.qkv.weight, att.qkv.bias, prec)
-        self.att_proj = PackedConv(att.proj_out.weight, att.proj_out.bias, prec)
+        self.spatial_transformer = None
+        if hasattr(att, "transformer_blocks"):      # use_spatial_transformer=True (openaimodel.py:648-652)
+            self.spatial_transformer = PackedSpatialTransformer(att, prec)
+        else:
+            self.att_norm = PackedNorm(att.norm, 1e-5)
+            self.att_qkv = PackedConv(att.qkv.weight, att.qkv.bias, prec)
+            self.att_proj = PackedConv(att.proj_out.weight, att.proj_out.bias, prec)
         self.mid3 = pack_res(mb[3], ("mid", 3))
         # ---- decoder
         self.dec = []
@@ -371,7 +375,9 @@ class UNetRunner:
             if emb_all.shape[0] > 1:
                 emb_all = torch.cat([emb_all] * G, 0)
         h = self.mid1(h, None, emb_style, pool)
-        h = self._attention(h, pool)
+        # TimestepEmbedSequential hands the context to StyleBlocks only (openaimodel.py:93-101): the transformer runs
+        # without one, i.e. both of its attentions are self-attentions
+        h = self.spatial_transformer(h, pool) if self.spatial_transformer is not None else self._attention(h, pool)
         h = self.mid3(h, None, self._emb_view(emb_all, ("mid", 3)), pool)
         for rb, key, up in self.dec:
             h = rb(h, hs.pop(), self._emb_view(emb_all, key), pool)
@@ -512,3 +518,87 @@ class DecoderRunner:
                 outs.append(ops.attention_simt(q, q, q, 1, Cc, T, 0, Cc, 2 * Cc, 3 * Cc, Cc, scale, prec.act))
             o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return self.att_proj(o.view(B, H, W, Cc), residual=x, want_stats=True)
+
+
+class PackedSpatialTransformer:
+    """SpatialTransformer.forward (ldm/modules/attention.py:245-261) on an NHWC map: GroupNorm(eps 1e-6) -> proj_in
+    (1x1) -> depth x BasicTransformerBlock._forward (:211-215: x = attn1(norm1(x)) + x; x = attn2(norm2(x), context) + x;
+    x = ff(norm3(x)) + x with the GEGLU feed-forward) -> proj_out (1x1) + x_in.  Tokens are the pixels of the NHWC map,
+    the transformer's residual stream is fp32, GEMM operands are the activation dtype."""
+
+    def __init__(self, st, prec):
+        from .style_engine import PackedLinear, PackedNormLN
+        self.prec = prec
+        self.norm = PackedNorm(st.norm, st.norm.eps)
+        self.proj_in = PackedConv(st.proj_in.weight, st.proj_in.bias, prec)
+        self.proj_out = PackedConv(st.proj_out.weight, st.proj_out.bias, prec)
+        self.heads, self.d = st.n_heads, st.d_head
+        self.inner = self.heads * self.d
+        self.blocks = []
+        for blk in st.transformer_blocks:
+            a1, a2 = blk.attn1, blk.attn2
+            ent = dict(
+                n1=PackedNormLN(blk.norm1), n2=PackedNormLN(blk.norm2), n3=PackedNormLN(blk.norm3),
+                qkv1=PackedLinear(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, prec),
+                out1=PackedLinear(a1.to_out[0].weight, a1.to_out[0].bias, prec),
+                out2=PackedLinear(a2.to_out[0].weight, a2.to_out[0].bias, prec),
+                ff1=PackedLinear(blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias, prec),
+                ff2=PackedLinear(blk.ff.net[2].weight, blk.ff.net[2].bias, prec),
+                scale1=a1.scale, scale2=a2.scale, ctx_dim=a2.to_k.weight.shape[1])
+            if ent["ctx_dim"] == self.inner:     # usable without a context (self-attention): q, k, v in one GEMM
+                ent["qkv2"] = PackedLinear(torch.cat([a2.to_q.weight, a2.to_k.weight, a2.to_v.weight], 0), None, prec)
+            ent["q2"] = PackedLinear(a2.to_q.weight, None, prec)
+            ent["kv2_w"] = torch.cat([a2.to_k.weight, a2.to_v.weight], 0).detach().float().contiguous()
+            self.blocks.append(ent)
+
+    def _ln(self, x, n):
+        tc = self.prec.tc
+        f32, b16 = ops.layernorm(x, None, n.gamma, n.beta, n.eps, want_f32=not tc, want_bf16=tc)
+        return b16 if tc else f32
+
+    def _self_attention(self, qkv, T, scale):
+        B, inner, d = qkv.shape[0], self.inner, self.d
+        q3 = qkv.view(B, T, 3 * inner)
+        if self.prec.tc and ops.attention_tc_supported(d, T):
+            return ops.attention_tc(q3, q3, q3, self.heads, d, T, (T * 3 * inner, d, 3 * inner), scale,
+                                    q_off=0, k_off=inner, v_off=2 * inner)
+        return ops.attention_simt(q3, q3, q3, self.heads, d, T, 0, inner, 2 * inner, 3 * inner, d, scale, self.prec.act)
+
+    def _cross_attention(self, q, kv, T, N, scale):
+        """q [B, T, inner]; kv [B, N, 2*inner] = [k | v] of the context tokens."""
+        B, inner, d = q.shape[0], self.inner, self.d
+        if self.prec.tc and ops.attention_tc_supported(d, T):
+            return ops.attention_tc(q, kv, kv, self.heads, d, T, (T * inner, d, inner), scale, q_off=0, k_off=0,
+                                    v_off=inner, tokens_kv=N, kv_strides=(N * 2 * inner, d, 2 * inner))
+        return ops.attention_simt(q, kv, kv, self.heads, d, T, 0, 0, inner, inner, d, scale, self.prec.act,
+                                  tokens_kv=N, kv_token_stride=2 * inner)
+
+    def __call__(self, x_in, pool, context=None):
+        prec = self.prec
+        B, H, W, C = x_in.shape
+        T = H * W
+        a = self.norm(x_in, None, False, prec.act, pool.next())
+        x = self.proj_in(a, out_dtype=torch.float32)                       # fp32 residual stream [B, H, W, inner]
+        if context is not None and context.dim() == 2:
+            context = context[:, None, :]
+        for bi, e in enumerate(self.blocks):
+            o = self._self_attention(e["qkv1"](self._ln(x, e["n1"])), T, e["scale1"])
+            x = e["out1"](o.view(B, H, W, self.inner), residual=x, out_dtype=torch.float32)
+            n2 = self._ln(x, e["n2"])
+            if context is None:
+                if "qkv2" not in e:
+                    raise RuntimeError(f"SpatialTransformer called without a context but context_dim {e['ctx_dim']} != "
+                                       f"{self.inner}: the reference fails here too (to_k applied to the tokens)")
+                o = self._self_attention(e["qkv2"](n2), T, e["scale2"])
+            else:
+                N = context.shape[1]
+                assert context.shape[0] == B and context.shape[2] == e["ctx_dim"], tuple(context.shape)
+                kv = ops.linear(context.reshape(B * N, -1).float().contiguous(), e["kv2_w"], None)
+                kv = kv.to(prec.act).view(B, N, 2 * self.inner)
+                o = self._cross_attention(e["q2"](n2).view(B, T, self.inner), kv, T, N, e["scale2"])
+            x = e["out2"](o.view(B, H, W, self.inner), residual=x, out_dtype=torch.float32)
+            g = ops.geglu(e["ff1"](self._ln(x, e["n3"])))
+            # the last block hands its tokens to proj_out: written in the GEMM operand dtype directly
+            last = bi == len(self.blocks) - 1
+            x = e["ff2"](g, residual=x, out_dtype=prec.act if last else torch.float32)
+        return self.proj_out(x, residual=x_in, want_stats=True)

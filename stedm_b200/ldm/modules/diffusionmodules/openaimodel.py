@@ -90,11 +90,16 @@ class UNetModel(nn.Module):
         unsupported = dict(dropout=dropout != 0, dims=dims != 2, num_classes=num_classes is not None,
                            use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
                            use_new_attention_order=use_new_attention_order, conv_resample=not conv_resample,
-                           use_spatial_transformer=use_spatial_transformer, context_dim=context_dim is not None,
                            n_embed=n_embed is not None, num_head_channels=num_head_channels != -1)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError(f"UNetModel options outside STEDM's sampling path: {bad}")
+        if use_spatial_transformer:                                         # openaimodel.py:494-501
+            assert context_dim is not None, "Fool!! You forgot to include the dimension of your cross-attention conditioning..."
+        if context_dim is not None:
+            assert use_spatial_transformer, "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
         if num_heads == -1:
             raise AssertionError("Either num_heads or num_head_channels has to be set")
         channel_mult = tuple(channel_mult)
@@ -130,8 +135,15 @@ class UNetModel(nn.Module):
                 down.kind = "down"
                 self.input_blocks.append(down)
                 skip_chans.append(ch)
-        self.middle_block = _Seq(ResBlock(ch, ted), ResBlockStyle(ch, ted), AttentionBlock(ch, num_heads),
-                                 ResBlock(ch, ted))
+        if use_spatial_transformer:
+            # middle_block[2] = SpatialTransformer(ch, num_heads, ch // num_heads, depth, context_dim)
+            # (openaimodel.py:625-652, legacy=True); it is called without a context (see engine.UNetRunner)
+            from ..attention import SpatialTransformer
+            mid_attn = SpatialTransformer(ch, num_heads, ch // num_heads, depth=transformer_depth,
+                                          context_dim=context_dim, precision=precision)
+        else:
+            mid_attn = AttentionBlock(ch, num_heads)
+        self.middle_block = _Seq(ResBlock(ch, ted), ResBlockStyle(ch, ted), mid_attn, ResBlock(ch, ted))
         self.output_blocks = nn.ModuleList()
         for level, mult in list(enumerate(channel_mult))[::-1]:
             for i in range(num_res_blocks + 1):

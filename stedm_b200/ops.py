@@ -220,21 +220,25 @@ def softmax_rows(x, scale=1.0, out=None, mask_diag_period=0):
 
 
 def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
-                   scale, out_dtype, mask_diag=False, batch_tokens=None):
+                   scale, out_dtype, mask_diag=False, batch_tokens=None, tokens_kv=None, kv_token_stride=None):
     """fp32-accumulate attention on CUDA cores with a materialised score matrix (parity mode).
     q/k/v live in [B, T, token_stride] buffers at channel offset ``*_off + head*head_stride``; for the U-Net's
     legacy head-major qkv layout head_stride = 3*head_dim, for separate q/k/v tensors head_stride = head_dim."""
     b = q_src.shape[0]
     hs = head_stride
     bt = batch_tokens or tokens        # rows per sample in the q/k/v/out buffers (> tokens when padded)
-    s = torch.empty((b, heads, tokens, tokens), device=q_src.device, dtype=torch.float32)
-    gemm_simt(q_src, k_src, s, tokens, tokens, head_dim, token_stride, token_stride, tokens, True, b, heads,
-              (bt * token_stride, hs), (bt * token_stride, hs), (heads * tokens * tokens, tokens * tokens),
+    # cross-attention: tokens_kv keys / values per sample in their own buffer (row stride kv_token_stride)
+    tk = tokens_kv or tokens
+    kts = kv_token_stride or token_stride
+    kv_sb = (tk if tokens_kv else bt) * kts
+    s = torch.empty((b, heads, tokens, tk), device=q_src.device, dtype=torch.float32)
+    gemm_simt(q_src, k_src, s, tokens, tk, head_dim, token_stride, kts, tk, True, b, heads,
+              (bt * token_stride, hs), (kv_sb, hs), (heads * tokens * tk, tokens * tk),
               alpha=scale, a_off=q_off, b_off=k_off)
     softmax_rows(s, mask_diag_period=tokens if mask_diag else 0)
     out = torch.zeros((b, bt, heads * head_dim), device=q_src.device, dtype=out_dtype)
-    gemm_simt(s, v_src, out, tokens, head_dim, tokens, tokens, token_stride, heads * head_dim, False, b, heads,
-              (heads * tokens * tokens, tokens * tokens), (bt * token_stride, hs),
+    gemm_simt(s, v_src, out, tokens, head_dim, tk, tk, kts, heads * head_dim, False, b, heads,
+              (heads * tokens * tk, tokens * tk), (kv_sb, hs),
               (bt * heads * head_dim, head_dim), b_off=v_off)
     return out
 
@@ -245,7 +249,7 @@ def attention_tc_supported(head_dim, tokens):
 
 
 def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0, mask_diag=False,
-                 batch_tokens=None):
+                 batch_tokens=None, tokens_kv=0, kv_strides=(0, 0, 0)):
     """Fused tcgen05 flash attention; q/k/v are bf16 views described by element offsets and (b, h, t) strides.
     ``batch_tokens`` > tokens: the output keeps that many (zero) rows per sample; ``mask_diag``: sViT's LSA mask."""
     _cuda(q, k, v)
@@ -256,7 +260,7 @@ def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_of
     es = 2
     _call("stedm_attention_tc", _ptr(q) + q_off * es, _ptr(k) + k_off * es, _ptr(v) + v_off * es, _ptr(out), b, heads,
           tokens, head_dim, strides[0], strides[1], strides[2], float(scale), bt * heads * head_dim,
-          1 if mask_diag else 0, _stream())
+          1 if mask_diag else 0, tokens_kv, kv_strides[0], kv_strides[1], kv_strides[2], _stream())
     return out
 
 
@@ -388,6 +392,15 @@ def set_reduce(x, mode):
     b, n, f = x.shape
     out = torch.empty((b, f), device=x.device, dtype=torch.float32)
     _call("stedm_set_reduce", _ptr(x), _ptr(out), b, n, f, {"mean": 0, "max": 1}[mode], _stream())
+    return out
+
+
+def geglu(x):
+    """[..., 2F] = [x | gate] -> [..., F] = x * gelu(gate) (attention.py:37-44)."""
+    _cuda(x)
+    f = x.shape[-1] // 2
+    out = torch.empty(x.shape[:-1] + (f,), device=x.device, dtype=x.dtype)
+    _call("stedm_geglu", _ptr(x), _ptr(out), _DT[x.dtype], x.numel() // (2 * f), f, _stream())
     return out
 
 

@@ -114,16 +114,24 @@ def attention_tc_supported(head_dim, tokens):
     return False
 
 
+def geglu(x):
+    a, g = x.float().chunk(2, dim=-1)
+    return (a * F.gelu(g)).to(x.dtype)
+
+
 def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v_off, token_stride, head_stride,
-                   scale, out_dtype, mask_diag=False, batch_tokens=None):
+                   scale, out_dtype, mask_diag=False, batch_tokens=None, tokens_kv=None, kv_token_stride=None):
     b = q_src.shape[0]
     bt = batch_tokens or tokens
+    tk = tokens_kv or tokens
+    kts = kv_token_stride or token_stride
     flat = lambda t: t.reshape(b, bt, token_stride).float()[:, :tokens]
+    flat_kv = (lambda t: t.reshape(b, tk, kts).float()) if tokens_kv else (lambda t: t.reshape(b, bt, kts).float()[:, :tk])
     outs = []
     for h in range(heads):
         q = flat(q_src)[:, :, q_off + h * head_stride: q_off + h * head_stride + head_dim]
-        k = flat(k_src)[:, :, k_off + h * head_stride: k_off + h * head_stride + head_dim]
-        v = flat(v_src)[:, :, v_off + h * head_stride: v_off + h * head_stride + head_dim]
+        k = flat_kv(k_src)[:, :, k_off + h * head_stride: k_off + h * head_stride + head_dim]
+        v = flat_kv(v_src)[:, :, v_off + h * head_stride: v_off + h * head_stride + head_dim]
         s = torch.einsum("btc,bsc->bts", q, k) * scale
         if mask_diag:
             s = s.masked_fill(torch.eye(tokens, dtype=torch.bool), float("-inf"))
@@ -135,10 +143,11 @@ def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v
 
 
 def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0, mask_diag=False,
-                 batch_tokens=None):
-    assert strides[1] == head_dim and q is k and k is v
+                 batch_tokens=None, tokens_kv=0, kv_strides=(0, 0, 0)):
+    assert strides[1] == head_dim and k is v
     return attention_simt(q, k, v, heads, head_dim, tokens, q_off, k_off, v_off, strides[2], strides[1], scale,
-                          torch.bfloat16, mask_diag=mask_diag, batch_tokens=batch_tokens)
+                          torch.bfloat16, mask_diag=mask_diag, batch_tokens=batch_tokens,
+                          tokens_kv=tokens_kv or None, kv_token_stride=kv_strides[2] or None)
 
 
 def vq_nearest(z, codebook, return_indices=False):

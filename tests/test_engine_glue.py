@@ -59,3 +59,83 @@ def test_decoder_runner_glue(cpu_model, patched):
     with torch.no_grad():
         assert max_abs(runner(z), g["dec_quant"]) < 1e-3
         assert max_abs(runner(z, force_not_quantize=True), g["dec_noquant"]) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- SpatialTransformer
+ST_UNET_KW = dict(image_size=32, in_channels=6, out_channels=3, model_channels=128, attention_resolutions=[32, 16, 8],
+                  num_res_blocks=2, channel_mult=[1, 4, 8], num_heads=8, use_spatial_transformer=True, context_dim=1024)
+
+
+def st_inputs():
+    g = torch.Generator().manual_seed(31)                 # the draw order of oracle/make_golden.py gen_spatial_transformer
+    x = torch.randn(2, 6, 32, 32, generator=g)
+    ctx = torch.randn(2, 512, generator=g) * 0.5
+    xs = torch.randn(2, 256, 16, 16, generator=g)
+    c10 = torch.randn(2, 10, 512, generator=g)
+    c1 = torch.randn(2, 1, 512, generator=g)
+    return x, ctx, xs, c10, c1
+
+
+def build_st_unet():
+    from stedm_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    holder = torch.nn.Module()
+    holder.model = torch.nn.Module()
+    holder.model.diffusion_model = UNetModel(**ST_UNET_KW).eval()
+    apply_fixture_weights(holder, seed=0)
+    return holder
+
+
+def build_st_module():
+    from stedm_b200.ldm.modules.attention import SpatialTransformer
+    from stedm_b200.utils.fixture import apply_fixture_weights
+    h = torch.nn.Module()
+    h.st = SpatialTransformer(256, 4, 64, depth=2, context_dim=512).eval()
+    apply_fixture_weights(h, seed=0)
+    return h
+
+
+@pytest.fixture()
+def patched_all(monkeypatch):
+    from stedm_b200 import engine, style_engine
+    monkeypatch.setattr(engine, "ops", fake_ops)
+    monkeypatch.setattr(style_engine, "ops", fake_ops)
+    return engine
+
+
+def test_spatial_transformer_oracle_matches_reference_golden():
+    """oracle.unet_forward / spatial_transformer on fixture weights == the reference's own classes
+    (tests/golden/spatial_transformer.npz from oracle/make_golden.py --only st)."""
+    from oracle import stedm_oracle as O
+    g = load_golden("spatial_transformer")
+    x, ctx, xs, c10, c1 = st_inputs()
+    sd = {k: v.detach().float() for k, v in build_st_unet().state_dict().items()}
+    with torch.no_grad():
+        eps = O.unet_forward(sd, x, torch.full((2,), 981, dtype=torch.long), ctx)
+    assert max_abs(eps, g["unet_eps_981"]) < 1e-5
+    sd2 = {k: v.detach().float() for k, v in build_st_module().state_dict().items()}
+    with torch.no_grad():
+        assert max_abs(O.spatial_transformer(xs, sd2, "st.", 4, c10), g["st_ctx10"]) < 1e-5
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_spatial_transformer_glue(patched_all, precision, bar):
+    """Host logic of PackedSpatialTransformer (fused qkv weights, head split, cross-attention k/v packing, GEGLU halves,
+    residual order) and its wiring into the U-Net's middle block, through the torch stand-in for the kernels."""
+    g = load_golden("spatial_transformer")
+    x, ctx, xs, c10, c1 = st_inputs()
+    unet = build_st_unet().model.diffusion_model
+    runner = patched_all.UNetRunner(unet, precision)
+    with torch.no_grad():
+        eps = runner(x[:, :3].contiguous(), x[:, 3:].contiguous(), torch.full((2,), 981, dtype=torch.long), ctx)
+    scale = float(abs(g["unet_eps_981"]).max()) if precision == "bf16" else 1.0
+    assert max_abs(eps, g["unet_eps_981"]) < bar * scale, max_abs(eps, g["unet_eps_981"])
+    st = build_st_module().st
+    r = patched_all.PackedSpatialTransformer(st, patched_all.Precision(precision))
+    pool = patched_all.StatsPool(1, 2, "cpu")
+    for c, name in ((c10, "st_ctx10"), (c1, "st_ctx1")):
+        with torch.no_grad():
+            h = xs.permute(0, 2, 3, 1).contiguous().to(r.prec.act)
+            out = r(h, pool, c).float().permute(0, 3, 1, 2)
+        scale = float(abs(g[name]).max()) if precision == "bf16" else 1.0
+        assert max_abs(out, g[name]) < bar * scale, (name, max_abs(out, g[name]))

@@ -444,3 +444,42 @@ def test_plms_sampler_matches_oracle():
     assert tuple(z.shape) == (2, 3, 32, 32) and bool(torch.isfinite(z).all()) and len(inter["x_inter"]) == 7
     with pytest.raises(ValueError):
         s.make_schedule(ddim_num_steps=50, ddim_eta=0.5, verbose=False)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_with_spatial_transformer_matches_reference(precision):
+    """use_spatial_transformer=True, context_dim=1024: the reference's UNetModel with a SpatialTransformer in
+    middle_block[2] (golden from the reference itself, oracle/make_golden.py --only st) vs the native engine."""
+    from tests.test_engine_glue import build_st_unet, st_inputs
+    g = load_golden("spatial_transformer")
+    x, ctx, _, _, _ = st_inputs()
+    unet = build_st_unet().model.diffusion_model.cuda()
+    unet.set_precision(precision)
+    for t in (981, 1):
+        eps = unet(x.cuda(), torch.full((2,), t, device="cuda", dtype=torch.long), ctx.cuda())
+        want = g[f"unet_eps_{t}"]
+        if precision == "fp32":
+            assert max_abs(eps, want) < FP32_EPS_BAR, max_abs(eps, want)
+        else:
+            r = rel_err(eps, want)
+            print(f"SpatialTransformer U-Net bf16 eps rel err t={t}: {r:.3e}")
+            assert r < BF16_EPS_BAR, r
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_spatial_transformer_cross_attention_over_style_tokens(precision):
+    """Stand-alone SpatialTransformer.forward(x, context) with (B, N, 512) style tokens, N = 10 and 1: cross-attention on
+    the tcgen05 flash kernel (separate key/value length) vs the reference class's output."""
+    from tests.test_engine_glue import build_st_module, st_inputs
+    g = load_golden("spatial_transformer")
+    _, _, xs, c10, c1 = st_inputs()
+    st = build_st_module().st.cuda()
+    st.set_precision(precision)
+    for c, name in ((c10, "st_ctx10"), (c1, "st_ctx1")):
+        out = st(xs.cuda(), c.cuda())
+        if precision == "fp32":
+            assert max_abs(out, g[name]) < 2e-4, max_abs(out, g[name])
+        else:
+            r = rel_err(out, g[name])
+            print(f"SpatialTransformer cross-attention bf16 rel err {name}: {r:.3e}")
+            assert r < BF16_EPS_BAR, r

@@ -239,3 +239,35 @@ def test_softmax_rows_warp_and_block_kernels(cols, mask):
     got32 = ops.softmax_rows(x.clone().cuda(), 0.37, mask_diag_period=period)
     assert float((got32.cpu() - want).abs().max()) < 1e-6
     assert float((got16.float().cpu() - want).abs().max()) < 4e-3
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_geglu(dt):
+    from stedm_b200 import ops
+    from tests import fake_ops
+    x = (torch.randn(37, 5, 2 * 264) * 2).to(dt)
+    got = ops.geglu(x.cuda())
+    assert tuple(got.shape) == (37, 5, 264)
+    want = fake_ops.geglu(x.float())
+    err = ((got.float().cpu() - want).abs() / want.abs().clamp_min(1.0)).max()      # bf16: half an ulp of the result
+    assert float(err) < (1e-5 if dt == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("T,N,heads,d", [(256, 10, 8, 128), (64, 1, 4, 64), (300, 77, 2, 64), (128, 200, 2, 128)])
+def test_attention_tc_cross_attention(T, N, heads, d):
+    """CrossAttention (attention.py:169-193) on the flash kernel: tokens_kv != tokens, k/v in their own buffer."""
+    from stedm_b200 import ops
+    from tests import fake_ops
+    g = torch.Generator().manual_seed(T + N)
+    inner = heads * d
+    q = torch.randn(2, T, inner, generator=g).to(torch.bfloat16)
+    kv = torch.randn(2, N, 2 * inner, generator=g).to(torch.bfloat16)
+    scale = d ** -0.5
+    want = fake_ops.attention_simt(q, kv, kv, heads, d, T, 0, 0, inner, inner, d, scale, torch.float32,
+                                   tokens_kv=N, kv_token_stride=2 * inner)
+    got = ops.attention_tc(q.cuda(), kv.cuda(), kv.cuda(), heads, d, T, (T * inner, d, inner), scale, q_off=0, k_off=0,
+                           v_off=inner, tokens_kv=N, kv_strides=(N * 2 * inner, d, 2 * inner))
+    assert float((got.float().cpu() - want).abs().max()) < 2e-2
+    s = ops.attention_simt(q.float().cuda(), kv.float().cuda(), kv.float().cuda(), heads, d, T, 0, 0, inner, inner, d,
+                           scale, torch.float32, tokens_kv=N, kv_token_stride=2 * inner)
+    assert float((s.cpu() - want).abs().max()) < 1e-4
