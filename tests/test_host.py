@@ -54,8 +54,17 @@ def test_unet_rejects_configs_the_reference_cannot_build():
     from stedm_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
     with pytest.raises(TypeError):      # ds=1 in attention_resolutions -> reference: list.append() TypeError
         UNetModel(64, 6, 64, 3, 1, [1], channel_mult=(1, 2), num_heads=4)
+    with pytest.raises(AssertionError):  # openaimodel.py:494-498: the two spatial-transformer options come together
+        UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, use_spatial_transformer=True)
+    with pytest.raises(AssertionError):
+        UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, context_dim=512)
+    # the configuration the reference CAN build: a SpatialTransformer in middle_block[2], reference parameter names
+    m = UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, use_spatial_transformer=True, context_dim=128)
+    keys = set(m.state_dict())
+    assert {"middle_block.2.proj_in.weight", "middle_block.2.transformer_blocks.0.attn2.to_k.weight",
+            "middle_block.2.transformer_blocks.0.ff.net.0.proj.weight", "middle_block.2.proj_out.bias"} <= keys
     with pytest.raises(NotImplementedError):
-        UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, use_spatial_transformer=True, context_dim=512)
+        UNetModel(64, 6, 64, 3, 1, [32], channel_mult=(1, 2), num_heads=4, use_scale_shift_norm=True)
 
 
 def test_config_loader_composes_defaults_and_overrides():
