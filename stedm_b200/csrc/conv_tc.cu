@@ -20,8 +20,13 @@
 // with a single accumulator the tensor pipe idled ~30 % of the time behind the epilogue's global loads/stores.
 // CL = 2: the two CTAs of a cluster take neighbouring pixel tiles of the same channel tile and TMA-multicast one
 // half of the weight slab each into both CTAs (per-SM L2->SM traffic A+B/2 instead of A+B per slab).
-// Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287) + residual[m][n]
-// (skip connection, openaimodel.py:288); bf16/fp32 NHWC with 16-byte stores, or channel-major (eps/image heads).
+// K loop extras: the 1x1 skip_connection of a channel-changing ResBlock (openaimodel.py:246-256, 288) is folded in as
+// extra K slabs read from the block input through two more tensor maps, so conv3x3(a) + skip1x1(x) is one accumulator.
+// Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287), optional exact-erf GELU,
+// + residual[m][n] (identity skip, openaimodel.py:288); the bias / embedding rows are fetched while tcgen05.ld is in
+// flight, and NHWC outputs pass through a per-warp XOR-swizzled shared-memory transpose so that 4 lanes write one pixel
+// row's 64 contiguous bytes (whole 32-byte sectors; a thread owns a ROW of the accumulator, so direct stores were 32
+// half-written sectors per instruction); channel-major output for the eps / image heads; per-tile GroupNorm statistics.
 #include "../../include/stedm_b200.h"
 #include <stdlib.h>
 
