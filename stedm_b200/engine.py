@@ -34,6 +34,32 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def tc_geometry_ok(b, h, w, x1_batch=0):
+    """Can stedm_conv_tc tile this NHWC map?  128 consecutive pixels of the flattened (b, y, x) index must form one TMA
+    box {w_t, h_t, b_t}: true for the path's power-of-two maps (the shipped 512^2 / BASELINE's 256^2), false e.g. for a
+    96-wide latent.  Maps that do not tile run on the CUDA-core implicit-GEMM kernel instead (same results, far
+    slower): the layer stays functional for any size the reference accepts."""
+    if w >= 128:
+        if w % 128:
+            return False
+        tb = 1
+    else:
+        if 128 % w:
+            return False
+        rows = 128 // w
+        if h >= rows:
+            if h % rows:
+                return False
+            tb = 1
+        else:
+            if rows % h:
+                return False
+            tb = rows // h
+    if x1_batch and x1_batch != b and (x1_batch * h * w) % 128 and tb != 1:
+        return False
+    return True
+
+
 class PackedConv:
     """One convolution (nn.Conv2d 3x3/1x1 or nn.Conv1d k=1) repacked for the selected kernel.
 
@@ -43,7 +69,9 @@ class PackedConv:
     ``cin_split`` = (c0, c1) when the input is a two-source concat (each part padded separately)."""
 
     def __init__(self, weight, bias, prec, *, stride=1, force_simt=False, cin_split=None, cout_pad=None,
-                 fold_upsample=False):
+                 fold_upsample=False, pad=None):
+        self._src = (weight, bias, stride, cin_split)     # for the lazily built CUDA-core twin (odd map sizes)
+        self._twin = None
         w = weight.detach()
         if w.dim() == 3:  # Conv1d k=1
             w = w[:, :, :, None]
@@ -51,7 +79,7 @@ class PackedConv:
         assert kh == kw and kh in (1, 3)
         self.ksize, self.stride = kh, stride
         self.tc = prec.tc and not force_simt
-        pad = PAD_TC if self.tc else PAD_SIMT
+        pad = pad or (PAD_TC if self.tc else PAD_SIMT)
         parts = cin_split or (cin,)
         assert sum(parts) == cin
         w = w.permute(0, 2, 3, 1).float()                      # [Cout, kh, kw, Cin]
@@ -123,9 +151,30 @@ class PackedConv:
             self.bias = skip.bias.clone() if self.bias is None else (self.bias + skip.bias).contiguous()
         self.has_skip = True
 
+    def tc_ok(self, x0, x1=None):
+        """Does the tensor-core kernel take this call's map (the GEMM rows are the OUTPUT pixels for stride 2)?"""
+        b, h, w_, _ = x0.shape
+        if self.stride == 2:
+            h, w_ = h // 2, w_ // 2
+        return tc_geometry_ok(b, h, w_, 0 if x1 is None else x1.shape[0])
+
+    def _simt_twin(self):
+        """The same convolution packed for stedm_conv_simt (fp32 weights, the tensor-core path's channel padding)."""
+        if self._twin is None:
+            weight, bias, stride, cin_split = self._src
+            self._twin = PackedConv(weight, bias, self.prec, stride=stride, force_simt=True, cin_split=cin_split,
+                                    pad=PAD_TC)
+        return self._twin
+
     def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False,
                  want_stats=False, skip=None):
         out_dtype = out_dtype or self.prec.act
+        if self.tc and not self.tc_ok(x0, x1):
+            assert skip is None, "callers check tc_ok() before asking for the fused skip convolution"
+            out = self._simt_twin()(x0, x1, emb=emb, residual=residual, out_dtype=out_dtype, upsample=upsample,
+                                    out_nchw=out_nchw)
+            out._gn_tiles = None
+            return out
         if skip is not None:
             assert self.tc and getattr(self, "has_skip", False) and not upsample and self.stride == 1
             tiles, meta = self._tile_stats(x0, want_stats)
@@ -212,7 +261,7 @@ class PackedResBlock:
         a = self.n1(x0, x1, True, self.prec.act, pool.next())
         h = self.c1(a, emb=emb, want_stats=True)
         a = self.n2(h, None, True, self.prec.act, pool.next())
-        if self.fused_skip:
+        if self.fused_skip and self.c2.tc_ok(a):
             return self.c2(a, want_stats=True, skip=(x0, x1))
         if self.skip is not None:
             xs = self.skip(x0, x1)
@@ -493,7 +542,13 @@ class DecoderRunner:
         T = H * W
         a = self.att_norm(x, None, False, prec.act, pool.next())
         scale = float(Cc) ** -0.5
-        if prec.tc:
+        if prec.tc and not (tc_geometry_ok(1, H, W) and T % 16 == 0):
+            # a map the tensor-core kernel cannot tile (e.g. 96 x 96): materialised attention on CUDA cores
+            q, k, v = self.att_q(a), self.att_k(a), self.att_v(a)
+            outs = [ops.attention_simt(q[i:i + 1], k[i:i + 1], v[i:i + 1], 1, Cc, T, 0, 0, 0, Cc, Cc, scale, prec.act)
+                    for i in range(B)]
+            o = outs[0] if B == 1 else torch.cat(outs, 0)
+        elif prec.tc:
             # d = 512 is too wide for one CTA's TMEM (S + O accumulators), so the decoder attention runs as two
             # tensor-core GEMMs per sample on the implicit-GEMM kernel: S = Q K^T (K as the "weight" [T][C]) into a
             # reused fp32 T x T buffer, a scaled row softmax to bf16, and O = P V (V^T [C][T] written channel-major

@@ -27,7 +27,7 @@ import math
 import torch
 
 from . import ops
-from .engine import Precision
+from .engine import Precision, tc_geometry_ok
 
 
 class PackedLinear:
@@ -40,10 +40,28 @@ class PackedLinear:
         self.weight = w.to(torch.bfloat16).contiguous() if self.tc else w.t().contiguous()
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.act_dtype = prec.act
+        self._w32 = w if self.tc else None       # source of the CUDA-core twin for row counts that do not tile
+        self._simt_weight = None
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None):
-        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=out_dtype or self.act_dtype,
-                        tensor_core=self.tc, act=act, residual=residual)
+        od = out_dtype or self.act_dtype
+        if self.tc:
+            b, h, w_, c = x.shape
+            if not tc_geometry_ok(b, h, w_):
+                # a linear layer only needs ROWS: re-view the token matrix as whole 128-row tiles when it has them,
+                # otherwise (e.g. a 6 x 6 map with an odd batch) run the same GEMM on CUDA cores
+                rows = b * h * w_
+                if rows % 128 == 0 or 128 % rows == 0:
+                    shape = (1, rows // 128, 128) if rows % 128 == 0 else (1, 1, rows)
+                    out = ops.conv(x.view(*shape, c), self.weight, self.bias, self.n, 1, out_dtype=od, tensor_core=True,
+                                   act=act, residual=None if residual is None else residual.view(*shape, self.n))
+                    return out.view(b, h, w_, self.n)
+                if self._simt_weight is None:
+                    self._simt_weight = self._w32.t().contiguous()
+                return ops.conv(x, self._simt_weight, self.bias, self.n, 1, out_dtype=od, tensor_core=False, act=act,
+                                residual=residual)
+        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=od, tensor_core=self.tc, act=act,
+                        residual=residual)
 
 
 class PackedNormLN:
@@ -168,7 +186,7 @@ def _gemm_view(x2d_rows, c, t):
         return t.view(1, x2d_rows // 128, 128, c)
     if 128 % x2d_rows == 0:
         return t.view(1, 1, x2d_rows, c)
-    raise RuntimeError(f"style encoder: {x2d_rows} token rows do not tile into 128-row GEMM tiles")
+    return t.view(1, 1, x2d_rows, c)        # does not tile: PackedLinear runs it on the CUDA-core kernel
 
 
 class SetViTRunner:

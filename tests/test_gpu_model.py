@@ -483,3 +483,33 @@ def test_spatial_transformer_cross_attention_over_style_tokens(precision):
             r = rel_err(out, g[name])
             print(f"SpatialTransformer cross-attention bf16 rel err {name}: {r:.3e}")
             assert r < BF16_EPS_BAR, r
+
+
+def test_odd_latent_size_falls_back_to_cuda_cores_and_matches_oracle():
+    """A 96 x 96 image (latent 24; maps 24, 12, 6 in the U-Net, 24, 48, 96 in the decoder, 24/12/6/3 in the style encoder)
+    cannot be tiled by the tcgen05 kernel: in bf16 mode those layers run on the CUDA-core implicit-GEMM kernel (no
+    fused skip / statistics), everything else (GroupNorm, attention, step kernel, VQ) is unchanged.  The path must stay
+    functional for every size the reference accepts and keep the bf16 bars."""
+    L, B = 24, 1
+    m = build_model(L, n_style=1, precision="bf16")
+    model = m._model
+    sd = oracle_state_dict(model)
+    seg, style, x_T = O.synthetic_batch(B, 4 * L, 1, seed=9)
+    batch = {"image": torch.zeros(B, 4 * L, 4 * L, 3).cuda(), "segmentation": seg.cuda(), "style_imgs": style.cuda()}
+    _, c = model.get_input(batch, "image")
+    with torch.no_grad():
+        want_c = O.get_conditioning(sd, seg, style)
+    assert rel_err(c["c_crossattn"][0], want_c["c_crossattn"][0]) < BF16_EPS_BAR
+    t = torch.full((B,), 481, dtype=torch.long)
+    eps = model.apply_model(x_T.cuda(), t.cuda(), c)
+    with torch.no_grad():
+        want = O.apply_model(sd, x_T, t, want_c)
+    r = rel_err(eps, want)
+    print(f"latent-24 (CUDA-core fallback) bf16 eps rel err {r:.3e}")
+    assert r < BF16_EPS_BAR, r
+    img = model.decode_first_stage(x_T.cuda() * 40)
+    with torch.no_grad():
+        want_img = O.decode_first_stage(sd, x_T * 40)
+    p = psnr(img.clamp(-1, 1), want_img.clamp(-1, 1))
+    print(f"latent-24 bf16 decode PSNR {p:.1f} dB")
+    assert tuple(img.shape) == (B, 3, 96, 96) and p >= PSNR_BAR
