@@ -196,6 +196,9 @@ int stedm_nhwc_to_nchw_f32(const void* x, int dtype, float* out, int batch, int 
  * K8  Embedding path.
  * timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out[b] = [cos(t f) | sin(t f)], dim even. */
 int stedm_timestep_embedding(const long long* t, float* out, int batch, int dim, void* stream);
+/* The same for fractional timesteps: DPM-Solver feeds the U-Net t = (t_continuous - 1/N) * 1000 as a float
+ * (ldm/models/diffusion/dpm_solver/dpm_solver.py:246-255; util.py:165 multiplies timesteps[:, None].float()). */
+int stedm_timestep_embedding_f32(const float* t, float* out, int batch, int dim, void* stream);
 /* out[b][n] = g(bias[n] + sum_k f(in[b][k]) * w[n][k]) (nn.Linear (out,in) layout); act is a bit set:
  * 1 = f is SiLU, 2 = f is ReLU, 4 = g is ReLU.  Covers time_embed (openaimodel.py:530-534), all emb_layers
  * (openaimodel.py:231-237) in one launch when their weights are stacked along n, the style encoder's head

@@ -3,7 +3,7 @@ on fixture weights, and assert that oracle/stedm_oracle.py reproduces every tens
 
 Run once in the build container (the reference cannot travel to the GPU box):
 
-    python -m oracle.make_golden [--only small|c1|sched|svit|plms|st]
+    python -m oracle.make_golden [--only small|c1|sched|svit|plms|st|dpm]
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -244,6 +244,42 @@ def gen_spatial_transformer():
     print("[st] wrote spatial_transformer.npz")
 
 
+@torch.no_grad()
+def gen_dpm():
+    """DPM-Solver on the REAL reference model (it takes STEDM's dict conditioning, dpm_solver.py:306-316): the reference's
+    DPMSolverSampler on S_ZSS_DM with fixture weights, S = 12 (second-order multistep, first-order final step) and
+    S = 16; asserts oracle.dpm_solver_sample == reference and stores the final latents."""
+    import contextlib
+    import io
+    model = ref_shims.build_reference_model(latent_size=32, style_sampling="mp", num_patches=2)
+    apply_fixture_weights(model, seed=0)
+    sd = canonical_sd(model)
+    from ldm.models.diffusion.dpm_solver.sampler import DPMSolverSampler
+    g = load_small_cond()
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["c_crossattn"])]}
+    unc = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["uc_crossattn"])]}
+    _, _, x_T = O.synthetic_batch(2, 128, 2, 0)
+    out = {}
+    for S in (12, 16):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            want, _ = DPMSolverSampler(model, device=torch.device("cpu")).sample(
+                S, 2, (3, 32, 32), conditioning=cond, verbose=False, x_T=x_T, unconditional_guidance_scale=1.5,
+                unconditional_conditioning=unc)
+        got = O.dpm_solver_sample(lambda x, t: O.apply_model(sd, x, t, cond), x_T, model.alphas_cumprod.numpy(), S,
+                                  cfg_scale=1.5, uncond_eps_fn=lambda x, t: O.apply_model(sd, x, t, unc))
+        d = maxdiff(want, got)
+        print(f"[dpm S={S}] oracle vs reference DPMSolverSampler: max|d| = {d:.3e} (|x|max {float(want.abs().max()):.3f})")
+        assert d < 1e-3 * float(want.abs().max())
+        out[f"dpm_s{S}"] = want.numpy()
+    np.savez_compressed(os.path.join(GOLD, "dpm_solver.npz"), **out)
+    print("[dpm] wrote dpm_solver.npz")
+
+
+def load_small_cond():
+    z = np.load(os.path.join(GOLD, "small_b2_l32.npz"))
+    return {k: z[k] for k in ("c_concat", "c_crossattn", "uc_crossattn")}
+
+
 class _StandInModel:
     """The minimum a reference sampler touches (plms.py:12-56, 177-191), with a deterministic non-linear eps so that the
     sampler arithmetic — timestep sequence, multistep coefficients, guidance combine, x_prev update — can be run through
@@ -306,6 +342,8 @@ if __name__ == "__main__":
         gen_plms()
     if a.only in ("all", "st"):
         gen_spatial_transformer()
+    if a.only in ("all", "dpm"):
+        gen_dpm()
     if a.only in ("all", "small"):
         # B=2, latent 32 (128^2 image), two style images per sample (exercises Agg_Mean), full DDIM-50
         gen_case("small_b2_l32", B=2, L=32, n_style=2, S=50, full_steps=True, seed=0, store_f16_image=False)

@@ -243,6 +243,81 @@ def ddim_sample(sd, cond, uncond, x_T, S=50, eta=0.0, cfg_scale=1.5, num_heads=8
     return img, inter
 
 
+class DiscreteVPSchedule:
+    """NoiseScheduleVP('discrete', alphas_cumprod=...), ldm/models/diffusion/dpm_solver/dpm_solver.py:7-160, restated on
+    the host in float64: key points t_n = (n + 1) / N with log alpha(t_n) = 0.5 log(alphas_cumprod[n]) (:78-88),
+    log alpha(t) piecewise linear in between (interpolate_fn, :1113-1151), sigma = sqrt(1 - alpha^2) (:126-130),
+    lambda = log alpha - log sigma (:132-138)."""
+
+    def __init__(self, alphas_cumprod):
+        ac = np.asarray(alphas_cumprod, dtype=np.float64)
+        self.N = ac.shape[0]
+        self.t = np.arange(1, self.N + 1, dtype=np.float64) / self.N
+        self.log_alpha_n = 0.5 * np.log(ac)
+
+    def log_alpha(self, t):
+        return float(np.interp(t, self.t, self.log_alpha_n))
+
+    def alpha(self, t):
+        return math.exp(self.log_alpha(t))
+
+    def sigma(self, t):
+        return math.sqrt(1.0 - math.exp(2.0 * self.log_alpha(t)))
+
+    def lam(self, t):
+        la = self.log_alpha(t)
+        return la - 0.5 * math.log(1.0 - math.exp(2.0 * la))
+
+    def model_time(self, t):
+        """get_model_input_time, :246-255: continuous t in [1/N, 1] -> the U-Net's (fractional) timestep."""
+        return (t - 1.0 / self.N) * 1000.0
+
+
+def dpm_solver_sample(eps_fn, x_T, alphas_cumprod, S, cfg_scale=1.0, uncond_eps_fn=None):
+    """DPMSolverSampler.sample (dpm_solver/sampler.py:27-95) as the reference configures it: DPM_Solver(predict_x0=True,
+    thresholding=False).sample(steps=S, skip_type='time_uniform', method='multistep', order=2, lower_order_final=True)
+    with plain classifier-free guidance (dpm_solver.py:302-320).  data prediction x0 = (x - sigma eps) / alpha (:361-374);
+    first-order update x_t = (sigma_t / sigma_s) x - alpha_t expm1(-h) x0_s (:478-510); second-order multistep update
+    with D1 = (x0_0 - x0_1) / r0, r0 = h_0 / h (:732-768); time steps linspace(1, 1/N, S + 1) (:402-403); the last step
+    drops to first order when S < 15 (:1075-1078).  ``eps_fn(x, t_model)`` takes the FLOAT model time."""
+    ns = DiscreteVPSchedule(alphas_cumprod)
+    ts = np.linspace(1.0, 1.0 / ns.N, S + 1)
+    b = x_T.shape[0]
+
+    def x0_of(x, t):
+        tm = torch.full((b,), ns.model_time(t), dtype=torch.float32)
+        e = eps_fn(x, tm)
+        if uncond_eps_fn is not None and cfg_scale != 1.0:
+            e_u = uncond_eps_fn(x, tm)
+            e = e_u + cfg_scale * (e - e_u)
+        return (x - ns.sigma(t) * e) / ns.alpha(t)
+
+    def first(x, s, t, m_s):
+        h = ns.lam(t) - ns.lam(s)
+        return (ns.sigma(t) / ns.sigma(s)) * x - (ns.alpha(t) * math.expm1(-h)) * m_s
+
+    def second(x, t_p1, t_p0, t, m_p1, m_p0):
+        h0, h = ns.lam(t_p0) - ns.lam(t_p1), ns.lam(t) - ns.lam(t_p0)
+        d1 = (1.0 / (h0 / h)) * (m_p0 - m_p1)
+        c = ns.alpha(t) * (math.exp(-h) - 1.0)
+        return (ns.sigma(t) / ns.sigma(t_p0)) * x - c * m_p0 - 0.5 * c * d1
+
+    x = x_T
+    m_prev = [x0_of(x, ts[0])]
+    t_prev = [ts[0]]
+    x = first(x, ts[0], ts[1], m_prev[0])                       # init order 1
+    m_prev.append(x0_of(x, ts[1]))
+    t_prev.append(ts[1])
+    for step in range(2, S + 1):
+        order = min(2, S + 1 - step) if S < 15 else 2
+        t = ts[step]
+        x = second(x, t_prev[0], t_prev[1], t, m_prev[0], m_prev[1]) if order == 2 else first(x, t_prev[1], t, m_prev[1])
+        t_prev, m_prev = [t_prev[1], t], [m_prev[1], None]
+        if step < S:
+            m_prev[1] = x0_of(x, t)
+    return x
+
+
 def plms_sample(eps_fn, x_T, S=50, cfg_scale=1.0, uncond_eps_fn=None, max_steps=None):
     """PLMSSampler.sample / plms_sampling / p_sample_plms, ldm/models/diffusion/plms.py:113-236, eta = 0:
     e_t = e_u + w (e_c - e_u) (plain guidance, :184); first step = pseudo improved Euler (:219-223), then

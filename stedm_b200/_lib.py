@@ -47,6 +47,7 @@ SIGNATURES = {
     "stedm_pack_nchw_to_nhwc": [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp],
     "stedm_nhwc_to_nchw_f32": [vp, i32, vp, i32, i32, i32, vp],
     "stedm_timestep_embedding": [vp, vp, i32, i32, vp],
+    "stedm_timestep_embedding_f32": [vp, vp, i32, i32, vp],
     "stedm_linear": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "stedm_vq_nearest": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "stedm_spatial_rescale": [vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -241,7 +241,8 @@ extern "C" int stedm_im2col_3x3_s2(const void* x, void* out, int dtype, int batc
 // =====================================================================================================
 // K8: sinusoidal timestep embedding and small row-vector linears (fp32; weights are read once per launch).
 // =====================================================================================================
-__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int dim) {
+template <typename TT>
+__global__ void timestep_embedding_kernel(const TT* __restrict__ t, float* __restrict__ out, int dim) {
   const int b = blockIdx.x, half = dim / 2;
   const float tv = static_cast<float>(t[b]);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -255,8 +256,14 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, float
 
 extern "C" int stedm_timestep_embedding(const long long* t, float* out, int batch, int dim, void* stream) {
   STEDM_REQUIRE(t && out && batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad argument");
-  timestep_embedding_kernel<<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(t, out, dim);
+  timestep_embedding_kernel<long long><<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(t, out, dim);
   return check_launch("timestep_embedding");
+}
+
+extern "C" int stedm_timestep_embedding_f32(const float* t, float* out, int batch, int dim, void* stream) {
+  STEDM_REQUIRE(t && out && batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding_f32: bad argument");
+  timestep_embedding_kernel<float><<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(t, out, dim);
+  return check_launch("timestep_embedding_f32");
 }
 
 // One warp per output feature n; the weight row is read once (float4) and reused for up to 8 batch rows held in

@@ -379,7 +379,10 @@ class UNetRunner:
         cache = self.__dict__.setdefault("_temb_cache", {})
         row = cache.get(t_value)
         if row is None or row.device != device:
-            t = torch.full((1,), int(t_value), dtype=torch.int64, device=device)
+            if isinstance(t_value, float) and not t_value.is_integer():     # DPM-Solver's fractional model time
+                t = torch.full((1,), t_value, dtype=torch.float32, device=device)
+            else:
+                t = torch.full((1,), int(t_value), dtype=torch.int64, device=device)
             e = ops.linear(ops.timestep_embedding(t, self.mc), *self.te0)
             e = ops.linear(e, *self.te2, silu_in=True)
             row = cache[t_value] = ops.linear(e, self.emb_w, self.emb_b, silu_in=True)

@@ -302,10 +302,12 @@ def nhwc_to_nchw_f32(x):
 
 # ------------------------------------------------------------------------------------------------ K8
 def timestep_embedding(t, dim):
+    """util.py:151-171 for int64 timesteps, or float32 ones (DPM-Solver's fractional model times)."""
     _cuda(t)
-    assert t.dtype == torch.int64
+    assert t.dtype in (torch.int64, torch.float32)
     out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
-    _call("stedm_timestep_embedding", _ptr(t), _ptr(out), t.shape[0], dim, _stream())
+    name = "stedm_timestep_embedding" if t.dtype == torch.int64 else "stedm_timestep_embedding_f32"
+    _call(name, _ptr(t), _ptr(out), t.shape[0], dim, _stream())
     return out
 
 

@@ -513,3 +513,20 @@ def test_odd_latent_size_falls_back_to_cuda_cores_and_matches_oracle():
     p = psnr(img.clamp(-1, 1), want_img.clamp(-1, 1))
     print(f"latent-24 bf16 decode PSNR {p:.1f} dB")
     assert tuple(img.shape) == (B, 3, 96, 96) and p >= PSNR_BAR
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dpm_solver_sampler_matches_reference(precision):
+    """DPMSolverSampler (dpm_solver/sampler.py) on the native U-Net at fractional model times vs the reference's own
+    sampler run on the reference model (tests/golden/dpm_solver.npz, S = 12 and 16)."""
+    from stedm_b200.ldm.models.diffusion.dpm_solver import DPMSolverSampler
+    g, _, _, x_T = _small_inputs()
+    m = build_model(32, n_style=2, precision=precision)
+    cond, unc = _cond(g, "c_crossattn"), _cond(g, "uc_crossattn")
+    gold = load_golden("dpm_solver")
+    for S in (12, 16):
+        z, _ = DPMSolverSampler(m._model).sample(S, 2, (3, 32, 32), conditioning=cond, verbose=False, x_T=x_T.cuda(),
+                                                 unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
+        r = rel_err(z, gold[f"dpm_s{S}"])
+        print(f"DPM-Solver S={S} {precision} final latent rel err {r:.3e}")
+        assert r < (1e-4 if precision == "fp32" else BF16_EPS_BAR), r

@@ -86,3 +86,21 @@ def test_oracle_plms_matches_reference_sampler_golden():
     got1 = O.plms_sample(lambda x, t: eps(x, t, c), x_T, S=20)
     got3 = O.plms_sample(lambda x, t: eps(x, t, c), x_T, S=20, cfg_scale=3.0, uncond_eps_fn=lambda x, t: eps(x, t, uc))
     assert max_abs(got1, gold["plms_s20_cfg1"]) < 1e-6 and max_abs(got3, gold["plms_s20_cfg3"]) < 1e-6
+
+
+def test_oracle_dpm_solver_matches_reference_golden(fixture_sd):
+    """oracle.dpm_solver_sample (multistep order 2, data prediction, plain CFG) == the reference's DPMSolverSampler run on
+    its own S_ZSS_DM with fixture weights (tests/golden/dpm_solver.npz), S = 12: ten second-order steps, first-order
+    init and final step."""
+    import torch
+    from oracle import stedm_oracle as O
+    g = load_golden("small_b2_l32")
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["c_crossattn"])]}
+    unc = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["uc_crossattn"])]}
+    _, _, x_T = O.synthetic_batch(2, 128, 2, 0)
+    ac, _ = O.alphas_cumprod_linear()
+    with torch.no_grad():
+        got = O.dpm_solver_sample(lambda x, t: O.apply_model(fixture_sd, x, t, cond), x_T, ac, 12, cfg_scale=1.5,
+                                  uncond_eps_fn=lambda x, t: O.apply_model(fixture_sd, x, t, unc))
+    want = load_golden("dpm_solver")["dpm_s12"]
+    assert max_abs(got, want) < 1e-5 * float(abs(want).max())
