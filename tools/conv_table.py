@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--what", default="unet", help="unet (one guided DDIM step) | decode (one VQ decode)")
     a = ap.parse_args()
     from stedm_b200 import ops
     from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
@@ -30,6 +31,8 @@ def main():
         s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
         ts = torch.full((a.batch,), 481, device=dev, dtype=torch.long)
         step = lambda: s.p_sample_ddim(x_T, c, ts, index=24, unconditional_guidance_scale=1.5, unconditional_conditioning=cu)
+        if a.what == "decode":
+            step = lambda: model.decode_first_stage(x_T * 60)
         for _ in range(3):
             step()
         rec, orig = [], ops.conv
