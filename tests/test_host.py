@@ -108,3 +108,20 @@ def test_no_cpu_fallback(model):
                                            context=torch.zeros(1, 512))
     with pytest.raises(RuntimeError):
         model._model.first_stage_model.decode(torch.zeros(1, 3, 32, 32))
+
+
+def test_prepare_batch_merges_multi_class_layouts(model):
+    """CATCH / HER2 layouts have K > 2 classes (conf/data/catch.yaml: 6, her2.yaml: 8): prepare_batch sums classes
+    1..K-1 into the foreground channel and keeps two channels, channels-last (modules/ldm_diffusion.py:51-60)."""
+    g = torch.Generator().manual_seed(0)
+    B, K, P, N = 2, 6, 16, 3
+    lab = torch.randint(0, K, (B, P, P), generator=g)
+    seg_oh = torch.nn.functional.one_hot(lab, K).permute(0, 3, 1, 2).float()
+    img = torch.rand(B, 3, P, P, generator=g)
+    style = torch.rand(B, N, 3, P, P, generator=g)
+    out = model.prepare_batch((img, seg_oh.clone(), lab, style, torch.arange(B)))
+    assert tuple(out["image"].shape) == (B, P, P, 3) and tuple(out["style_imgs"].shape) == (B, N, P, P, 3)
+    assert tuple(out["segmentation"].shape) == (B, P, P, 2)
+    assert torch.equal(out["segmentation"][..., 0], (lab == 0).float())
+    assert torch.equal(out["segmentation"][..., 1], (lab != 0).float())
+    assert torch.equal(out["style_imgs"][1, 2, :, :, 0], style[1, 2, 0])
