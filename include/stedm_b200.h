@@ -130,6 +130,12 @@ typedef struct stedm_conv_desc {
                           [cout][k*k*(c0+c1) + skip_c0 + skip_c1] (the 1x1 weights appended along K), `bias` = the sum
                           of both biases.  NULL => no fused skip. */
   const void* skip_x1; /* second skip source (channel concat) or NULL */
+  int32_t x0_pix_stride; /* tensor-core path: channels between consecutive pixels of x0 when x0 is a channel SLICE of a
+                            wider NHWC tensor (0 => c0, dense) */
+  int32_t res_batch;     /* tensor-core path: samples in `residual` when it has fewer than `batch` (broadcast as
+                            b % res_batch; 0 => batch).  Together these let a convolution over a concat [h | skip] whose
+                            skip half is shared by the two halves of a guided batch run as conv(h) + conv(skip), the
+                            second term computed once and added here as a broadcast fp32 residual */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,

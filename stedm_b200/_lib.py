@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("upsample", C.c_int32), ("emb_stride", C.c_int32), ("res_dtype", C.c_int32),
                 ("out_dtype", C.c_int32), ("out_nchw", C.c_int32), ("cout", C.c_int32), ("cout_store", C.c_int32), ("tap_mode", C.c_int32), ("phase", C.c_int32),
                 ("act", C.c_int32), ("skip_c0", C.c_int32), ("skip_c1", C.c_int32), ("skip_x1_batch", C.c_int32),
-                ("skip_x0", vp), ("skip_x1", vp)]
+                ("skip_x0", vp), ("skip_x1", vp), ("x0_pix_stride", C.c_int32), ("res_batch", C.c_int32)]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)

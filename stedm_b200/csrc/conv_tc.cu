@@ -80,6 +80,7 @@ struct TcParams {
   // fused 1x1 skip convolution (ResBlock skip_connection / nin_shortcut): extra K slabs after the k x k taps, read at
   // the output pixel itself from a second input [skip0 | skip1]; its weights are appended along K
   int skip_c0_blks, skip_blks, skip_x1_batch;
+  int res_rows;          // > 0: the residual has fewer samples than the output and is broadcast: row = m % res_rows
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -359,8 +360,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         const size_t o = o_row + n;
         if (valid && p.residual) {
+          // a residual with fewer samples (the part of a sum that is shared by the cond / uncond halves of a guided
+          // batch) is read at row m % res_rows
+          const size_t o_res = p.res_rows > 0 ? static_cast<size_t>(m % p.res_rows) * p.cout + n : o;
           if (p.res_dtype == DT_BF16) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o);
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o_res);
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               const uint4 u = rp[j / 8];
@@ -371,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               f = unpack_bf16x2(u.w); v[j + 6] += f.x; v[j + 7] += f.y;
             }
           } else {
-            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o);
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o_res);
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 t = rp[j / 4];
@@ -530,10 +534,11 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
     o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
   }
   if (p.residual) {
+    const size_t o_res = p.res_rows > 0 ? static_cast<size_t>(m % p.res_rows) * p.cout + n : o;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[j] += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[o + j]
-                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[o + j]);
+      v[j] += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[o_res + j]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[o_res + j]);
   }
   if (p.out_nchw) {
     const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
@@ -704,8 +709,10 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->c0), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                               static_cast<uint64_t>(B)};
-    const uint64_t str[3] = {static_cast<uint64_t>(d->c0) * 2, static_cast<uint64_t>(W) * d->c0 * 2,
-                             static_cast<uint64_t>(H) * W * d->c0 * 2};
+    // x0 may be a channel slice of a wider NHWC tensor: its pixels are x0_pix_stride channels apart
+    const uint64_t ps0 = d->x0_pix_stride > 0 ? d->x0_pix_stride : d->c0;
+    STEDM_REQUIRE(ps0 >= static_cast<uint64_t>(d->c0) && ps0 % 8 == 0, "conv_tc: bad x0 pixel stride %d", d->x0_pix_stride);
+    const uint64_t str[3] = {ps0 * 2, static_cast<uint64_t>(W) * ps0 * 2, static_cast<uint64_t>(H) * W * ps0 * 2};
     const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
     int rc = make_tmap_bf16(&ma0, d->x0, 4, dims, str, box);
     if (rc) return rc;
@@ -791,6 +798,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
   p.act = d->act;
   p.skip_blks = skip_blks; p.skip_c0_blks = skip_c > 0 ? d->skip_c0 / TC_BK : 0; p.skip_x1_batch = skip_x1b;
+  p.res_rows = 0;
+  if (d->residual != nullptr && d->res_batch > 0 && d->res_batch != B) {
+    STEDM_REQUIRE(d->tap_mode == 0 && B % d->res_batch == 0, "conv_tc: residual batch %d does not divide the batch %d",
+                  d->res_batch, B);
+    p.res_rows = d->res_batch * H * W;
+  }
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {
     STEDM_REQUIRE(bn >= 64 && d->cout % bn == 0 && d->out_nchw == 0 && (H * W) % TC_BM == 0,

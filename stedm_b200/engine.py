@@ -17,6 +17,8 @@ from . import ops
 
 PAD_TC = 64   # channel padding granularity of the tensor-core path (one 128-byte K slab of bf16)
 FUSE_SKIP = [True]   # fold ResBlock 1x1 skip convolutions into the second 3x3 conv (A/B switch for measurements)
+SPLIT_CONCAT = [True]  # decoder conv1([h | skip]): the skip channels shared by cond / uncond convolved once per distinct sample
+SPLIT_MIN_SHARED = 384  # ... when at least this many input channels are shared (PackedResBlock._split_point)
 PAD_SIMT = 4
 
 
@@ -104,6 +106,7 @@ class PackedConv:
                     b = torch.nn.functional.pad(b, (0, cp - cout))
                 self.cout = cp
             self.weight = w.reshape(self.cout, -1).to(torch.bfloat16).contiguous()
+            self._split_cache = {}
             self.phase_weights = None
             if fold_upsample:
                 # nearest-x2 upsample followed by a 3x3 conv == four 2x2 convs on the low-resolution input, one per
@@ -139,6 +142,17 @@ class PackedConv:
         m_tiles = b * h * w_ // 128
         tiles = torch.empty((reps * m_tiles, self.cout, 2), device=x.device, dtype=torch.float32)
         return tiles, (tiles, self.cout, reps, m_tiles, h * w_ // 128, b)
+
+    def split_weights(self, sp):
+        """The same convolution as two K ranges, conv([x_lo | x_hi]) = conv_lo(x[..., :sp]) + conv_hi(x[..., sp:]), for
+        a split channel ``sp`` (a multiple of the K slab): used when the channels above ``sp`` are shared by the cond /
+        uncond halves of a guided batch (PackedResBlock.__call__)."""
+        if sp not in self._split_cache:
+            assert self.tc and sp % PAD_TC == 0 and 0 < sp < self.cin_pad and not getattr(self, "has_skip", False)
+            w = self.weight.view(self.cout, self.ksize * self.ksize, self.cin_pad)
+            self._split_cache[sp] = (w[..., :sp].reshape(self.cout, -1).contiguous(),
+                                     w[..., sp:].reshape(self.cout, -1).contiguous())
+        return self._split_cache[sp]
 
     def fuse_skip(self, skip):
         """Fold a 1x1 skip convolution on the block input (ResBlock.skip_connection, openaimodel.py:246-256;
@@ -257,9 +271,38 @@ class PackedResBlock:
             self.fused_skip = True
         self.prec = prec
 
+    def _split_point(self, x0, x1):
+        """conv1([h | skip]) may run as conv_lo(a[..., :sp]) + conv_hi(a[..., sp:]) with the second term computed once
+        per DISTINCT skip sample: every GroupNorm group that lies wholly inside the skip half is normalised with
+        statistics of the skip tensor alone, so those channels of the normalised concat are identical for the cond and
+        uncond halves of a guided batch.  sp = the first K-slab boundary at or above the end of the group that straddles
+        the h | skip boundary (= c0 when no group straddles).  Returns 0 when not applicable or not worth it: the saved
+        FLOPs (9 * shared * 2 per output) must outweigh writing and twice re-reading the fp32 partial (12 B per
+        output) at ~200 FLOP per HBM byte, with margin."""
+        if not (SPLIT_CONCAT[0] and self.c1.tc and x1 is not None and x1.shape[0] < x0.shape[0]):
+            return 0
+        c0, c1 = x0.shape[-1], x1.shape[-1]
+        if c0 % PAD_TC or c1 % PAD_TC or (c0 + c1) % 32 or not self.c1.tc_ok(x0):
+            return 0
+        cpg = (c0 + c1) // 32
+        sp = _round_up(_round_up(c0, cpg), PAD_TC)
+        return sp if c0 + c1 - sp >= SPLIT_MIN_SHARED else 0
+
     def __call__(self, x0, x1, emb, pool):
         a = self.n1(x0, x1, True, self.prec.act, pool.next())
-        h = self.c1(a, emb=emb, want_stats=True)
+        sp = self._split_point(x0, x1)
+        if sp:
+            bs = x1.shape[0]
+            w_lo, w_hi = self.c1.split_weights(sp)
+            # shared channels: one pass over the bs distinct samples (fp32 partial sums, no bias) ...
+            part = ops.conv(a[:bs, :, :, sp:], w_hi, None, self.c1.cout, 3, out_dtype=torch.float32, tensor_core=True)
+            # ... the rest: + bias + embedding + the partial broadcast as b % bs, statistics of the sum for the next GN
+            tiles, meta = self.c1._tile_stats(x0, True)
+            h = ops.conv(a[..., :sp], w_lo, self.c1.bias, self.c1.cout, 3, emb=emb, residual=part,
+                         out_dtype=self.prec.act, tensor_core=True, stats_out=tiles)
+            h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
+        else:
+            h = self.c1(a, emb=emb, want_stats=True)
         a = self.n2(h, None, True, self.prec.act, pool.next())
         if self.fused_skip and self.c2.tc_ok(a):
             return self.c2(a, want_stats=True, skip=(x0, x1))

@@ -140,7 +140,19 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
          act=0, skip_x0=None, skip_x1=None):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
-    _cuda(x0, x1, weight, bias, residual, skip_x0, skip_x1)
+    x0_pix_stride = 0
+    if x0.is_cuda and not x0.is_contiguous():
+        # a channel slice a[..., lo:hi] of a wider NHWC tensor: same pixels, stride(2) channels apart
+        bb, hh, ww, cc = x0.shape
+        ps = x0.stride(2)
+        assert x0.stride(3) == 1 and ps >= cc and x0.stride(1) == ww * ps and x0.stride(0) == hh * ww * ps, x0.stride()
+        assert tensor_core, "channel-slice inputs are a tensor-core path feature"
+        x0_pix_stride = ps
+        _cuda(x1, weight, bias, residual, skip_x0, skip_x1)
+        if not x0.is_cuda:
+            raise RuntimeError("stedm_b200 ops take CUDA tensors only (no CPU fallback)")
+    else:
+        _cuda(x0, x1, weight, bias, residual, skip_x0, skip_x1)
     if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
         assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] == cout
         assert emb.shape[0] in (1, x0.shape[0])          # one row per sample, or one row broadcast to all samples
@@ -166,6 +178,10 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.cout_store = cout_store if out_nchw else 0
     d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
     d.act = act
+    d.x0_pix_stride = x0_pix_stride
+    if residual is not None and residual.shape[0] != b:   # broadcast residual (b % res_batch), tensor-core path
+        assert tensor_core and b % residual.shape[0] == 0 and residual.shape[1:] == (oh, ow, cout)
+        d.res_batch = residual.shape[0]
     skip_c = 0
     if skip_x0 is not None:     # fused 1x1 skip convolution over [skip_x0 | skip_x1] (weights appended along K)
         assert tensor_core and skip_x0.shape[1:3] == (h, w) and skip_x0.shape[0] == b and skip_x0.dtype == x0.dtype

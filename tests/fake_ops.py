@@ -104,7 +104,8 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     if act == 1:
         y = F.gelu(y)
     if residual is not None:
-        y = y + _nchw(residual.float())
+        r = _nchw(residual.float())
+        y = y + (r if r.shape[0] == y.shape[0] else r.repeat(y.shape[0] // r.shape[0], 1, 1, 1))
     if out_nchw:
         return y[:, :cout_store or cout].contiguous()
     return _nhwc(y).to(out_dtype or x0.dtype)

@@ -27,7 +27,7 @@ def test_library_exports_header_symbols():
 
 def test_conv_desc_layout_matches_header():
     from stedm_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 22 * 4 + 2 * 8  # 9 pointers, int64, 22 int32, 2 pointers
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 22 * 4 + 2 * 8 + 2 * 4  # 9 ptrs, int64, 22 int32, 2 ptrs, 2 int32
 
 
 def test_sass_is_blackwell_native():

@@ -139,3 +139,23 @@ def test_spatial_transformer_glue(patched_all, precision, bar):
             out = r(h, pool, c).float().permute(0, 3, 1, 2)
         scale = float(abs(g[name]).max()) if precision == "bf16" else 1.0
         assert max_abs(out, g[name]) < bar * scale, (name, max_abs(out, g[name]))
+
+
+# ------------------------------------------------------------------------------ split of the decoder's concat conv
+@pytest.mark.parametrize("c0,c1,want", [(1024, 1024, 1024),   # 64 ch / group: no group straddles -> split at c0
+                                        (1024, 512, 1088),    # 48 ch / group: group 1008..1055 straddles -> next slab
+                                        (512, 512, 512),
+                                        (512, 128, 0),        # 20 ch / group: only 64 shared channels -> not worth it
+                                        (128, 128, 0)])       # 128 shared channels at 64^2: HBM cost > FLOPs saved
+def test_split_point_of_concat_conv(patched, c0, c1, want):
+    """PackedResBlock._split_point: the channels of the normalised [h | skip] concat above the split must belong to
+    GroupNorm groups that lie wholly inside the skip half (their values are then shared by cond / uncond)."""
+    blk = patched.PackedResBlock.__new__(patched.PackedResBlock)
+    blk.c1 = type("C", (), {"tc": True, "tc_ok": staticmethod(lambda x: True)})()
+    x0, x1 = torch.empty(4, 16, 16, c0), torch.empty(2, 16, 16, c1)
+    sp = blk._split_point(x0, x1)
+    assert sp == want
+    if sp:
+        cpg = (c0 + c1) // 32
+        assert sp % 64 == 0 and sp >= c0 and (sp // cpg) * cpg >= c0 and all((g * cpg >= c0) for g in range(-(-sp // cpg), 32))
+    assert blk._split_point(x0, torch.empty(4, 16, 16, c1)) == 0      # unguided pass: nothing is shared

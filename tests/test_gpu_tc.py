@@ -254,3 +254,24 @@ def test_conv_tc_fused_skip_connection(ops, B, hw, cmid, cs0, cs1, co, sb):
     if stats is not None:
         tiles = nhwc(want).reshape(-1, 128, co)
         assert max_abs(stats[..., 0].cpu(), tiles.sum(1)) < 0.05 and max_abs(stats[..., 1].cpu(), (tiles ** 2).sum(1)) < 0.5
+
+
+def test_conv_tc_channel_slice_input_and_broadcast_residual(ops):
+    """conv([h | s]) as conv_h(a[..., :c0]) + conv_s(a[:Bs, ..., c0:]): channel-slice views of one NHWC tensor as inputs
+    (x0_pix_stride) and the fp32 partial of the shared half added as a residual broadcast over b % Bs (res_batch)."""
+    g = torch.Generator().manual_seed(123)
+    B, Bs, c0, c1, co, hw = 4, 2, 128, 64, 256, 16
+    h = bf(torch.randn(B, c0, hw, hw, generator=g))
+    s = bf(torch.randn(Bs, c1, hw, hw, generator=g))
+    w = bf(torch.randn(co, c0 + c1, 3, 3, generator=g) / math.sqrt(9 * (c0 + c1)))
+    b = torch.randn(co, generator=g)
+    a_full = torch.cat([h, s.repeat(B // Bs, 1, 1, 1)], 1)
+    want = F.conv2d(a_full, w, b, padding=1)
+    a = nhwc(a_full).to(torch.bfloat16).cuda()                       # [B, H, W, c0 + c1]
+    part = ops.conv(a[:Bs, :, :, c0:], tc_w(w[:, c0:]).cuda(), None, co, 3, out_dtype=torch.float32, tensor_core=True)
+    assert tuple(part.shape) == (Bs, hw, hw, co)
+    got = ops.conv(a[..., :c0], tc_w(w[:, :c0]).cuda(), b.cuda(), co, 3, residual=part, out_dtype=torch.float32,
+                   tensor_core=True)
+    assert max_abs(nchw(got.cpu()), want) < 3e-3, max_abs(nchw(got.cpu()), want)
+    whole = ops.conv(a, tc_w(w).cuda(), b.cuda(), co, 3, out_dtype=torch.float32, tensor_core=True)
+    assert max_abs(got, whole) < 1e-4                                 # only the fp32 summation order differs
