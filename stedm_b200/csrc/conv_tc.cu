@@ -58,6 +58,12 @@ static bool g_tc_pair_enabled = [] {
   return !(e && e[0] == '0');
 }();
 
+// STEDM_TC_HALO=0 loads one activation slab per filter tap instead of one halo box per (channel block, horizontal tap)
+static bool g_tc_halo_enabled = [] {
+  const char* e = getenv("STEDM_TC_HALO");
+  return !(e && e[0] == '0');
+}();
+
 struct TcParams {
   const float* bias;
   const float* emb;
@@ -81,6 +87,14 @@ struct TcParams {
   // the output pixel itself from a second input [skip0 | skip1]; its weights are appended along K
   int skip_c0_blks, skip_blks, skip_x1_batch;
   int res_rows;          // > 0: the residual has fewer samples than the output and is broadcast: row = m % res_rows
+  // halo mode (k x k taps over tiles made of whole image rows of one sample): ONE TMA load of the tile's rows plus the
+  // n_t - 1 halo rows per (64-channel block, horizontal tap) serves the n_t vertical taps of that column — the MMA's A
+  // descriptor start advances by one image row (W * 128 B, a whole number of swizzle atoms) per vertical tap
+  int halo;              // 0: one A slab per tap
+  int n_t;               // taps per dimension in halo mode: 3, or 2 for the sub-pixel phases
+  int na;                // A ring buffers (a_buf_bytes each, carved out of the STAGES * 16 KB pool)
+  int a_buf_bytes;       // 16 KB, or the halo box (th + n_t - 1) * W * 128 B
+  int a_row_bytes;       // W * 128
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -89,14 +103,17 @@ struct TcParams {
 // only its HALF of the weight slab and the tensor core reads both halves, so the bytes that must enter an SM per
 // MMA drop from A + B to A + B/2 (the measured limiter of cta_group::1 at BN = 256: ~75 B/clk/SM of SM ingest
 // against 96 B/clk/SM needed -> tensor pipe 79 % active).
+constexpr int tc_stages(int bn, bool pair) { return pair ? (bn >= 256 ? 6 : 4) : (bn >= 256 ? 4 : (bn >= 128 ? 3 : 4)); }
+
 template <int BN, bool PAIR = false>
 struct TcCfg {
-  static constexpr int STAGES = PAIR ? (BN >= 256 ? 6 : 4) : ((BN >= 256) ? 4 : (BN >= 128 ? 3 : 4));
+  static constexpr int STAGES = tc_stages(BN, PAIR);
   static constexpr int ACC = 2;  // TMEM accumulator stages
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;  // bytes of the weight slab staged in THIS CTA
   static constexpr int B_BYTES_PAD = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES_PAD;
+  static constexpr int A_POOL = STAGES * A_BYTES;  // A ring: STAGES slabs of 16 KB, or fewer and larger halo boxes
   static constexpr int ACC_COLS = BN;  // fp32 columns per accumulator
   static constexpr int TMEM_COLS = (ACC * BN) < 32 ? 32 : ACC * BN;  // 32 / 128 / 256 / 512: powers of two
   static constexpr int STATS_BYTES = 4 * BN * 2 * 4;  // [4 epilogue warps][BN][sum, sumsq] fp32
@@ -115,9 +132,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;   // [ACC]
+  // two rings: activation buffers (A) and weight slabs (B), each with full / empty mbarriers
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_a = full_a + Cfg::STAGES;
+  uint64_t* full_b = empty_a + Cfg::STAGES;
+  uint64_t* empty_b = full_b + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_b + Cfg::STAGES;     // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
   float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
@@ -128,6 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const int main_kb = p.taps * p.c_blks;
   const int num_kb = main_kb + p.skip_blks;
+  const int halo_items = p.halo ? p.c_blks * p.n_t : 0;  // (64-channel block, horizontal tap) items served by halo loads
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_a0);
@@ -138,9 +159,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tma_prefetch_desc(&map_s1);
     }
     for (int i = 0; i < Cfg::STAGES; ++i) {
-      // PAIR: the leader's full barrier collects both CTAs' producers; its single commit frees the slab in both
-      mbar_init(&full_bar[i], PAIR ? 2 : 1);
-      mbar_init(&empty_bar[i], PAIR ? 1 : CL);  // multicast: released by the MMA commit of every CTA writing into it
+      // PAIR: the leader's full barriers collect both CTAs' producers; its single commit frees the slab in both
+      mbar_init(&full_a[i], PAIR ? 2 : 1);
+      mbar_init(&full_b[i], PAIR ? 2 : 1);
+      mbar_init(&empty_a[i], 1);                // activations are never multicast
+      mbar_init(&empty_b[i], PAIR ? 1 : CL);    // multicast: released by the MMA commit of every CTA writing into it
     }
     for (int i = 0; i < Cfg::ACC; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -165,7 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
-      uint32_t it = 0;  // K-slab counter, runs across tiles
+      uint32_t ia = 0, pa = 0, ib = 0, pb = 0;  // slot / phase of the A and B rings, running across tiles
+      const int dyf = p.tap_mode == 1 ? p.py - 1 : -1, dxf = p.tap_mode == 1 ? p.px - 1 : -1;  // first tap offsets
       for (int work = cluster_id; work < p.num_work; work += num_clusters) {
         const int tile_id = work / p.ksplit, split = work - tile_id * p.ksplit;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
@@ -173,49 +197,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
         const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
         const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          const uint32_t ph = (it / Cfg::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if constexpr (PAIR) mbar_arrive_expect_tx_cluster(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES, 0);
-          else mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-          // which activation slab: tap (r, s) x 64-channel block of [x0 | x1], or a block of the fused skip input
+        // work items: halo mode = (channel block, horizontal tap) with n_t weight slabs each, then the fused-skip
+        // slabs; otherwise one item per K slab of [kb0, kb1)
+        const int n_items = p.halo ? halo_items + p.skip_blks : kb1 - kb0;
+        for (int i = 0; i < n_items; ++i) {
           const CUtensorMap* amap;
-          int ach, ab, dy = 0, dx = 0;
-          if (kb < main_kb) {
-            const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
-            if (p.tap_mode == 1) {      // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
-              dy = (tap >> 1) - 1 + p.py;
-              dx = (tap & 1) - 1 + p.px;
-            } else if (p.ksize == 3) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
-            }
+          int ach, ab, cx = x0, cy = y0, groups = 1, kb, kb_step = 0;
+          uint32_t a_bytes = Cfg::A_BYTES;
+          if (i < halo_items) {
+            // taps (a, bx): dy = dyf + a, dx = dxf + bx, weight K slab (a * n_t + bx) * c_blks + cb
+            const int cb = i / p.n_t, bx = i - cb * p.n_t;
             const bool first = cb < p.c0_blks;
             amap = first ? &map_a0 : &map_a1;
             ach = (first ? cb : cb - p.c0_blks) * TC_BK;
             ab = first ? b0 : b1;
+            cx = x0 + dxf + bx;
+            cy = y0 + dyf;
+            groups = p.n_t;
+            kb = bx * p.c_blks + cb;
+            kb_step = p.n_t * p.c_blks;
+            a_bytes = static_cast<uint32_t>(p.a_buf_bytes);
           } else {
-            const int sb = kb - main_kb;
-            const bool first = sb < p.skip_c0_blks;
-            amap = first ? &map_s0 : &map_s1;
-            ach = (first ? sb : sb - p.skip_c0_blks) * TC_BK;
-            ab = (first || p.skip_x1_batch <= 0) ? b0 : (b0 % p.skip_x1_batch);
+            kb = p.halo ? main_kb + (i - halo_items) : kb0 + i;
+            // which activation slab: tap (r, s) x 64-channel block of [x0 | x1], or a block of the fused skip input
+            if (kb < main_kb) {
+              const int tap = kb / p.c_blks, cb = kb - tap * p.c_blks;
+              if (p.tap_mode == 1) {    // taps (a, b) in {0,1}^2 read source pixel (y + a - 1 + py, x + b - 1 + px)
+                cy += (tap >> 1) + dyf;
+                cx += (tap & 1) + dxf;
+              } else if (p.ksize == 3) {
+                cy += tap / 3 - 1;
+                cx += tap % 3 - 1;
+              }
+              const bool first = cb < p.c0_blks;
+              amap = first ? &map_a0 : &map_a1;
+              ach = (first ? cb : cb - p.c0_blks) * TC_BK;
+              ab = first ? b0 : b1;
+            } else {
+              const int sb = kb - main_kb;
+              const bool first = sb < p.skip_c0_blks;
+              amap = first ? &map_s0 : &map_s1;
+              ach = (first ? sb : sb - p.skip_c0_blks) * TC_BK;
+              ab = (first || p.skip_x1_batch <= 0) ? b0 : (b0 % p.skip_x1_batch);
+            }
           }
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          mbar_wait(&empty_a[ia], pa ^ 1);
+          uint8_t* sa = smem + ia * p.a_buf_bytes;
           if constexpr (PAIR) {
-            tma_load_4d_2sm(sa, amap, &full_bar[s], ach, x0 + dx, y0 + dy, ab);
-            // this CTA's half of the weight slab: rows [rank*BN/2, +BN/2)
-            tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
-            continue;
+            mbar_arrive_expect_tx_cluster(&full_a[ia], a_bytes, 0);
+            tma_load_4d_2sm(sa, amap, &full_a[ia], ach, cx, cy, ab);
+          } else {
+            mbar_arrive_expect_tx(&full_a[ia], a_bytes);
+            tma_load_4d(sa, amap, &full_a[ia], ach, cx, cy, ab);
           }
-          tma_load_4d(sa, amap, &full_bar[s], ach, x0 + dx, y0 + dy, ab);
-          if (CL == 1) {
-            tma_load_2d(sa + Cfg::A_BYTES, &map_w, &full_bar[s], kb * TC_BK, n0);
-          } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
-            constexpr int ROWS = BN / CL;
-            tma_load_2d_mcast(sa + Cfg::A_BYTES + cta_rank * (ROWS * TC_BK * 2), &map_w, &full_bar[s], kb * TC_BK,
-                              n0 + static_cast<int>(cta_rank) * ROWS, static_cast<uint16_t>((1u << CL) - 1));
+          if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
+          for (int g = 0; g < groups; ++g, kb += kb_step) {
+            mbar_wait(&empty_b[ib], pb ^ 1);
+            uint8_t* sb = smem + Cfg::A_POOL + ib * Cfg::B_BYTES_PAD;
+            if constexpr (PAIR) {
+              // this CTA's half of the weight slab: rows [rank*BN/2, +BN/2)
+              mbar_arrive_expect_tx_cluster(&full_b[ib], Cfg::B_BYTES, 0);
+              tma_load_2d_2sm(sb, &map_w, &full_b[ib], kb * TC_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            } else if (CL == 1) {
+              mbar_arrive_expect_tx(&full_b[ib], Cfg::B_BYTES);
+              tma_load_2d(sb, &map_w, &full_b[ib], kb * TC_BK, n0);
+            } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
+              constexpr int ROWS = BN / CL;
+              mbar_arrive_expect_tx(&full_b[ib], Cfg::B_BYTES);
+              tma_load_2d_mcast(sb + cta_rank * (ROWS * TC_BK * 2), &map_w, &full_b[ib], kb * TC_BK,
+                                n0 + static_cast<int>(cta_rank) * ROWS, static_cast<uint16_t>((1u << CL) - 1));
+            }
+            if (++ib == static_cast<uint32_t>(Cfg::STAGES)) { ib = 0; pb ^= 1; }
           }
         }
       }
@@ -224,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================================== MMA issuer =======================================
     if ((!PAIR || cta_rank == 0) && elect_one()) {  // PAIR: only the leader CTA issues (for both)
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
-      uint32_t it = 0, tile = 0;
+      uint32_t ia = 0, pa = 0, ib = 0, pb = 0, tile = 0;
       for (int work = cluster_id; work < p.num_work; work += num_clusters, ++tile) {
         const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
@@ -232,24 +284,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         const int split = work % p.ksplit;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          const uint32_t ph = (it / Cfg::STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        const int n_items = p.halo ? halo_items + p.skip_blks : kb1 - kb0;
+        uint32_t started = 0;
+        for (int i = 0; i < n_items; ++i) {
+          const int groups = i < halo_items ? p.n_t : 1;
+          mbar_wait(&full_a[ia], pa);
+          const uint32_t a_addr = smem_u32(smem + ia * p.a_buf_bytes);
+          for (int g = 0; g < groups; ++g) {
+            mbar_wait(&full_b[ib], pb);
+            tc_fence_after();
+            // vertical tap g of a halo box: the same buffer, g image rows further down
+            const uint64_t adesc = umma_desc_sw128(a_addr + g * p.a_row_bytes);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + Cfg::A_POOL + ib * Cfg::B_BYTES_PAD));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
-            const uint32_t accumulate = ((kb - kb0) | k) != 0 ? 1u : 0u;
-            if constexpr (PAIR) umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+            for (int k = 0; k < TC_BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
+              const uint32_t accumulate = (started | k) != 0 ? 1u : 0u;
+              if constexpr (PAIR) umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+            }
+            started = 1;
+            // frees the weight slab once these MMAs have read it — in every CTA that multicasts into it / of the pair
+            if constexpr (PAIR) umma_commit_2sm_mcast(&empty_b[ib], 3);
+            else if (CL == 1) umma_commit(&empty_b[ib]);
+            else umma_commit_mcast(&empty_b[ib], static_cast<uint16_t>((1u << CL) - 1));
+            if (++ib == static_cast<uint32_t>(Cfg::STAGES)) { ib = 0; pb ^= 1; }
           }
-          // frees the slab once these MMAs have read it — in every CTA that multicasts into it / of the pair
-          if constexpr (PAIR) umma_commit_2sm_mcast(&empty_bar[s], 3);
-          else if (CL == 1) umma_commit(&empty_bar[s]);
-          else umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << CL) - 1));
+          // ... and the activation buffer after its last tap (in both CTAs of a pair)
+          if constexpr (PAIR) umma_commit_2sm_mcast(&empty_a[ia], 3);
+          else umma_commit(&empty_a[ia]);
+          if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs in PAIR mode)
         if constexpr (PAIR) umma_commit_2sm_mcast(&tmem_full_bar[acc], 3);
@@ -581,6 +644,15 @@ int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap&
     }
     configured = true;
   }
+  if (!p.halo) {
+    p.a_buf_bytes = Cfg::A_BYTES;
+    p.na = Cfg::STAGES;
+    p.a_row_bytes = 0;
+    p.n_t = 1;
+  } else if (p.na > Cfg::STAGES || p.na * p.a_buf_bytes > Cfg::A_POOL) {
+    set_error("conv_tc: halo ring (%d x %d B) does not fit the %d B pool", p.na, p.a_buf_bytes, Cfg::A_POOL);
+    return ERR_ARG;
+  }
   const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
   const int m_groups = (m_tiles + CL - 1) / CL;  // an odd tile count gets one all-out-of-bounds tile (zero-filled loads, no stores)
   p.num_work = m_groups * p.n_tiles * p.ksplit;
@@ -705,6 +777,31 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   const long long M = static_cast<long long>(B) * H * W;
   STEDM_REQUIRE(M < (1LL << 31), "conv_tc: too many pixels");
 
+  const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
+  // channel tile, 2-CTA cluster (cta_group::2 pair or weight multicast) and split-K plan
+  const int c_blks = (ctot + TC_BK - 1) / TC_BK;
+  // fused 1x1 skip convolution: a second input [skip_x0 | skip_x1] of the output's spatial size, extra K slabs
+  const int skip_c = d->skip_x0 ? d->skip_c0 + d->skip_c1 : 0;
+  const int skip_blks = skip_c / TC_BK;
+  TcPlan plan = tc_plan(M, d->cout, taps * c_blks + skip_blks, d->stats_out != nullptr);
+  if (plan.ksplit > 1 && (d->workspace == nullptr || static_cast<size_t>(d->workspace_bytes) < plan.ws_bytes)) {
+    plan.ksplit = 1;                        // no (or too small a) workspace: single pass
+    plan.kb_per_split = taps * c_blks + skip_blks;
+  }
+  // halo mode: tiles of th >= 2 whole image rows of one sample; the activation box grows by the n_t - 1 halo rows and
+  // is loaded once per (channel block, horizontal tap).  The ring holds as many boxes as fit the STAGES * 16 KB pool.
+  const int n_t = d->tap_mode == 1 ? 2 : 3;
+  int halo = 0, halo_na = 0, halo_bytes = 0;
+  if (g_tc_halo_enabled && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
+      plan.ksplit == 1) {
+    halo_bytes = (th + n_t - 1) * W * TC_BK * 2;
+    const int stages = tc_stages(plan.bn, plan.pair);
+    halo_na = stages * TC_BM * TC_BK * 2 / halo_bytes;
+    if (halo_na > stages) halo_na = stages;
+    halo = halo_na >= 2 && halo_bytes % 1024 == 0;
+  }
+  const uint32_t abox_h = static_cast<uint32_t>(halo ? th + n_t - 1 : th);
+
   CUtensorMap ma0, ma1, mw;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->c0), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -713,7 +810,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
     const uint64_t ps0 = d->x0_pix_stride > 0 ? d->x0_pix_stride : d->c0;
     STEDM_REQUIRE(ps0 >= static_cast<uint64_t>(d->c0) && ps0 % 8 == 0, "conv_tc: bad x0 pixel stride %d", d->x0_pix_stride);
     const uint64_t str[3] = {ps0 * 2, static_cast<uint64_t>(W) * ps0 * 2, static_cast<uint64_t>(H) * W * ps0 * 2};
-    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), abox_h, static_cast<uint32_t>(tb)};
     int rc = make_tmap_bf16(&ma0, d->x0, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -723,18 +820,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
                               static_cast<uint64_t>(b1)};
     const uint64_t str[3] = {static_cast<uint64_t>(d->c1) * 2, static_cast<uint64_t>(W) * d->c1 * 2,
                              static_cast<uint64_t>(H) * W * d->c1 * 2};
-    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), abox_h, static_cast<uint32_t>(tb)};
     int rc = make_tmap_bf16(&ma1, d->x1, 4, dims, str, box);
     if (rc) return rc;
   } else {
     ma1 = ma0;
   }
-  const int ctot = d->c0 + d->c1, taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
-  // channel tile, 2-CTA cluster (cta_group::2 pair or weight multicast) and split-K plan
-  const int c_blks = (ctot + TC_BK - 1) / TC_BK;
-  // fused 1x1 skip convolution: a second input [skip_x0 | skip_x1] of the output's spatial size, extra K slabs
-  const int skip_c = d->skip_x0 ? d->skip_c0 + d->skip_c1 : 0;
-  const int skip_blks = skip_c / TC_BK;
   if (d->skip_x0) {
     STEDM_REQUIRE(d->tap_mode == 0 && ctot % TC_BK == 0 && d->skip_c0 > 0 && d->skip_c0 % TC_BK == 0 &&
                       d->skip_c1 % TC_BK == 0 && (d->skip_c1 == 0 || d->skip_x1),
@@ -767,11 +858,6 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
       if (rc) return rc;
     }
   }
-  TcPlan plan = tc_plan(M, d->cout, taps * c_blks + skip_blks, d->stats_out != nullptr);
-  if (plan.ksplit > 1 && (d->workspace == nullptr || static_cast<size_t>(d->workspace_bytes) < plan.ws_bytes)) {
-    plan.ksplit = 1;                        // no (or too small a) workspace: single pass
-    plan.kb_per_split = taps * c_blks + skip_blks;
-  }
   const int bn = plan.bn, cl = plan.cl;
   const bool pair = plan.pair;
   {
@@ -798,6 +884,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
   p.act = d->act;
   p.skip_blks = skip_blks; p.skip_c0_blks = skip_c > 0 ? d->skip_c0 / TC_BK : 0; p.skip_x1_batch = skip_x1b;
+  p.halo = halo; p.n_t = n_t; p.na = halo_na; p.a_buf_bytes = halo_bytes; p.a_row_bytes = W * TC_BK * 2;
   p.res_rows = 0;
   if (d->residual != nullptr && d->res_batch > 0 && d->res_batch != B) {
     STEDM_REQUIRE(d->tap_mode == 0 && B % d->res_batch == 0, "conv_tc: residual batch %d does not divide the batch %d",

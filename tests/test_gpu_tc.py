@@ -47,6 +47,13 @@ CASES = [
     (2, 32, 32, 192, 512, 1),     # 1x1, K not a power of two
     (1, 16, 16, 1024, 1024, 3),   # deep K (144 slabs), 4 n-tiles
     (5, 4, 4, 64, 48, 3),         # eight samples per tile, cout = 3 x 16
+    # halo mode (tiles of >= 2 whole rows of one sample: one activation box per (channel block, horizontal tap))
+    (2, 32, 32, 128, 512, 3),     # 32x4 tiles + 2 halo rows, BN=256 CTA pairs
+    (1, 24, 16, 64, 128, 3),      # 16x8 tiles, three tiles: the pair's odd tile is all out of bounds
+    (3, 16, 16, 64, 16, 3),       # BN=16, two halo boxes in the ring
+    (1, 16, 32, 192, 64, 3),      # non-square map, three channel blocks, BN=64
+    (1, 8, 16, 64, 64, 3),        # H < tile rows + halo: falls back to one slab per tap
+    (2, 64, 64, 128, 128, 3),     # 64x2 tiles + 2 halo rows (32 KB boxes, two per ring), BN=128 CTA pairs
 ]
 
 
