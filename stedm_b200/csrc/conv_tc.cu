@@ -241,31 +241,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               ab = (first || p.skip_x1_batch <= 0) ? b0 : (b0 % p.skip_x1_batch);
             }
           }
-          mbar_wait(&empty_a[ia], pa ^ 1);
-          uint8_t* sa = smem + ia * p.a_buf_bytes;
-          if constexpr (PAIR) {
-            mbar_arrive_expect_tx_cluster(&full_a[ia], a_bytes, 0);
-            tma_load_4d_2sm(sa, amap, &full_a[ia], ach, cx, cy, ab);
-          } else {
-            mbar_arrive_expect_tx(&full_a[ia], a_bytes);
-            tma_load_4d(sa, amap, &full_a[ia], ach, cx, cy, ab);
+          // Halo mode: the activation box has its own ring slot and barriers (it outlives several weight slabs).
+          // Otherwise the two rings run in lock step (one 16 KB slab each per item), so the activation slab shares
+          // the weight slab's slot index and barriers — one wait and one commit per K slab in the MMA thread.
+          if (p.halo) {
+            mbar_wait(&empty_a[ia], pa ^ 1);
+            uint8_t* sa = smem + ia * p.a_buf_bytes;
+            if constexpr (PAIR) {
+              mbar_arrive_expect_tx_cluster(&full_a[ia], a_bytes, 0);
+              tma_load_4d_2sm(sa, amap, &full_a[ia], ach, cx, cy, ab);
+            } else {
+              mbar_arrive_expect_tx(&full_a[ia], a_bytes);
+              tma_load_4d(sa, amap, &full_a[ia], ach, cx, cy, ab);
+            }
+            if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
           }
-          if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
+          const uint32_t b_tx = p.halo ? Cfg::B_BYTES : Cfg::A_BYTES + Cfg::B_BYTES;
           for (int g = 0; g < groups; ++g, kb += kb_step) {
             mbar_wait(&empty_b[ib], pb ^ 1);
             uint8_t* sb = smem + Cfg::A_POOL + ib * Cfg::B_BYTES_PAD;
             if constexpr (PAIR) {
               // this CTA's half of the weight slab: rows [rank*BN/2, +BN/2)
-              mbar_arrive_expect_tx_cluster(&full_b[ib], Cfg::B_BYTES, 0);
+              mbar_arrive_expect_tx_cluster(&full_b[ib], b_tx, 0);
+              if (!p.halo) tma_load_4d_2sm(smem + ib * Cfg::A_BYTES, amap, &full_b[ib], ach, cx, cy, ab);
               tma_load_2d_2sm(sb, &map_w, &full_b[ib], kb * TC_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
-            } else if (CL == 1) {
-              mbar_arrive_expect_tx(&full_b[ib], Cfg::B_BYTES);
-              tma_load_2d(sb, &map_w, &full_b[ib], kb * TC_BK, n0);
-            } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
-              constexpr int ROWS = BN / CL;
-              mbar_arrive_expect_tx(&full_b[ib], Cfg::B_BYTES);
-              tma_load_2d_mcast(sb + cta_rank * (ROWS * TC_BK * 2), &map_w, &full_b[ib], kb * TC_BK,
-                                n0 + static_cast<int>(cta_rank) * ROWS, static_cast<uint16_t>((1u << CL) - 1));
+            } else {
+              mbar_arrive_expect_tx(&full_b[ib], b_tx);
+              if (!p.halo) tma_load_4d(smem + ib * Cfg::A_BYTES, amap, &full_b[ib], ach, cx, cy, ab);
+              if (CL == 1) {
+                tma_load_2d(sb, &map_w, &full_b[ib], kb * TC_BK, n0);
+              } else {  // this CTA fetches rows [rank*BN/CL, +BN/CL) of the weight slab for the whole cluster
+                constexpr int ROWS = BN / CL;
+                tma_load_2d_mcast(sb + cta_rank * (ROWS * TC_BK * 2), &map_w, &full_b[ib], kb * TC_BK,
+                                  n0 + static_cast<int>(cta_rank) * ROWS, static_cast<uint16_t>((1u << CL) - 1));
+              }
             }
             if (++ib == static_cast<uint32_t>(Cfg::STAGES)) { ib = 0; pb ^= 1; }
           }
@@ -288,13 +297,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         uint32_t started = 0;
         for (int i = 0; i < n_items; ++i) {
           const int groups = i < halo_items ? p.n_t : 1;
-          mbar_wait(&full_a[ia], pa);
-          const uint32_t a_addr = smem_u32(smem + ia * p.a_buf_bytes);
+          uint32_t a_addr = 0;
+          if (p.halo) {
+            mbar_wait(&full_a[ia], pa);
+            a_addr = smem_u32(smem + ia * p.a_buf_bytes);
+          }
           for (int g = 0; g < groups; ++g) {
             mbar_wait(&full_b[ib], pb);
             tc_fence_after();
-            // vertical tap g of a halo box: the same buffer, g image rows further down
-            const uint64_t adesc = umma_desc_sw128(a_addr + g * p.a_row_bytes);
+            // halo: vertical tap g reads the same box g image rows further down; otherwise the slab of this slot
+            const uint64_t adesc = umma_desc_sw128(p.halo ? a_addr + g * p.a_row_bytes : smem_u32(smem + ib * Cfg::A_BYTES));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + Cfg::A_POOL + ib * Cfg::B_BYTES_PAD));
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 B -> start address field += 2
@@ -303,16 +315,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
             }
             started = 1;
-            // frees the weight slab once these MMAs have read it — in every CTA that multicasts into it / of the pair
+            // frees the slot once these MMAs have read it — in every CTA that multicasts into it / of the pair
             if constexpr (PAIR) umma_commit_2sm_mcast(&empty_b[ib], 3);
             else if (CL == 1) umma_commit(&empty_b[ib]);
             else umma_commit_mcast(&empty_b[ib], static_cast<uint16_t>((1u << CL) - 1));
             if (++ib == static_cast<uint32_t>(Cfg::STAGES)) { ib = 0; pb ^= 1; }
           }
-          // ... and the activation buffer after its last tap (in both CTAs of a pair)
-          if constexpr (PAIR) umma_commit_2sm_mcast(&empty_a[ia], 3);
-          else umma_commit(&empty_a[ia]);
-          if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
+          if (p.halo) {  // ... and the activation box after its last tap (in both CTAs of a pair)
+            if constexpr (PAIR) umma_commit_2sm_mcast(&empty_a[ia], 3);
+            else umma_commit(&empty_a[ia]);
+            if (++ia == static_cast<uint32_t>(p.na)) { ia = 0; pa ^= 1; }
+          }
         }
         // accumulator complete -> epilogue (of both CTAs in PAIR mode)
         if constexpr (PAIR) umma_commit_2sm_mcast(&tmem_full_bar[acc], 3);
