@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstedm_b200.so")
+# STEDM_B200_LIB: another build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("STEDM_B200_LIB") or os.path.join(_HERE, "libstedm_b200.so")
 
 F32, BF16 = 0, 1
 

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--what", default="unet", help="unet (one guided DDIM step) | decode (one VQ decode)")
+    ap.add_argument("--reps", type=int, default=20)
     a = ap.parse_args()
     from stedm_b200 import ops
     from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
@@ -53,13 +54,16 @@ def main():
             return out
 
         ops.conv = timed
+        clocks = bench.ClockSampler(0)
+        clocks.start()
         try:
-            reps = 5
+            reps = a.reps
             for _ in range(reps):
                 step()
             torch.cuda.synchronize()
         finally:
             ops.conv = orig
+        clk = clocks.stop()
     n = len(rec) // reps
     print(f"{'#':>3s} {'B':>4s} {'HxW':>9s} {'Cin':>10s} {'Cout':>5s} {'taps':>4s} res stats {'ms':>8s} {'TFLOP/s':>8s} {'GFLOP':>8s}")
     tot_ms = tot_fl = 0.0
@@ -71,7 +75,7 @@ def main():
         tot_fl += fl
         cin = (f"{c0}+{c1}" if c1 else f"{c0}") + (f"|s{skc}" if skc else "")
         print(f"{i:3d} {b:4d} {h:4d}x{w:<4d} {cin:>10s} {cout:5d} {taps:4d} {int(res):3d} {int(st):5d} {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.1f}")
-    print(f"total {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s over {n} launches")
+    print(f"total {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s over {n} launches; clocks {clk}")
 
 
 if __name__ == "__main__":
