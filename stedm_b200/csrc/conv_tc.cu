@@ -20,6 +20,12 @@
 // with a single accumulator the tensor pipe idled ~30 % of the time behind the epilogue's global loads/stores.
 // CL = 2: the two CTAs of a cluster take neighbouring pixel tiles of the same channel tile and TMA-multicast one
 // half of the weight slab each into both CTAs (per-SM L2->SM traffic A+B/2 instead of A+B per slab).
+// HALO mode (k x k taps, tiles of >= 2 whole image rows of one sample): the activation box of the tile's rows plus the
+// n_t - 1 halo rows is loaded ONCE per (64-channel block, horizontal tap) and serves the n_t vertical taps — the A
+// descriptor's start address advances by one image row (W * 128 B = whole swizzle atoms) per vertical tap — so an
+// activation byte crosses L2->SM 3 (th + 2) / th times instead of 9.  Boxes and weight slabs then live in two rings
+// with their own barriers (a box outlives n_t weight slabs); otherwise both rings run in lock step on one barrier pair.
+// The producer is ONE thread and its instruction count per slab was the measured limiter: no divisions in its slab loop.
 // K loop extras: the 1x1 skip_connection of a channel-changing ResBlock (openaimodel.py:246-256, 288) is folded in as
 // extra K slabs read from the block input through two more tensor maps, so conv3x3(a) + skip1x1(x) is one accumulator.
 // Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287), optional exact-erf GELU,
