@@ -39,7 +39,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, int swizzle_bytes) {
+                   const uint32_t* box) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled is unavailable (driver too old or no CUDA device)");
@@ -68,8 +68,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     }
   }
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,

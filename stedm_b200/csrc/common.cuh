@@ -184,18 +184,6 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem, const CUtensorMap*
       : "memory");
 }
 
-// ---- PTX: TMA tile store (shared -> global) through the bulk async-group mechanism ------------------------
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all of this thread's committed bulk stores have finished READING shared memory (the staging rows may be rewritten)
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// ... have completed entirely
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // ---- PTX: CTA-pair (cta_group::2) variants ------------------------------------------------------------
 // In a 2-CTA cluster the shared::cluster address of the peer differs from the local one in one bit; clearing it
 // addresses the same offset in CTA 0 (the MMA leader), which owns the "full" barriers of the pair.
@@ -396,8 +384,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
-// swizzle_bytes: 128 (operand tiles) or 64 (the conv epilogue's 64-byte output rows).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, int swizzle_bytes = 128);
+                   const uint32_t* box);
 
 }  // namespace stedm

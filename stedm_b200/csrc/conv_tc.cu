@@ -70,12 +70,6 @@ static bool g_tc_halo_enabled = [] {
   return !(e && e[0] == '0');
 }();
 
-// STEDM_TC_TMA_STORE=0 writes bf16 NHWC outputs with per-lane 16-byte stores instead of TMA tile stores
-static bool g_tc_tma_store_enabled = [] {
-  const char* e = getenv("STEDM_TC_TMA_STORE");
-  return !(e && e[0] == '0');
-}();
-
 struct TcParams {
   const float* bias;
   const float* emb;
@@ -107,7 +101,6 @@ struct TcParams {
   int na;                // A ring buffers (a_buf_bytes each, carved out of the STAGES * 16 KB pool)
   int a_buf_bytes;       // 16 KB, or the halo box (th + n_t - 1) * W * 128 B
   int a_row_bytes;       // W * 128
-  int tma_out;           // bf16 NHWC output: each epilogue warp's staged 32 rows x 64 B leave through one TMA tile store
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -140,8 +133,7 @@ template <int BN, int CL, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, PAIR>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_s0,
-               const __grid_constant__ CUtensorMap map_s1, const __grid_constant__ CUtensorMap map_o,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap map_s1, const TcParams p) {
   static_assert(!PAIR || CL == 2, "cta_group::2 needs a 2-CTA cluster");
   using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -151,16 +143,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto slab_a = [](uint8_t* base, uint32_t s) { return base + s * Cfg::A_BYTES; };
   auto slab_b = [](uint8_t* base, uint32_t s, int) { return base + Cfg::A_POOL + s * Cfg::B_BYTES_PAD; };
   // two rings: activation buffers (A) and weight slabs (B), each with full / empty mbarriers
-  // [operands | output staging (1024-aligned: its XOR pattern is TMA's SWIZZLE_64B) | barriers | statistics]
-  uint8_t* s_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(s_out + Cfg::OUT_STAGE_BYTES);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_a = full_a + Cfg::STAGES;
   uint64_t* full_b = empty_a + Cfg::STAGES;
   uint64_t* empty_b = full_b + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_b + Cfg::STAGES;     // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
-  float* s_stats = reinterpret_cast<float*>(s_out + Cfg::OUT_STAGE_BYTES + 256);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  uint8_t* s_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::STATS_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -173,7 +164,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_w);
-    if (p.tma_out) tma_prefetch_desc(&map_o);
     if (p.skip_blks > 0) {
       tma_prefetch_desc(&map_s0);
       tma_prefetch_desc(&map_s1);
@@ -534,25 +524,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // contiguous bytes (2 whole sectors).  16-byte slots are XOR-swizzled: 4 wavefronts per access, the minimum.
           const int jj = lane & 3;
           if (p.out_dtype == DT_BF16) {
-            if (p.tma_out) {  // the previous chunk's tile store must have finished reading the staging rows
-              if (lane == 0) tma_store_wait_read();
-              __syncwarp();
-            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
                   make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            if (p.tma_out) {
-              // the staged image IS the SWIZZLE_64B box {32 channels, 32 rows}: one TMA tile store per warp and chunk
-              // (rows >= M are clipped by the tensor map) instead of 4 LDS + 4 predicated STG per lane
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&map_o, stg, n, m - lane);
-                tma_store_commit();
-              }
-            } else {
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -562,7 +538,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     *reinterpret_cast<const uint4*>(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
             }
             __syncwarp();
-            }
           } else {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {  // 16 fp32 channels = 64 B per pass
@@ -641,7 +616,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-    if (p.tma_out && lane == 0) tma_store_wait_all();  // this warp's tile stores are complete before the CTA retires
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA may exit while a peer can still write into it
@@ -714,7 +688,7 @@ int tc_num_sms() {
 
 template <int BN, int CL, bool PAIR, bool HALO>
 int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
-                   const CUtensorMap& ms1, const CUtensorMap& mo, TcParams p, cudaStream_t stream) {
+              const CUtensorMap& ms1, TcParams p, cudaStream_t stream) {
   using Cfg = TcCfg<BN, PAIR>;
   static bool configured = false;  // per-process; the attribute is per-function and idempotent
   if (!configured) {
@@ -750,7 +724,7 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO>, ma0, ma1, mw, ms0, ms1, mo, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO>, ma0, ma1, mw, ms0, ms1, p);
   if (e != cudaSuccess) {
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
@@ -766,9 +740,9 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
 
 template <int BN, int CL, bool PAIR = false>
 int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
-              const CUtensorMap& ms1, const CUtensorMap& mo, const TcParams& p, cudaStream_t stream) {
-  return p.halo ? launch_tc_impl<BN, CL, PAIR, true>(ma0, ma1, mw, ms0, ms1, mo, p, stream)
-                : launch_tc_impl<BN, CL, PAIR, false>(ma0, ma1, mw, ms0, ms1, mo, p, stream);
+              const CUtensorMap& ms1, const TcParams& p, cudaStream_t stream) {
+  return p.halo ? launch_tc_impl<BN, CL, PAIR, true>(ma0, ma1, mw, ms0, ms1, p, stream)
+                : launch_tc_impl<BN, CL, PAIR, false>(ma0, ma1, mw, ms0, ms1, p, stream);
 }
 
 // Tile / cluster / split-K plan of one launch: shared by stedm_conv_tc and stedm_conv_tc_workspace_bytes.
@@ -980,18 +954,6 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
                   d->res_batch, B);
     p.res_rows = d->res_batch * H * W;
   }
-  // bf16 NHWC rows of whole 32-channel chunks leave through TMA tile stores of the epilogue's staged 32 x 64 B image
-  CUtensorMap mo = ma0;
-  p.tma_out = 0;
-  if (g_tc_tma_store_enabled && bn >= 32 && d->out_dtype == DT_BF16 && !d->out_nchw && d->tap_mode == 0 &&
-      plan.ksplit == 1 && d->cout % 32 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) {
-    const uint64_t dims[2] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(M)};
-    const uint64_t str[1] = {static_cast<uint64_t>(d->cout) * 2};
-    const uint32_t box[2] = {32, 32};
-    int rc = make_tmap_bf16(&mo, d->out, 2, dims, str, box, 64);
-    if (rc) return rc;
-    p.tma_out = 1;
-  }
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {
     STEDM_REQUIRE(bn >= 64 && d->cout % bn == 0 && d->out_nchw == 0 && (H * W) % TC_BM == 0,
@@ -1003,12 +965,12 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   auto s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256:
-      if (pair) return launch_tc<256, 2, true>(ma0, ma1, mw, ms0, ms1, mo, p, s);
-      return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, ms0, ms1, mo, p, s) : launch_tc<256, 1>(ma0, ma1, mw, ms0, ms1, mo, p, s);
+      if (pair) return launch_tc<256, 2, true>(ma0, ma1, mw, ms0, ms1, p, s);
+      return cl == 2 ? launch_tc<256, 2>(ma0, ma1, mw, ms0, ms1, p, s) : launch_tc<256, 1>(ma0, ma1, mw, ms0, ms1, p, s);
     case 128:
-      if (pair) return launch_tc<128, 2, true>(ma0, ma1, mw, ms0, ms1, mo, p, s);
-      return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, ms0, ms1, mo, p, s) : launch_tc<128, 1>(ma0, ma1, mw, ms0, ms1, mo, p, s);
-    case 64: return launch_tc<64, 1>(ma0, ma1, mw, ms0, ms1, mo, p, s);
-    default: return launch_tc<16, 1>(ma0, ma1, mw, ms0, ms1, mo, p, s);
+      if (pair) return launch_tc<128, 2, true>(ma0, ma1, mw, ms0, ms1, p, s);
+      return cl == 2 ? launch_tc<128, 2>(ma0, ma1, mw, ms0, ms1, p, s) : launch_tc<128, 1>(ma0, ma1, mw, ms0, ms1, p, s);
+    case 64: return launch_tc<64, 1>(ma0, ma1, mw, ms0, ms1, p, s);
+    default: return launch_tc<16, 1>(ma0, ma1, mw, ms0, ms1, p, s);
   }
 }
