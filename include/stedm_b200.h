@@ -147,6 +147,13 @@ int stedm_conv_tc(const stedm_conv_desc* d, void* stream);
 /* Bytes of `workspace` stedm_conv_tc would use for this descriptor (0 when it runs in a single pass; always 0 when
  * stats_out is set: the fused statistics need the single-pass epilogue). */
 long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d);
+/* The launch plan stedm_conv_tc would choose for this descriptor, computed on the host without touching the device
+ * (no pointer of the descriptor is dereferenced; non-NULL-ness of x1 / skip_x0 / stats_out / workspace is what selects
+ * the variants), so the tile-geometry checks and the mode selection are testable on a CPU-only machine:
+ * plan8[0] = output-channel tile BN, [1] = cluster size, [2] = 1 for the cta_group::2 CTA pair, [3] = 1 for halo mode
+ * (one activation box per (channel block, horizontal tap)), [4] = activation ring slots, [5] = bytes per slot,
+ * [6] = split-K factor, [7] = K slabs per output tile.  Returns the same error codes as stedm_conv_tc. */
+int stedm_conv_tc_plan(const stedm_conv_desc* d, int32_t* plan8);
 /* General fp32-accumulate SIMT implicit GEMM: the fp32 parity mode and every shape the tensor-core path rejects. */
 int stedm_conv_simt(const stedm_conv_desc* d, void* stream);
 

@@ -794,8 +794,19 @@ extern "C" long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d) {
   return static_cast<long long>(tc_plan(M, d->cout, num_kb, d->stats_out != nullptr).ws_bytes);
 }
 
-extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
-  STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_tc: null pointer");
+namespace {
+
+// Everything stedm_conv_tc decides before it touches the device: argument checks, tile geometry, channel tile /
+// cluster / split-K plan and the halo-mode choice (also exported as stedm_conv_tc_plan for CPU-side tests).
+struct TcLaunch {
+  int tw, th, tb, x1b;
+  long long M;
+  int ctot, taps, c_blks, skip_c, skip_blks, n_t, halo, halo_na, halo_bytes;
+  TcPlan plan;
+};
+
+int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
+  STEDM_REQUIRE(d != nullptr, "conv_tc: null descriptor");
   STEDM_REQUIRE(d->in_dtype == DT_BF16, "conv_tc: operands must be bf16");
   STEDM_REQUIRE(d->stride == 1 && d->upsample == 0,
                 "conv_tc: stride / upsample are handled by im2col_3x3_s2 / upsample_nearest2x");
@@ -863,6 +874,39 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
     if (halo_na > stages) halo_na = stages;
     halo = halo_na >= 2 && halo_bytes % 1024 == 0;
   }
+  L->tw = tw; L->th = th; L->tb = tb; L->x1b = x1b; L->M = M;
+  L->ctot = ctot; L->taps = taps; L->c_blks = c_blks; L->skip_c = skip_c; L->skip_blks = skip_blks;
+  L->n_t = n_t; L->halo = halo; L->halo_na = halo_na; L->halo_bytes = halo_bytes; L->plan = plan;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int stedm_conv_tc_plan(const stedm_conv_desc* d, int32_t* out8) {
+  STEDM_REQUIRE(out8 != nullptr, "conv_tc_plan: null output");
+  TcLaunch L;
+  const int rc = tc_prepare(d, &L);
+  if (rc) return rc;
+  const int stages = tc_stages(L.plan.bn, L.plan.pair);
+  out8[0] = L.plan.bn; out8[1] = L.plan.cl; out8[2] = L.plan.pair ? 1 : 0; out8[3] = L.halo;
+  out8[4] = L.halo ? L.halo_na : stages; out8[5] = L.halo ? L.halo_bytes : TC_BM * TC_BK * 2;
+  out8[6] = L.plan.ksplit; out8[7] = L.taps * L.c_blks + L.skip_blks;
+  return 0;
+}
+
+extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
+  STEDM_REQUIRE(d && d->x0 && d->weight && d->out, "conv_tc: null pointer");
+  TcLaunch L;
+  {
+    const int rc = tc_prepare(d, &L);
+    if (rc) return rc;
+  }
+  const int H = d->in_h, W = d->in_w, B = d->batch;
+  const int tw = L.tw, th = L.th, tb = L.tb, x1b = L.x1b;
+  const long long M = L.M;
+  const int ctot = L.ctot, taps = L.taps, c_blks = L.c_blks, skip_c = L.skip_c, skip_blks = L.skip_blks;
+  const TcPlan plan = L.plan;
+  const int n_t = L.n_t, halo = L.halo, halo_na = L.halo_na, halo_bytes = L.halo_bytes;
   const uint32_t abox_h = static_cast<uint32_t>(halo ? th + n_t - 1 : th);
 
   CUtensorMap ma0, ma1, mw;
