@@ -148,9 +148,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
         assert x0.stride(3) == 1 and ps >= cc and x0.stride(1) == ww * ps and x0.stride(0) == hh * ww * ps, x0.stride()
         assert tensor_core, "channel-slice inputs are a tensor-core path feature"
         x0_pix_stride = ps
-        _cuda(x1, weight, bias, residual, skip_x0, skip_x1)
-        if not x0.is_cuda:
-            raise RuntimeError("stedm_b200 ops take CUDA tensors only (no CPU fallback)")
+        _cuda(x1, weight, bias, residual, skip_x0, skip_x1)      # x0 itself: CUDA, strided as checked above
     else:
         _cuda(x0, x1, weight, bias, residual, skip_x0, skip_x1)
     if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
