@@ -3,7 +3,7 @@ on fixture weights, and assert that oracle/stedm_oracle.py reproduces every tens
 
 Run once in the build container (the reference cannot travel to the GPU box):
 
-    python -m oracle.make_golden [--only small|c1|sched|svit|plms|st|dpm]
+    python -m oracle.make_golden [--only small|c1|sched|svit|plms|st|dpm|ancestral]
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -275,6 +275,39 @@ def gen_dpm():
     print("[dpm] wrote dpm_solver.npz")
 
 
+@torch.no_grad()
+def gen_ancestral():
+    """DDPM ancestral sampler (kept API): the reference's LatentDiffusion.sample(cond, timesteps=5) on
+    fixture weights (ddpm.py:1050-1110, 1168-1235), plain and with quantize_denoised=True.  The per-step N(0,1) draws
+    are fixed: the reference's noise_like is replaced by a reader of pre-drawn tensors (seed 7), stored in the golden so
+    the GPU test can feed the very same noise.  Asserts oracle.ddpm_ancestral_sample == reference."""
+    model = ref_shims.build_reference_model(latent_size=32, style_sampling="mp", num_patches=2)
+    apply_fixture_weights(model, seed=0)
+    sd = canonical_sd(model)
+    import ldm.models.diffusion.ddpm as ref_ddpm
+    g = load_small_cond()
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["c_crossattn"])]}
+    _, _, x_T = O.synthetic_batch(2, 128, 2, 0)
+    T = 5
+    noises = torch.randn(T, 2, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    out = {"timesteps": T, "noises": noises.numpy()}
+    orig = ref_ddpm.noise_like
+    try:
+        for name, scale, quant in (("ancestral_t5", 1.0, False), ("ancestral_t5_quant", 40.0, True)):
+            it = iter(noises)
+            ref_ddpm.noise_like = lambda shape, device, repeat=False: next(it).clone()
+            want = model.sample(cond, batch_size=2, x_T=x_T * scale, timesteps=T, verbose=False, quantize_denoised=quant)
+            got = O.ddpm_ancestral_sample(sd, cond, x_T * scale, T, noises, quantize_denoised=quant)
+            d = maxdiff(want, got)
+            print(f"[{name}] oracle vs reference LatentDiffusion.sample: max|d| = {d:.3e} (|x|max {float(want.abs().max()):.3f})")
+            assert d < 1e-4 * max(1.0, float(want.abs().max()))
+            out[name] = want.numpy()
+    finally:
+        ref_ddpm.noise_like = orig
+    np.savez_compressed(os.path.join(GOLD, "ancestral.npz"), **out)
+    print("[ancestral] wrote ancestral.npz")
+
+
 def load_small_cond():
     z = np.load(os.path.join(GOLD, "small_b2_l32.npz"))
     return {k: z[k] for k in ("c_concat", "c_crossattn", "uc_crossattn")}
@@ -344,6 +377,8 @@ if __name__ == "__main__":
         gen_spatial_transformer()
     if a.only in ("all", "dpm"):
         gen_dpm()
+    if a.only in ("all", "ancestral"):
+        gen_ancestral()
     if a.only in ("all", "small"):
         # B=2, latent 32 (128^2 image), two style images per sample (exercises Agg_Mean), full DDIM-50
         gen_case("small_b2_l32", B=2, L=32, n_style=2, S=50, full_steps=True, seed=0, store_f16_image=False)

@@ -243,6 +243,37 @@ def ddim_sample(sd, cond, uncond, x_T, S=50, eta=0.0, cfg_scale=1.5, num_heads=8
     return img, inter
 
 
+def ddpm_ancestral_sample(sd, cond, x_T, timesteps, noises, quantize_denoised=False, clip_denoised=False, num_heads=8,
+                          v_posterior=0.0, linear_start=0.0015, linear_end=0.0205, T=1000):
+    """LatentDiffusion.sample -> p_sample_loop -> p_sample -> p_mean_variance (ddpm.py:1050-1110, 1168-1235) with the
+    schedule buffers of register_schedule (ddpm.py:120-172: float64 numpy, stored fp32), predict_start_from_noise
+    (:219-223) and q_posterior (:225-232).  ``noises[i]`` is the N(0,1) draw of loop iteration i (t = timesteps-1-i);
+    the t == 0 draw is masked out.  ``quantize_denoised`` snaps x_recon to the VQ codebook (:1071-1072)."""
+    betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=np.float64) ** 2
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    sqrt_recip, sqrt_recipm1 = f32(np.sqrt(1.0 / ac)), f32(np.sqrt(1.0 / ac - 1))
+    pv = (1 - v_posterior) * betas * (1.0 - ac_prev) / (1.0 - ac) + v_posterior * betas
+    logvar = f32(np.log(np.maximum(pv, 1e-20)))
+    coef1 = f32(betas * np.sqrt(ac_prev) / (1.0 - ac))
+    coef2 = f32((1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac))
+    img = x_T
+    for i, t_i in enumerate(reversed(range(0, timesteps))):
+        t = torch.full((img.shape[0],), t_i, dtype=torch.long)
+        eps = apply_model(sd, img, t, cond, num_heads)
+        x_recon = sqrt_recip[t_i] * img - sqrt_recipm1[t_i] * eps
+        if clip_denoised:
+            x_recon = x_recon.clamp(-1.0, 1.0)
+        if quantize_denoised:
+            x_recon, _ = vq_quantize(x_recon, sd[VAE + "quantize.embedding.weight"])
+        mean = coef1[t_i] * x_recon + coef2[t_i] * img
+        nonzero = 0.0 if t_i == 0 else 1.0
+        img = mean + nonzero * (0.5 * logvar[t_i]).exp() * noises[i]
+    return img
+
+
 class DiscreteVPSchedule:
     """NoiseScheduleVP('discrete', alphas_cumprod=...), ldm/models/diffusion/dpm_solver/dpm_solver.py:7-160, restated on
     the host in float64: key points t_n = (n + 1) / N with log alpha(t_n) = 0.5 log(alphas_cumprod[n]) (:78-88),

@@ -281,15 +281,15 @@ template <int HD>
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("attention_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return ERR_CUDA;
     }
-    configured = true;
+    configured.done();
   }
   dim3 grid((p.tokens + AT_BM - 1) / AT_BM, p.heads, batch);
   attention_tc_kernel<HD><<<grid, AT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, p);

@@ -26,6 +26,19 @@ static inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
     }                                            \
   } while (0)
 
+// ---- per-device one-time setup (cudaFuncSetAttribute is per device; a process may touch several GPUs) -------------
+// `mask` is a function-local static: bit d is set once the attribute has been applied on device d.  Racing threads may
+// both apply it (idempotent); nothing is ever cleared.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  int dev = 0;
+  bool needed() {
+    cudaGetDevice(&dev);
+    return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & (1ull << (dev & 63))) == 0;
+  }
+  void done() { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+
 // ---- small device utilities ----------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

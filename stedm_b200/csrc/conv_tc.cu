@@ -677,11 +677,14 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
 }
 
 int tc_num_sms() {
-  static int n = 0;
+  static int cached[64] = {0};  // per device (a process may drive several GPUs)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cached[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n = v;
   }
   return n;
 }
@@ -690,14 +693,14 @@ template <int BN, int CL, bool PAIR, bool HALO>
 int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
               const CUtensorMap& ms1, TcParams p, cudaStream_t stream) {
   using Cfg = TcCfg<BN, PAIR>;
-  static bool configured = false;  // per-process; the attribute is per-function and idempotent
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per function AND per device
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return ERR_CUDA;
     }
-    configured = true;
+    configured.done();
   }
   if (!HALO) {
     p.a_buf_bytes = Cfg::A_BYTES;

@@ -309,13 +309,13 @@ extern "C" int stedm_linear(const float* in, const float* w, const float* bias, 
   const size_t smem = static_cast<size_t>(LIN_BT) * k * 4;
   STEDM_REQUIRE(smem <= 200 * 1024, "linear: k = %d too large for the staging buffer", k);
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.needed()) {
       if (cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
         set_error("linear: cannot raise the dynamic shared memory limit");
         return ERR_CUDA;
       }
-      configured = true;
+      configured.done();
     }
   }
   dim3 grid((n + 7) / 8, (batch + LIN_BT - 1) / LIN_BT);
@@ -377,6 +377,9 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
         besti = oi;
       }
     }
+    // a pixel whose every distance is NaN (diverged sampling) wins no comparison: code 0, like torch.argmin on an
+    // all-NaN row, instead of an out-of-bounds gather
+    if (static_cast<unsigned>(besti) >= static_cast<unsigned>(n_codes)) besti = 0;
     if (lane < C) zq[(b * C + lane) * hw + pix] = s_cb[besti * (C + 1) + lane];
     if (lane == 0 && idx != nullptr) idx[p] = besti;
   }

@@ -478,10 +478,10 @@ extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int 
     const int ppb_bulk = max(ppb, 4 * (GB_STAGE_BYTES / (C * 2) > 0 ? GB_STAGE_BYTES / (C * 2) : 1));
     dim3 grid_b((hw + ppb_bulk - 1) / ppb_bulk, batch);
     const size_t smem_b = static_cast<size_t>(GB_STAGES) * GB_STAGE_BYTES + static_cast<size_t>(2) * C * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.needed()) {
       cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      configured = true;
+      configured.done();
     }
     gn_apply_bulk_kernel<<<grid_b, GN_THREADS, smem_b, s>>>(
         static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), x1_batch, hw, c0, c1, ppb_bulk,

@@ -50,6 +50,7 @@ class VQModelInterface(nn.Module):
         self.post_quant_conv = nn.Conv2d(embed_dim, dd["z_channels"], 1)
         self.precision = precision
         self._runner = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         if monitor is not None:
             self.monitor = monitor
         if ckpt_path is not None:
@@ -64,6 +65,10 @@ class VQModelInterface(nn.Module):
         missing, unexpected = self.load_state_dict(sd, strict=False)
         print(f"Restored from {path} with {len(missing)} missing and {len(unexpected)} unexpected keys")
 
+    # packed-weight lifecycle: same contract as UNetModel (see its comment)
+    def invalidate_packed(self):
+        self._runner = None
+
     def _apply(self, fn, *a, **k):
         self._runner = None
         return super()._apply(fn, *a, **k)
@@ -76,12 +81,18 @@ class VQModelInterface(nn.Module):
         if precision != self.precision:
             self.precision, self._runner = precision, None
 
+    def _weights_signature(self):
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+
     def runner(self):
+        if self._runner is not None and self._runner_sig != self._weights_signature():
+            self._runner = None
         if self._runner is None:
             from ...engine import DecoderRunner
             if not self.post_quant_conv.weight.is_cuda:
                 raise RuntimeError("VQModelInterface.decode runs only on a CUDA (sm_100a) device")
             self._runner = DecoderRunner(self, self.precision)
+            self._runner_sig = self._weights_signature()
         return self._runner
 
     def encode(self, x):

@@ -248,19 +248,29 @@ class LatentDiffusion(DDPM):
         return out[0] if isinstance(out, tuple) and not return_ids else out
 
     # ---- DDPM ancestral sampler (ddpm.py:1050-1235); elementwise tail in torch, U-Net native -----------------
-    def p_mean_variance(self, x, c, t, clip_denoised: bool, return_x0=False, **unused):
+    def p_mean_variance(self, x, c, t, clip_denoised: bool, return_codebook_ids=False, quantize_denoised=False,
+                        return_x0=False, score_corrector=None, corrector_kwargs=None):
+        if return_codebook_ids or score_corrector is not None:
+            raise NotImplementedError("codebook-id outputs / score correctors are not on STEDM's path")
         eps = self.apply_model(x, t, c)
         x_recon = self.predict_start_from_noise(x, t=t, noise=eps)
         if clip_denoised:
             x_recon.clamp_(-1., 1.)
+        if quantize_denoised:           # ddpm.py:1071-1072: x_recon snapped to the first stage's VQ codebook
+            from .... import ops
+            x_recon = ops.vq_nearest(x_recon.float().contiguous(),
+                                     self.first_stage_model.quantize.embedding.weight.detach().float().contiguous())
         mean, var, logvar = self.q_posterior(x_start=x_recon, x_t=x, t=t)
         return (mean, var, logvar, x_recon) if return_x0 else (mean, var, logvar)
 
     @torch.no_grad()
-    def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_x0=False, temperature=1.,
-                 noise_dropout=0., **unused):
+    def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_codebook_ids=False,
+                 quantize_denoised=False, return_x0=False, temperature=1., noise_dropout=0., score_corrector=None,
+                 corrector_kwargs=None):
         b = x.shape[0]
-        outs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_x0=return_x0)
+        outs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_codebook_ids=return_codebook_ids,
+                                    quantize_denoised=quantize_denoised, return_x0=return_x0,
+                                    score_corrector=score_corrector, corrector_kwargs=corrector_kwargs)
         mean, logvar = outs[0], outs[2]
         noise = noise_like(x.shape, x.device, repeat_noise) * temperature
         if noise_dropout > 0.:
@@ -283,7 +293,7 @@ class LatentDiffusion(DDPM):
             timesteps = min(timesteps, start_T)
         for i in reversed(range(0, timesteps)):
             ts = torch.full((b,), i, device=device, dtype=torch.long)
-            img = self.p_sample(img, cond, ts, clip_denoised=self.clip_denoised)
+            img = self.p_sample(img, cond, ts, clip_denoised=self.clip_denoised, quantize_denoised=quantize_denoised)
             if mask is not None:
                 img = self.q_sample(x0, ts) * mask + (1. - mask) * img
             if i % log_every_t == 0 or i == timesteps - 1:

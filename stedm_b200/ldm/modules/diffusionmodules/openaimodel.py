@@ -156,36 +156,45 @@ class UNetModel(nn.Module):
         nn.init.zeros_(self.out[2].weight)
         nn.init.zeros_(self.out[2].bias)
         self._runner = None
-        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # ---- packed-weight lifecycle ------------------------------------------------------------------------
+    # The runner holds derived copies of the weights (bf16 repacks, stacked embedding tables, the per-timestep embedding
+    # cache) and captured CUDA graphs.  They are dropped whenever the nn.Parameters can have changed: .to()/.cuda()
+    # (_apply), load_state_dict on THIS module or on any parent (the post hook fires during a parent's recursive load,
+    # which never calls a child's load_state_dict override), and in-place updates that bump a parameter's version
+    # counter or move its storage (checked by runner()).  Writes through ``p.data`` bypass the version counter: call
+    # invalidate_packed() after those.
     def invalidate_packed(self):
         self._runner = None
         self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
 
     def _apply(self, fn, *a, **k):
-        self._runner = None
-        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
+        self.invalidate_packed()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._runner = None
-        self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
+        self.invalidate_packed()
         return super().load_state_dict(*a, **k)
 
     def set_precision(self, precision):
         if precision != self.precision:
             self.precision = precision
-            self._runner = None
-            self.__dict__.pop("_graph_cache", None)  # captured graphs hold the old packed weights
+            self.invalidate_packed()
+
+    def _weights_signature(self):
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
 
     def runner(self):
+        if self._runner is not None and self._runner_sig != self._weights_signature():
+            self.invalidate_packed()
         if self._runner is None:
             from ....engine import UNetRunner
             if not next(self.parameters()).is_cuda:
                 raise RuntimeError("UNetModel runs only on a CUDA (sm_100a) device: move the model with .cuda() "
                                    "first — there is no CPU path")
             self._runner = UNetRunner(self, self.precision)
+            self._runner_sig = self._weights_signature()
         return self._runner
 
     # ---- reference API ----------------------------------------------------------------------------------

@@ -1,7 +1,13 @@
 """Prediction entry point — the B200 counterpart of the reference's ``predict_diff.py`` (predict_diff.py:34-89).
 
-    python -m stedm_b200.predict [hydra-style overrides] [+ckpt_path=... +predict_dir=out] [+synthetic=N]
+    python -m stedm_b200.predict [hydra-style overrides] [+ckpt_path=/abs/file.ckpt | +ckpt_name=x.ckpt] [+predict_dir=out]
+                                 [+synthetic=N] [+fixture_weights=true]
     torchrun --nproc-per-node 8 -m stedm_b200.predict location=b200x8 ...
+
+Checkpoint: ``+ckpt_path=`` (a file) or, like predict_diff.py:39-44, ``+ckpt_name=`` / the default
+``Diff_<data>_<samples>_<sampling>_last.ckpt`` under ``location.result_dir/checkpoints``.  A missing checkpoint is an
+error, as in the reference (``load_from_checkpoint``) — unless ``+fixture_weights=true`` (or ``+synthetic=N``, the
+self-test mode) explicitly asks for the deterministic random-init weights the tests and the benchmark use.
 
 Same config tree and override syntax (``style_agg=mean ddim_steps=50 diffusion.image_size=64 data.patch_size=256``);
 the Lightning Trainer / DDPStrategy of the reference is replaced by one process per GPU: each rank takes the
@@ -39,7 +45,8 @@ class SyntheticPredictSet(torch.utils.data.Dataset):
         return torch.zeros(3, self.p, self.p), seg_oh, lab, style, i
 
 
-def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None, async_io=True):
+def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None, async_io=True,
+        allow_fixture_weights=False):
     """Generate and save images for every batch tuple of ``batches`` on this rank's GPU."""
     rank, world, local = parallel.env_rank_world()
     device = device or torch.device("cuda", local)
@@ -52,6 +59,20 @@ def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None, 
         sd = sd.get("state_dict", sd)
         missing, unexpected = module.load_state_dict(sd, strict=False)   # predict_diff.py:48
         print(f"[rank {rank}] restored {ckpt_path}: {len(missing)} missing, {len(unexpected)} unexpected keys")
+        for name, keys in (("missing", missing), ("unexpected", unexpected)):
+            if keys:
+                print(f"[rank {rank}]   {name}: {', '.join(keys[:12])}{' ...' if len(keys) > 12 else ''}")
+        # the sampled networks must come from the checkpoint: a file without them would sample random weights
+        # (encoder.* / loss.* / model_ema.* are outside the sampling path and may be absent)
+        vital = [k for k in missing if ".diffusion_model." in k or ".first_stage_model.decoder." in k
+                 or ".first_stage_model.quantize." in k or ".first_stage_model.post_quant_conv." in k
+                 or ".cond_stage_model." in k or ".agg_block." in k]
+        if vital:
+            raise RuntimeError(f"checkpoint {ckpt_path} lacks {len(vital)} weights of the sampling path "
+                               f"(first: {vital[0]}); refusing to sample partly random weights")
+    elif not allow_fixture_weights:
+        raise FileNotFoundError("no checkpoint: pass +ckpt_path=/abs/file.ckpt or +ckpt_name=... (looked up under "
+                                "location.result_dir/checkpoints), or +fixture_weights=true for random-init weights")
     else:
         from .utils.fixture import apply_fixture_weights
         apply_fixture_weights(module._model, seed=0)
@@ -72,6 +93,25 @@ def run(cfg, batches, predict_dir, ckpt_path=None, precision=None, device=None, 
     return n
 
 
+def resolve_checkpoint(cfg):
+    """``+ckpt_path=`` (a file; ``ckpt_path_full`` is the older spelling) or predict_diff.py:39-44's rule:
+    ``location.result_dir/checkpoints/<ckpt_name | Diff_<data>_<samples>_<sampling>_last.ckpt>``.  Returns None when no
+    checkpoint was named and the default file does not exist (run() then raises unless fixture weights are allowed)."""
+    explicit = cfg.get("ckpt_path") or cfg.get("ckpt_path_full")
+    if explicit:
+        if not os.path.isfile(str(explicit)):
+            raise FileNotFoundError(f"checkpoint {explicit} does not exist")
+        return str(explicit)
+    named = cfg.get("ckpt_name")
+    name = named or (f"Diff_{cfg.data.name}_{cfg.data.get('class_train_samples', '')}_{cfg.style_sampling.name}_last.ckpt")
+    path = os.path.join(str(cfg.location.result_dir), "checkpoints", str(name))
+    if os.path.isfile(path):
+        return path
+    if named:
+        raise FileNotFoundError(f"checkpoint {path} does not exist")
+    return None
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     cfg = load_config(argv)
@@ -87,7 +127,8 @@ def main(argv=None):
     loader = torch.utils.data.DataLoader(mine, batch_size=batch_size, shuffle=False, num_workers=workers,
                                          pin_memory=True, persistent_workers=workers > 0)
     out = cfg.get("predict_dir", os.path.join(os.getcwd(), "stedm_predict"))
-    done = run(cfg, loader, out, ckpt_path=cfg.get("ckpt_path_full"))
+    done = run(cfg, loader, out, ckpt_path=resolve_checkpoint(cfg),
+               allow_fixture_weights=bool(cfg.get("fixture_weights", False)) or cfg.get("synthetic") is not None)
     print(f"[rank {rank}/{world}] wrote {done} images to {out}")
     if world > 1:
         torch.distributed.barrier()

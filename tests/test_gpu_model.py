@@ -169,7 +169,7 @@ def test_predict_path_end_to_end(precision):
     mse = ((u8.astype(np.float64) - ref) ** 2).mean()
     p = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
     print(f"{precision} end-to-end uint8 PSNR vs reference: {p:.1f} dB")
-    assert p >= (PSNR_BAR if precision == "fp32" else 30.0)
+    assert p >= PSNR_BAR      # bf16 measured 42.6 dB (round 1)
 
 
 def test_batch_shard_invariance():
@@ -183,6 +183,62 @@ def test_batch_shard_invariance():
                 "c_crossattn": [torch.from_numpy(g["c_crossattn"][r:r + 1]).cuda()]}
         part = m._model.apply_model(x_T[r:r + 1].cuda(), tt[:1], cond)
         assert torch.equal(part[0], full[r])
+
+
+def _no_split_k():
+    """Context: force the single-pass K loop (the latency mode's split-K changes the fp32 summation order with the
+    number of output tiles, i.e. with the batch; bit-equality across batch sizes is a property of the throughput path)."""
+    import contextlib
+    from stedm_b200 import ops
+
+    @contextlib.contextmanager
+    def ctx():
+        saved = ops.SPLIT_K[0]
+        ops.SPLIT_K[0] = False
+        try:
+            yield
+        finally:
+            ops.SPLIT_K[0] = saved
+    return ctx()
+
+
+def test_bench_geometry_b64_l64_rows_equal_b4_golden_run():
+    """Parity at the BENCHMARKED geometry (BASELINE configs[1]: batch 64, latent 64, bf16; trunk at 64 samples, the
+    rest at 128, where the tile / cluster / halo plan differs from the B = 4 golden case): one guided DDIM step and one
+    apply_model at B = 64 whose samples 0-3 are the inputs of tests/golden/c1_b4_l64.npz.  Rows 0-3 must be BIT-EQUAL to
+    the B = 4 run (shard invariance at the bench geometry) and within the bf16 bar of the reference's golden eps / x."""
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    g = load_golden("c1_b4_l64")
+    _, _, x4 = O.synthetic_batch(4, 256, 1, 1)
+    B = 64
+    gen = torch.Generator().manual_seed(640)
+    x = torch.cat([x4, torch.randn(B - 4, 3, 64, 64, generator=gen)], 0).cuda()
+    cc = torch.cat([torch.from_numpy(g["c_concat"]), torch.randn(B - 4, 3, 64, 64, generator=gen)], 0).cuda()
+    ca = torch.cat([torch.from_numpy(g["c_crossattn"]), torch.randn(B - 4, 512, generator=gen)], 0).cuda()
+    cu = torch.cat([torch.from_numpy(g["uc_crossattn"]), torch.randn(B - 4, 512, generator=gen)], 0).cuda()
+    m = build_model(64, n_style=1, precision="bf16")
+    model = m._model
+    mk = lambda a, b, n: {"c_concat": [a[:n].contiguous()], "c_crossattn": [b[:n].contiguous()]}
+    with _no_split_k():
+        for t in (981, 481):
+            tt = torch.full((B,), t, dtype=torch.long, device="cuda")
+            e64 = model.apply_model(x, tt, mk(cc, ca, B))
+            e4 = model.apply_model(x[:4].contiguous(), tt[:4], mk(cc, ca, 4))
+            assert torch.equal(e64[:4], e4), f"eps rows 0-3 at B=64 differ from the B=4 run (t={t})"
+            r = rel_err(e64[:4], g[f"eps_c_{t}"])
+            print(f"B=64 L=64 bf16 eps rows 0-3 vs reference golden, t={t}: rel err {r:.3e}")
+            assert r < BF16_EPS_BAR, r
+        s = DDIMSampler(model)
+        s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+        ts = torch.full((B,), 981, dtype=torch.long, device="cuda")
+        x64, p64 = s.p_sample_ddim(x, mk(cc, ca, B), ts, index=49, unconditional_guidance_scale=1.5,
+                                   unconditional_conditioning=mk(cc, cu, B))
+        x4o, p4o = s.p_sample_ddim(x[:4].contiguous(), mk(cc, ca, 4), ts[:4], index=49, unconditional_guidance_scale=1.5,
+                                   unconditional_conditioning=mk(cc, cu, 4))
+    assert torch.equal(x64[:4], x4o) and torch.equal(p64[:4], p4o), "guided step rows 0-3 at B=64 differ from the B=4 run"
+    r = rel_err(x64[:4], g["x_after_1"])
+    print(f"B=64 L=64 bf16 guided step rows 0-3 vs reference golden x_after_1: rel err {r:.3e}")
+    assert r < BF16_EPS_BAR, r
 
 
 def test_cuda_graph_sampler_matches_eager():
@@ -233,7 +289,8 @@ def test_shared_trunk_is_bit_identical(precision):
 
 def test_latent128_eps_and_decode_vs_oracle():
     """BASELINE configs[3] geometry (512^2 image, latent 128: full-row 128-pixel tiles, 16 384-token decoder
-    attention) against the CPU oracle run live on the same fixture weights, batch 1."""
+    attention) against the CPU oracle run live on the same fixture weights: batch 1, and the same sample as row 0 of a
+    batch of 8 (bit-equal to the batch-1 run: shard invariance at this geometry too)."""
     m = build_model(128, n_style=1, precision="bf16")
     model = m._model
     sd = oracle_state_dict(model)
@@ -243,10 +300,17 @@ def test_latent128_eps_and_decode_vs_oracle():
     t = torch.full((1,), 481, dtype=torch.long)
     with torch.no_grad():
         want = O.apply_model(sd, x_T, t, cond)
-    got = model.apply_model(x_T.cuda(), t.cuda(), {k: [v[0].cuda()] for k, v in cond.items()})
-    r = rel_err(got, want)
-    print(f"latent-128 bf16 eps rel err {r:.3e}")
-    assert r < BF16_EPS_BAR
+    with _no_split_k():
+        got = model.apply_model(x_T.cuda(), t.cuda(), {k: [v[0].cuda()] for k, v in cond.items()})
+        r = rel_err(got, want)
+        print(f"latent-128 bf16 eps rel err {r:.3e}")
+        assert r < BF16_EPS_BAR
+        B = 8
+        x8 = torch.cat([x_T, torch.randn(B - 1, 3, 128, 128, generator=g)], 0).cuda()
+        c8 = {"c_concat": [torch.cat([cond["c_concat"][0], torch.randn(B - 1, 3, 128, 128, generator=g)], 0).cuda()],
+              "c_crossattn": [torch.cat([cond["c_crossattn"][0], torch.randn(B - 1, 512, generator=g)], 0).cuda()]}
+        got8 = model.apply_model(x8, torch.full((B,), 481, dtype=torch.long, device="cuda"), c8)
+    assert torch.equal(got8[:1], got), "row 0 of the B=8 latent-128 pass differs from the B=1 run"
     z = x_T * 60
     with torch.no_grad():
         want_img = O.decode_first_stage(sd, z, force_not_quantize=True)
@@ -254,6 +318,9 @@ def test_latent128_eps_and_decode_vs_oracle():
     p = psnr(img.clamp(-1, 1), want_img.clamp(-1, 1))
     print(f"latent-128 bf16 decode PSNR {p:.1f} dB")
     assert tuple(img.shape) == (1, 3, 512, 512) and p >= PSNR_BAR
+    z2 = torch.cat([z, torch.randn(1, 3, 128, 128, generator=g) * 60], 0).cuda()
+    img2 = model.decode_first_stage(z2, force_not_quantize=True)
+    assert torch.equal(img2[:1], img), "row 0 of the B=2 latent-128 decode differs from the B=1 run"
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -279,22 +346,43 @@ def test_multi_style_aggregation_her2_shape(precision):
     assert max_abs(c["c_concat"][0], want["c_concat"][0]) < 1e-6
 
 
-def test_ddpm_ancestral_last_step_is_deterministic_and_matches_formula():
-    """Kept API (ddpm.py:1081-1110): p_sample at t = 0 adds no noise; mean = coef1*x0 + coef2*x_t with
-    x0 = sqrt(1/acp)*x - sqrt(1/acp - 1)*eps."""
+def test_ddpm_ancestral_sampler_matches_reference_golden(monkeypatch):
+    """Kept API: LatentDiffusion.sample -> p_sample_loop -> p_sample -> p_mean_variance
+    (ddpm.py:1050-1110, 1168-1235), 5 ancestral steps with the per-step noise the reference run drew
+    (tests/golden/ancestral.npz, oracle/make_golden.py --only ancestral), plain and with quantize_denoised."""
+    import stedm_b200.ldm.models.diffusion.ddpm as native_ddpm
     g, _, _, x_T = _small_inputs()
+    gold = load_golden("ancestral")
+    T = int(gold["timesteps"])
     m = build_model(32, n_style=2, precision="fp32")
     model = m._model
     cond = _cond(g, "c_crossattn")
-    t = torch.zeros(2, dtype=torch.long, device="cuda")
-    x = x_T.cuda()
-    out = model.p_sample(x, cond, t, clip_denoised=False)
-    eps = model.apply_model(x, t, cond)
-    x0 = model.sqrt_recip_alphas_cumprod[0] * x - model.sqrt_recipm1_alphas_cumprod[0] * eps
-    want = model.posterior_mean_coef1[0] * x0 + model.posterior_mean_coef2[0] * x
-    assert max_abs(out, want) < 1e-5
-    z = model.sample(cond, batch_size=2, x_T=x, timesteps=2, verbose=False)
-    assert tuple(z.shape) == (2, 3, 32, 32) and bool(torch.isfinite(z).all())
+    for name, scale, quant in (("ancestral_t5", 1.0, False), ("ancestral_t5_quant", 40.0, True)):
+        it = iter(torch.from_numpy(gold["noises"]).cuda())
+        monkeypatch.setattr(native_ddpm, "noise_like", lambda shape, device, repeat=False: next(it).clone())
+        z = model.sample(cond, batch_size=2, x_T=x_T.cuda() * scale, timesteps=T, verbose=False, quantize_denoised=quant)
+        want = torch.from_numpy(gold[name])
+        if not quant:
+            assert rel_err(z, want) < 1e-4, rel_err(z, want)
+        else:
+            # a pixel whose two nearest codes are ~equidistant may snap differently: rare, and large when it happens
+            bad = ((z.cpu() - want).abs() > 1e-3 * float(want.abs().max())).float().mean()
+            print(f"ancestral quantize_denoised: fraction of differing values {float(bad):.2e}")
+            assert float(bad) < 0.01
+    # bf16 mode runs the same loop inside the bf16 eps bar
+    monkeypatch.undo()
+    it = iter(torch.from_numpy(gold["noises"]).cuda())
+    monkeypatch.setattr(native_ddpm, "noise_like", lambda shape, device, repeat=False: next(it).clone())
+    mb = build_model(32, n_style=2, precision="bf16")
+    zb = mb._model.sample(cond, batch_size=2, x_T=x_T.cuda(), timesteps=T, verbose=False)
+    r = rel_err(zb, gold["ancestral_t5"])
+    print(f"bf16 ancestral 5-step rel err {r:.3e}")
+    assert r < BF16_EPS_BAR
+    # p_sample at t = 0 adds no noise (ddpm.py:1103)
+    t0 = torch.zeros(2, dtype=torch.long, device="cuda")
+    a = mb._model.p_sample(x_T.cuda(), cond, t0)
+    b = mb._model.p_sample(x_T.cuda(), cond, t0)
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("B,L", [(3, 32), (1, 64)])
@@ -341,7 +429,7 @@ def test_predict_entry_point_writes_pngs(tmp_path):
         assert Image.open(f"{out}/seg_{i:05d}.png").size == (128, 128)
 
 
-@pytest.mark.parametrize("precision,z_bar,psnr_bar", [("fp32", 1e-3, 40.0), ("bf16", 5e-2, 30.0)])
+@pytest.mark.parametrize("precision,z_bar,psnr_bar", [("fp32", 1e-3, 40.0), ("bf16", 5e-2, 40.0)])
 def test_config0_flowers_b4_256_full_path_vs_reference_golden(precision, z_bar, psnr_bar):
     """BASELINE configs[0] (flowers proof of concept: batch 4, 256^2, DDIM-50, cfg 1.5) end to end against the
     golden produced by the reference's own code on CPU (tests/golden/c1_b4_l64.npz)."""

@@ -125,3 +125,44 @@ def test_prepare_batch_merges_multi_class_layouts(model):
     assert torch.equal(out["segmentation"][..., 0], (lab == 0).float())
     assert torch.equal(out["segmentation"][..., 1], (lab != 0).float())
     assert torch.equal(out["style_imgs"][1, 2, :, :, 0], style[1, 2, 0])
+
+
+def test_parent_level_load_and_in_place_updates_invalidate_packed_weights(model):
+    """nn.Module.load_state_dict on a PARENT never calls a child's load_state_dict override, so the packed
+    runners (bf16 repacks, embedding cache, CUDA graphs) are dropped by a load_state_dict post hook instead; in-place
+    parameter updates are caught by the (version, data_ptr) signature runner() compares."""
+    unet = model._model.model.diffusion_model
+    vq = model._model.first_stage_model
+    for mod in (unet, vq):
+        mod._runner = object()                       # stands for a built runner (building one needs a GPU)
+    unet.__dict__["_graph_cache"] = {"k": 1}
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.load_state_dict(sd, strict=False)          # top-level load, as predict.run / init_from_ckpt on the parent do
+    assert unet._runner is None and vq._runner is None and "_graph_cache" not in unet.__dict__
+    sig = unet._weights_signature()
+    with torch.no_grad():
+        unet.time_embed[0].weight.mul_(1.0)          # EMA-style in-place update: bumps the version counter
+    assert unet._weights_signature() != sig
+    sig = vq._weights_signature()
+    with torch.no_grad():
+        vq.quantize.embedding.weight.add_(0.0)
+    assert vq._weights_signature() != sig
+
+
+def test_predict_checkpoint_resolution(tmp_path):
+    """predict.resolve_checkpoint: +ckpt_path (documented key), the reference's ckpt_name rule (predict_diff.py:39-44),
+    hard errors for named-but-missing files, None when nothing was named."""
+    from stedm_b200.config import load_config
+    from stedm_b200.predict import resolve_checkpoint
+    f = tmp_path / "x.ckpt"
+    f.write_bytes(b"0")
+    assert resolve_checkpoint(load_config([f"+ckpt_path={f}"])) == str(f)
+    with pytest.raises(FileNotFoundError):
+        resolve_checkpoint(load_config([f"+ckpt_path={tmp_path}/nope.ckpt"]))
+    (tmp_path / "checkpoints").mkdir()
+    (tmp_path / "checkpoints" / "mine.ckpt").write_bytes(b"0")
+    cfg = load_config([f"location.result_dir={tmp_path}", "+ckpt_name=mine.ckpt"])
+    assert resolve_checkpoint(cfg) == str(tmp_path / "checkpoints" / "mine.ckpt")
+    with pytest.raises(FileNotFoundError):
+        resolve_checkpoint(load_config([f"location.result_dir={tmp_path}", "+ckpt_name=other.ckpt"]))
+    assert resolve_checkpoint(load_config([f"location.result_dir={tmp_path}"])) is None

@@ -104,3 +104,19 @@ def test_oracle_dpm_solver_matches_reference_golden(fixture_sd):
                                   uncond_eps_fn=lambda x, t: O.apply_model(fixture_sd, x, t, unc))
     want = load_golden("dpm_solver")["dpm_s12"]
     assert max_abs(got, want) < 1e-5 * float(abs(want).max())
+
+
+def test_oracle_ddpm_ancestral_matches_reference_golden(fixture_sd):
+    """a17: oracle.ddpm_ancestral_sample vs the reference's LatentDiffusion.sample(timesteps=5) with the stored noise
+    (tests/golden/ancestral.npz), plain and with quantize_denoised."""
+    g = load_golden("small_b2_l32")
+    gold = load_golden("ancestral")
+    _, _, x_T = O.synthetic_batch(2, 128, 2, 0)
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"])], "c_crossattn": [torch.from_numpy(g["c_crossattn"])]}
+    noises = torch.from_numpy(gold["noises"])
+    T = int(gold["timesteps"])
+    with torch.no_grad():
+        z = O.ddpm_ancestral_sample(fixture_sd, cond, x_T, T, noises)
+        zq = O.ddpm_ancestral_sample(fixture_sd, cond, x_T * 40.0, T, noises, quantize_denoised=True)
+    assert max_abs(z, gold["ancestral_t5"]) < 1e-4
+    assert max_abs(zq, gold["ancestral_t5_quant"]) < 1e-4 * float(np.abs(gold["ancestral_t5_quant"]).max())
