@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STEDM_ABI_VERSION 2
+#define STEDM_ABI_VERSION 3
 
 #define STEDM_F32 0
 #define STEDM_BF16 1
@@ -75,10 +75,14 @@ int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int 
 /* Statistics pass folded into the producing convolutions: reduce the per-(128-pixel tile, channel) sums written by
  * stedm_conv_tc (stedm_conv_desc.stats_out) for the one or two producers of a GroupNorm input into
  * out = double [batch][1][32][2].  Source s: fp32 [reps_s][rep_stride_s tiles][c_s][2]; sample b owns tile rows
- * (b % batch_s)*tps_s + j, j < tps_s, in each of the reps_s repetitions (4 for the sub-pixel upsample phases). */
+ * (b % batch_s)*tps_s + j, j < tps_s, in each of the reps_s repetitions (4 for the sub-pixel upsample phases).
+ * coef (optional, with gamma / beta / eps / hw = pixels per sample of the normalised tensor): fp32 [batch][c0+c1][2] =
+ * per-(sample, channel) (scale, shift) with y = x*scale + shift, computed exactly as stedm_gn_apply does — for consumers
+ * that normalise in their own operand path (stedm_conv_desc.gn_coef).  `out` may be NULL when only coef is wanted. */
 int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long long rep_stride0, int tps0, int batch0,
                         const float* tiles1, int c1, int reps1, long long rep_stride1, int tps1, int batch1, int batch,
-                        double* out, void* stream);
+                        double* out, const float* gamma, const float* beta, float eps, int hw, float* coef,
+                        void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * K1/K2/K3/K4/K9/K10  Convolution as implicit GEMM, M = B*Ho*Wo pixels, N = Cout, K = k*k*(c0+c1).
@@ -136,6 +140,17 @@ typedef struct stedm_conv_desc {
                             b % res_batch; 0 => batch).  Together these let a convolution over a concat [h | skip] whose
                             skip half is shared by the two halves of a guided batch run as conv(h) + conv(skip), the
                             second term computed once and added here as a broadcast fp32 residual */
+  int32_t x1_pix_stride; /* the same for x1 (0 => c1, dense) */
+  int32_t gn_cstride;    /* channels per sample row of gn_coef (the GroupNorm's full channel count) */
+  int32_t gn_c_off;      /* concat channel 0 of THIS convolution's input is channel gn_c_off of the GroupNorm */
+  int32_t gn_silu;       /* 1 => SiLU after the normalisation (ResBlock in_layers / out_layers), 0 => none */
+  const float* gn_coef;  /* tensor-core path, optional: GroupNorm (+ SiLU) applied to the RAW input inside the kernel's
+                            operand path (util.py:199-216, openaimodel.py:268-288) — fp32 [samples][gn_cstride][2] =
+                            (scale, shift) per (sample, channel) from stedm_gn_fold_tiles; the input tensors are then the
+                            producer's unnormalised outputs and no normalised tensor is ever written.  Needs ksize 3,
+                            cout % 256 == 0 and whole-row pixel tiles (stedm_conv_tc_plan reports whether a shape
+                            qualifies: it fails with a message when gn_coef is set and the shape does not).  The fused
+                            skip input is NOT normalised.  NULL => the input is used as given. */
 } stedm_conv_desc;
 
 /* tcgen05 + TMEM + TMA implicit GEMM (bf16 operands, fp32 accumulate).  Requires in_dtype == STEDM_BF16, stride 1,

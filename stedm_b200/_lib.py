@@ -23,7 +23,9 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("upsample", C.c_int32), ("emb_stride", C.c_int32), ("res_dtype", C.c_int32),
                 ("out_dtype", C.c_int32), ("out_nchw", C.c_int32), ("cout", C.c_int32), ("cout_store", C.c_int32), ("tap_mode", C.c_int32), ("phase", C.c_int32),
                 ("act", C.c_int32), ("skip_c0", C.c_int32), ("skip_c1", C.c_int32), ("skip_x1_batch", C.c_int32),
-                ("skip_x0", vp), ("skip_x1", vp), ("x0_pix_stride", C.c_int32), ("res_batch", C.c_int32)]
+                ("skip_x0", vp), ("skip_x1", vp), ("x0_pix_stride", C.c_int32), ("res_batch", C.c_int32),
+                ("x1_pix_stride", C.c_int32), ("gn_cstride", C.c_int32), ("gn_c_off", C.c_int32), ("gn_silu", C.c_int32),
+                ("gn_coef", vp)]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -35,7 +37,7 @@ SIGNATURES = {
     "stedm_gn_num_chunks": [i32, i32],
     "stedm_gn_stats": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "stedm_gn_apply": [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, i32, vp, i32, vp],
-    "stedm_gn_fold_tiles": [vp, i32, i32, i64, i32, i32, vp, i32, i32, i64, i32, i32, i32, vp, vp],
+    "stedm_gn_fold_tiles": [vp, i32, i32, i64, i32, i32, vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, f32, i32, vp, vp],
     "stedm_conv_tc": [C.POINTER(ConvDesc), vp],
     "stedm_conv_tc_workspace_bytes": [C.POINTER(ConvDesc)],
     "stedm_conv_tc_plan": [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],
@@ -83,7 +85,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.stedm_abi_version() != 2:
+    if lib.stedm_abi_version() != 3:
         raise RuntimeError("libstedm_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -28,6 +28,11 @@
 // The producer is ONE thread and its instruction count per slab was the measured limiter: no divisions in its slab loop.
 // K loop extras: the 1x1 skip_connection of a channel-changing ResBlock (openaimodel.py:246-256, 288) is folded in as
 // extra K slabs read from the block input through two more tensor maps, so conv3x3(a) + skip1x1(x) is one accumulator.
+// XF mode (GroupNorm + SiLU in the operand path, util.py:199-216 / openaimodel.py:268-288): the convolution reads the RAW
+// producer output; four extra "transform" warps turn each raw halo box (ONE TMA load per 64-channel block) into the three
+// horizontally shifted operand boxes y = silu(x * a[b][c] + s[b][c]) (the per-(sample, channel) coefficients come from
+// stedm_gn_fold_tiles), re-zeroing the padding rows / columns, between TMA arrival and the MMA — the normalised tensor
+// is never written to HBM and an activation byte crosses L2->SM once per channel tile instead of three times.
 // Epilogue: + bias[n] + emb[b][n] (timestep / style embedding, openaimodel.py:278-287), optional exact-erf GELU,
 // + residual[m][n] (identity skip, openaimodel.py:288); the bias / embedding rows are fetched while tcgen05.ld is in
 // flight, and NHWC outputs pass through a per-warp XOR-swizzled shared-memory transpose so that 4 lanes write one pixel
@@ -45,6 +50,11 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS_XF = 320;  // + 4 transform warps (warps 6-9)
+// XF mode shared-memory operand pool: 2 sets x 3 boxes (raw -> [dx=-1 | dx=0 | dx=+1]) + a weight ring in what is left
+constexpr int TC_XF_POOL = 209 * 1024;
+constexpr int TC_XF_SETS = 2;
+constexpr int TC_XF_MAX_NB = 8;
 
 // STEDM_TC_CLUSTER=0 disables the 2-CTA weight multicast (A/B measurements, debugging)
 static bool g_tc_cluster_enabled = [] {
@@ -101,6 +111,12 @@ struct TcParams {
   int na;                // A ring buffers (a_buf_bytes each, carved out of the STAGES * 16 KB pool)
   int a_buf_bytes;       // 16 KB, or the halo box (th + n_t - 1) * W * 128 B
   int a_row_bytes;       // W * 128
+  // XF mode: GroupNorm (+ SiLU) applied to the raw input inside the kernel
+  const float* gn_coef;  // fp32 [samples][gn_cstride][2] = (scale, shift) per (sample, concat channel); nullptr = off
+  int gn_cstride, gn_c_off, gn_silu;
+  int nb;                // weight ring depth (XF: what fits beside the 6 boxes; otherwise Cfg::STAGES)
+  int a_pool_bytes;      // XF: 6 * a_buf_bytes
+  int log2w;             // XF: W is a power of two
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -127,31 +143,40 @@ struct TcCfg {
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES + OUT_STAGE_BYTES;
   static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
+  static constexpr int SMEM_BYTES_XF = TC_XF_POOL + 1024 + 256 + STATS_BYTES + OUT_STAGE_BYTES;
 };
 
-template <int BN, int CL, bool PAIR, bool HALO>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, PAIR>::MIN_BLOCKS)
+template <int BN, int CL, bool PAIR, bool HALO, bool XF>
+__global__ void __launch_bounds__(XF ? TC_THREADS_XF : TC_THREADS, TcCfg<BN, PAIR>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_s0,
                const __grid_constant__ CUtensorMap map_s1, const TcParams p) {
   static_assert(!PAIR || CL == 2, "cta_group::2 needs a 2-CTA cluster");
+  static_assert(!XF || (PAIR && HALO), "the in-kernel GroupNorm transform is built on the CTA-pair halo pipeline");
   using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // Operand area: [activation pool: STAGES slabs of 16 KB, or fewer and larger halo boxes | STAGES weight slabs]
-  // (measured 2-3 % faster than [activation | weight] back to back per slot)
+  // (measured 2-3 % faster than [activation | weight] back to back per slot).  XF: [2 sets x 3 boxes | p.nb weight slabs].
+  constexpr int POOL_BYTES = XF ? TC_XF_POOL : Cfg::STAGES * Cfg::STAGE_BYTES;
+  constexpr int NA_BARS = XF ? TC_XF_SETS : Cfg::STAGES;     // A ring barriers (XF: one pair per SET of three boxes)
+  constexpr int NB_BARS = XF ? TC_XF_MAX_NB : Cfg::STAGES;   // weight ring barriers
+  const uint32_t b_base = XF ? static_cast<uint32_t>(p.a_pool_bytes) : static_cast<uint32_t>(Cfg::A_POOL);
+  const uint32_t nb = XF ? static_cast<uint32_t>(p.nb) : static_cast<uint32_t>(Cfg::STAGES);
   auto slab_a = [](uint8_t* base, uint32_t s) { return base + s * Cfg::A_BYTES; };
-  auto slab_b = [](uint8_t* base, uint32_t s, int) { return base + Cfg::A_POOL + s * Cfg::B_BYTES_PAD; };
+  auto slab_b = [b_base](uint8_t* base, uint32_t s, int) { return base + b_base + s * Cfg::B_BYTES_PAD; };
   // two rings: activation buffers (A) and weight slabs (B), each with full / empty mbarriers
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_a = full_a + Cfg::STAGES;
-  uint64_t* full_b = empty_a + Cfg::STAGES;
-  uint64_t* empty_b = full_b + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_b + Cfg::STAGES;     // [ACC]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + POOL_BYTES);
+  uint64_t* empty_a = full_a + NA_BARS;
+  uint64_t* full_b = empty_a + NA_BARS;
+  uint64_t* empty_b = full_b + NB_BARS;
+  uint64_t* tmem_full_bar = empty_b + NB_BARS;         // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::ACC);
-  float* s_stats = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
-  uint8_t* s_out = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::STATS_BYTES;
+  uint64_t* xf_ready = tmem_empty_bar + Cfg::ACC;      // [TC_XF_SETS] (XF only): the set's three boxes are transformed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_ready + TC_XF_SETS);
+  static_assert((2 * NA_BARS + 2 * NB_BARS + 2 * Cfg::ACC + TC_XF_SETS) * 8 + 4 <= 256, "barrier area");
+  float* s_stats = reinterpret_cast<float*>(smem + POOL_BYTES + 256);
+  uint8_t* s_out = smem + POOL_BYTES + 256 + Cfg::STATS_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -168,13 +193,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tma_prefetch_desc(&map_s0);
       tma_prefetch_desc(&map_s1);
     }
-    for (int i = 0; i < Cfg::STAGES; ++i) {
-      // PAIR: the leader's full barriers collect both CTAs' producers; its single commit frees the slab in both
-      mbar_init(&full_a[i], PAIR ? 2 : 1);
-      mbar_init(&full_b[i], PAIR ? 2 : 1);
+    for (int i = 0; i < NA_BARS; ++i) {
+      // PAIR: the leader's full barriers collect both CTAs' producers; its single commit frees the slab in both.
+      // XF: the raw box is consumed by this CTA's own transform warps -> a local barrier with one producer
+      mbar_init(&full_a[i], (PAIR && !XF) ? 2 : 1);
       mbar_init(&empty_a[i], 1);                // activations are never multicast
+    }
+    for (int i = 0; i < NB_BARS; ++i) {
+      mbar_init(&full_b[i], PAIR ? 2 : 1);
       mbar_init(&empty_b[i], PAIR ? 1 : CL);    // multicast: released by the MMA commit of every CTA writing into it
     }
+    if constexpr (XF)
+      for (int i = 0; i < TC_XF_SETS; ++i) mbar_init(&xf_ready[i], 8);  // 4 transform warps of each CTA of the pair
     for (int i = 0; i < Cfg::ACC; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], PAIR ? 256 : 128);  // every epilogue thread (of both CTAs) arrives
@@ -234,7 +264,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
         const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
         const int bs1 = (p.skip_x1_batch > 0) ? (b0 % p.skip_x1_batch) : b0;
-        if constexpr (HALO) {
+        if constexpr (XF) {
+          // ONE raw box (the tile's rows + 2 halo rows, horizontal offset 0) per 64-channel block into the middle slot
+          // of a set — the transform warps derive the three horizontally shifted operand boxes from it — then the nine
+          // weight slabs in the order the MMA consumes them: horizontal tap bx, vertical tap g
+          for (int cb = 0; cb < c_blks; ++cb) {
+            const bool first = cb < c0_blks;
+            mbar_wait(&empty_a[ia], pa ^ 1);
+            mbar_arrive_expect_tx(&full_a[ia], static_cast<uint32_t>(p.a_buf_bytes));
+            tma_load_4d(smem + (ia * 3 + 1) * p.a_buf_bytes, first ? &map_a0 : &map_a1, &full_a[ia],
+                        (first ? cb : cb - c0_blks) * TC_BK, x0, y0 - 1, first ? b0 : b1);
+            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+            for (int bx = 0; bx < 3; ++bx) {
+              int kb = bx * c_blks + cb;
+              for (int g = 0; g < 3; ++g, kb += 3 * c_blks) {
+                mbar_wait(&empty_b[ib], pb ^ 1);
+                arrive_full(&full_b[ib], Cfg::B_BYTES);
+                load_b(ib, kb, n0);
+                if (++ib == nb) { ib = 0; pb ^= 1; }
+              }
+            }
+          }
+          // fused 1x1 skip input: raw 16 KB slabs of the tile's own pixels, up to three per set (one per box slot)
+          for (int sb = 0; sb < p.skip_blks; sb += 3) {
+            const int n = min(3, p.skip_blks - sb);
+            mbar_wait(&empty_a[ia], pa ^ 1);
+            mbar_arrive_expect_tx(&full_a[ia], static_cast<uint32_t>(n * Cfg::A_BYTES));
+            for (int i = 0; i < n; ++i) {
+              const bool first = sb + i < p.skip_c0_blks;
+              tma_load_4d(smem + (ia * 3 + i) * p.a_buf_bytes, first ? &map_s0 : &map_s1, &full_a[ia],
+                          (first ? sb + i : sb + i - p.skip_c0_blks) * TC_BK, x0, y0, first ? b0 : bs1);
+            }
+            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+            for (int i = 0; i < n; ++i) {
+              mbar_wait(&empty_b[ib], pb ^ 1);
+              arrive_full(&full_b[ib], Cfg::B_BYTES);
+              load_b(ib, main_kb + sb + i, n0);
+              if (++ib == nb) { ib = 0; pb ^= 1; }
+            }
+          }
+        } else if constexpr (HALO) {
           // items (64-channel block cb, horizontal tap bx): one activation box of the tile's rows + halo, then the
           // n_t weight slabs of the vertical taps a: K slab (a * n_t + bx) * c_blks + cb
           for (int cb = 0; cb < c_blks; ++cb) {
@@ -333,7 +402,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         uint32_t started = 0;
-        if constexpr (HALO) {
+        if constexpr (XF) {
+          for (int cb = 0; cb < p.c_blks; ++cb) {
+            mbar_wait_cluster(&xf_ready[ia], pa);  // both CTAs' transform warps have written the set's three boxes
+            tc_fence_after();
+            for (int bx = 0; bx < 3; ++bx) {
+              const uint32_t a_addr = smem_u32(smem + (ia * 3 + bx) * p.a_buf_bytes);
+              for (int g = 0; g < 3; ++g) {
+                mbar_wait(&full_b[ib], pb);
+                tc_fence_after();
+                mma_slab(tmem_d, a_addr + g * p.a_row_bytes, ib, started);
+                started = 1;
+                if (++ib == nb) { ib = 0; pb ^= 1; }
+              }
+            }
+            release_a(ia);
+            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+          }
+          for (int sb = 0; sb < p.skip_blks; sb += 3) {
+            const int n = min(3, p.skip_blks - sb);
+            mbar_wait_cluster(&xf_ready[ia], pa);
+            tc_fence_after();
+            for (int i = 0; i < n; ++i) {
+              mbar_wait(&full_b[ib], pb);
+              tc_fence_after();
+              mma_slab(tmem_d, smem_u32(smem + (ia * 3 + i) * p.a_buf_bytes), ib, started);
+              started = 1;
+              if (++ib == nb) { ib = 0; pb ^= 1; }
+            }
+            release_a(ia);
+            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+          }
+        } else if constexpr (HALO) {
           const int n_t = p.n_t;
           for (int i = 0; i < halo_items; ++i) {
             mbar_wait(&full_a[ia], pa);
@@ -372,6 +472,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // accumulator complete -> epilogue (of both CTAs in PAIR mode)
         if constexpr (PAIR) umma_commit_2sm_mcast(&tmem_full_bar[acc], 3);
         else umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (XF && warp >= 6) {
+    // ============================ GroupNorm + SiLU transform (XF only) ==============================
+    // 128 threads: thread -> (16-byte chunk j = 8 channels, pixel lane); per set: read the raw box (middle slot, as
+    // TMA wrote it: pixel row p at p * 128 B, chunk j at slot j ^ (p & 7)), y = silu(x * a + s) in fp32, bf16 again, and
+    // write the three operand boxes: dx = 0 in place, dx = -1 / +1 one pixel to the right / left in the two outer
+    // slots, with the column that has no source pixel and the rows outside the image written as ZERO (the
+    // convolution's padding — TMA's zero fill would turn into silu(s) otherwise).  Same formula and rounding as
+    // gn_apply_kernel, so the result is bit-identical to the unfused path.
+    if constexpr (XF) {
+      const int tt = static_cast<int>(threadIdx.x) - 192;
+      const int j = tt & 7, pl = tt >> 3;
+      const int W = p.W, wmask = p.W - 1, box_px = p.a_buf_bytes >> 7;
+      uint32_t ia = 0, pa = 0;
+      for (int work = cluster_id; work < p.num_work; work += num_clusters) {
+        const int tile_id = work / p.ksplit;
+        const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
+        const int y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
+        const bool tile_ok = m0 < p.M;   // the all-out-of-bounds tile of an odd tile count: no coefficients to read
+        const float* crow = p.gn_coef + (static_cast<size_t>(tile_ok ? b0 : 0) * p.gn_cstride + p.gn_c_off + j * 8) * 2;
+        for (int cb = 0; cb < p.c_blks; ++cb) {
+          // (scale, shift) of this thread's 8 channels, fetched while the box is in flight
+          const float4* cp = reinterpret_cast<const float4*>(crow + static_cast<size_t>(cb) * (TC_BK * 2));
+          const float4 k0 = __ldg(cp), k1 = __ldg(cp + 1), k2 = __ldg(cp + 2), k3 = __ldg(cp + 3);
+          const float ca[8] = {k0.x, k0.z, k1.x, k1.z, k2.x, k2.z, k3.x, k3.z};
+          const float cs[8] = {k0.y, k0.w, k1.y, k1.w, k2.y, k2.w, k3.y, k3.w};
+          mbar_wait(&full_a[ia], pa);
+          uint8_t* v0 = smem + (ia * 3) * p.a_buf_bytes;
+          uint8_t* v1 = v0 + p.a_buf_bytes;
+          uint8_t* v2 = v1 + p.a_buf_bytes;
+#pragma unroll 2
+          for (int px = pl; px < box_px; px += 16) {
+            const int r = px >> p.log2w, x = px & wmask;
+            const bool row_ok = static_cast<unsigned>(y0 - 1 + r) < static_cast<unsigned>(p.H);
+            const uint32_t off = static_cast<uint32_t>(px) * 128u + (static_cast<uint32_t>(j ^ (px & 7)) << 4);
+            const uint4 u = *reinterpret_cast<const uint4*>(v1 + off);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok) {
+              float v[8];
+              float2 f;
+              f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+              f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+              f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+              f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float y = fmaf(v[i], ca[i], cs[i]);
+                v[i] = p.gn_silu ? silu_f(y) : y;
+              }
+              o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                             pack_bf16x2(v[6], v[7]));
+            }
+            *reinterpret_cast<uint4*>(v1 + off) = o;
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            {  // dx = -1 box: operand pixel (r, x') = source pixel (r, x' - 1): this value lands at x + 1; column 0 is padding
+              const bool has = x + 1 < W;
+              const int q = has ? px + 1 : px - wmask;
+              *reinterpret_cast<uint4*>(v0 + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(j ^ (q & 7)) << 4)) =
+                  has ? o : zero;
+            }
+            {  // dx = +1 box: this value lands at x - 1; column W - 1 is padding
+              const bool has = x >= 1;
+              const int q = has ? px - 1 : px + wmask;
+              *reinterpret_cast<uint4*>(v2 + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(j ^ (q & 7)) << 4)) =
+                  has ? o : zero;
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive_release_cluster(&xf_ready[ia], 0);
+          if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+        }
+        // fused-skip sets hold raw slabs that go to the MMA untouched: just pass the TMA completion on
+        for (int sb = 0; sb < p.skip_blks; sb += 3) {
+          mbar_wait(&full_a[ia], pa);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_release_cluster(&xf_ready[ia], 0);
+          if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+        }
       }
     }
   } else {
@@ -689,20 +869,31 @@ int tc_num_sms() {
   return n;
 }
 
-template <int BN, int CL, bool PAIR, bool HALO>
+template <int BN, int CL, bool PAIR, bool HALO, bool XF = false>
 int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
               const CUtensorMap& ms1, TcParams p, cudaStream_t stream) {
   using Cfg = TcCfg<BN, PAIR>;
+  constexpr int SMEM = XF ? Cfg::SMEM_BYTES_XF : Cfg::SMEM_BYTES;
   static DeviceOnce configured;  // the attribute is per function AND per device
   if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CL, PAIR, HALO, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
-      set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", SMEM, cudaGetErrorString(e));
       return ERR_CUDA;
     }
     configured.done();
   }
-  if (!HALO) {
+  if (XF) {
+    // 2 sets x 3 boxes, the weight ring in what is left of the pool
+    p.a_pool_bytes = TC_XF_SETS * 3 * p.a_buf_bytes;
+    p.nb = (TC_XF_POOL - p.a_pool_bytes) / Cfg::B_BYTES_PAD;
+    if (p.nb > TC_XF_MAX_NB) p.nb = TC_XF_MAX_NB;
+    if (p.nb < 3 || p.a_buf_bytes < Cfg::A_BYTES) {
+      set_error("conv_tc: halo box of %d B leaves no room for the weight ring in GroupNorm-fused mode", p.a_buf_bytes);
+      return ERR_ARG;
+    }
+    p.na = TC_XF_SETS;
+  } else if (!HALO) {
     p.a_buf_bytes = Cfg::A_BYTES;
     p.na = Cfg::STAGES;
     p.a_row_bytes = 0;
@@ -717,8 +908,8 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
   const int clusters = p.num_work < max_clusters ? p.num_work : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters) * CL);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.blockDim = dim3(XF ? TC_THREADS_XF : TC_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -727,7 +918,7 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO>, ma0, ma1, mw, ms0, ms1, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO, XF>, ma0, ma1, mw, ms0, ms1, p);
   if (e != cudaSuccess) {
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
@@ -744,6 +935,9 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
 template <int BN, int CL, bool PAIR = false>
 int launch_tc(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mw, const CUtensorMap& ms0,
               const CUtensorMap& ms1, const TcParams& p, cudaStream_t stream) {
+  if constexpr (BN == 256 && PAIR) {
+    if (p.gn_coef != nullptr) return launch_tc_impl<BN, CL, PAIR, true, true>(ma0, ma1, mw, ms0, ms1, p, stream);
+  }
   return p.halo ? launch_tc_impl<BN, CL, PAIR, true>(ma0, ma1, mw, ms0, ms1, p, stream)
                 : launch_tc_impl<BN, CL, PAIR, false>(ma0, ma1, mw, ms0, ms1, p, stream);
 }
@@ -869,7 +1063,23 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
   int halo = 0, halo_na = 0, halo_bytes = 0;
   // (fused-skip slabs take a whole box-sized ring slot each: with many of them the shallower ring costs more than the
   //  halo saves — measured break-even near one skip slab per five tap slabs)
-  if (g_tc_halo_enabled && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
+  if (d->gn_coef != nullptr) {
+    // GroupNorm (+ SiLU) in the operand path: built on the CTA-pair halo pipeline with 256-wide channel tiles
+    plan.ksplit = 1;
+    plan.kb_per_split = taps * c_blks + skip_blks;
+    halo_bytes = (th + 2) * W * TC_BK * 2;
+    const bool geometry = d->ksize == 3 && d->tap_mode == 0 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + 2 &&
+                          halo_bytes % 1024 == 0;
+    STEDM_REQUIRE(geometry && plan.bn == 256 && plan.pair && ctot % TC_BK == 0 &&
+                      TC_XF_SETS * 3 * halo_bytes + 3 * (256 / 2) * TC_BK * 2 <= TC_XF_POOL,
+                  "conv_tc: gn_coef (GroupNorm in the operand path) needs a 3x3 convolution over whole-row tiles of one "
+                  "sample (W in 8..64, H >= rows per tile + 2), cout %% 256 == 0 and more than one pixel tile");
+    STEDM_REQUIRE(d->gn_cstride >= d->gn_c_off + ctot && d->gn_c_off % 8 == 0 && d->gn_cstride % 4 == 0,
+                  "conv_tc: gn_coef row of %d channels does not cover channels [%d, %d)", d->gn_cstride, d->gn_c_off,
+                  d->gn_c_off + ctot);
+    halo = 1;
+    halo_na = TC_XF_SETS;
+  } else if (g_tc_halo_enabled && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
       plan.ksplit == 1 && skip_blks * 5 <= taps * c_blks) {
     halo_bytes = (th + n_t - 1) * W * TC_BK * 2;
     const int stages = tc_stages(plan.bn, plan.pair);
@@ -928,8 +1138,9 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
     const int b1 = x1b > 0 ? x1b : B;
     const uint64_t dims[4] = {static_cast<uint64_t>(d->c1), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                               static_cast<uint64_t>(b1)};
-    const uint64_t str[3] = {static_cast<uint64_t>(d->c1) * 2, static_cast<uint64_t>(W) * d->c1 * 2,
-                             static_cast<uint64_t>(H) * W * d->c1 * 2};
+    const uint64_t ps1 = d->x1_pix_stride > 0 ? d->x1_pix_stride : d->c1;   // x1 as a channel slice, like x0
+    STEDM_REQUIRE(ps1 >= static_cast<uint64_t>(d->c1) && ps1 % 8 == 0, "conv_tc: bad x1 pixel stride %d", d->x1_pix_stride);
+    const uint64_t str[3] = {ps1 * 2, static_cast<uint64_t>(W) * ps1 * 2, static_cast<uint64_t>(H) * W * ps1 * 2};
     const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), abox_h, static_cast<uint32_t>(tb)};
     int rc = make_tmap_bf16(&ma1, d->x1, 4, dims, str, box);
     if (rc) return rc;
@@ -1001,6 +1212,9 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
                   d->res_batch, B);
     p.res_rows = d->res_batch * H * W;
   }
+  p.gn_coef = d->gn_coef; p.gn_cstride = d->gn_cstride; p.gn_c_off = d->gn_c_off; p.gn_silu = d->gn_silu;
+  p.nb = 0; p.a_pool_bytes = 0; p.log2w = 0;
+  while ((1 << p.log2w) < W) ++p.log2w;
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {
     STEDM_REQUIRE(bn >= 64 && d->cout % bn == 0 && d->out_nchw == 0 && (H * W) % TC_BM == 0,

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
     const int g = c / cpg;
     const float a = s_mr[g * 2 + 1] * gamma[c];
     s_ab[c] = a;
-    s_ab[C + c] = beta[c] - s_mr[g * 2] * a;
+    s_ab[C + c] = fmaf(-s_mr[g * 2], a, beta[c]);
   }
   __syncthreads();
   // thread -> (pixel lane, channel item): no integer division in the streaming loop, the item's scale/shift
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
       for (int u = 0; u < GN_MLP; ++u) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float y = v[u][j] * a[j] + sh[j];
+          float y = fmaf(v[u][j], a[j], sh[j]);
           if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
           v[u][j] = y;
         }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
       load8<TI>(src + static_cast<size_t>(p) * src_stride, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float y = v[j] * a[j] + sh[j];
+        float y = fmaf(v[j], a[j], sh[j]);
         if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
         v[j] = y;
       }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_bulk_kernel(
     const int g = c / cpg;
     const float a = s_mr[g * 2 + 1] * gamma[c];
     s_ab[c] = a;
-    s_ab[C + c] = beta[c] - s_mr[g * 2] * a;
+    s_ab[C + c] = fmaf(-s_mr[g * 2], a, beta[c]);
   }
   __syncthreads();
 
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_bulk_kernel(
           f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float y = v[j] * a[j] + sh[j];
+            const float y = fmaf(v[j], a[j], sh[j]);
             v[j] = apply_silu ? silu_f(y) : y;
           }
           store8<__nv_bfloat16>(dst + static_cast<size_t>(q) * C, v);
@@ -358,7 +358,12 @@ struct FoldSrc {
 // a fixed order.  (The first version walked tiles with 16 lanes per output: 4-byte loads 1 KB apart, 18 us per launch
 // x 38 launches = 3.6 % of a guided step.)
 constexpr int FOLD_THREADS = 256;
-__global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out) {
+__global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, int hw,
+                                                                     float2* __restrict__ coef) {
+  __shared__ double s_tot[2 * GN_GROUPS];
+  __shared__ float s_mr[2 * GN_GROUPS];
   extern __shared__ double fold_sm[];  // [tile lanes][C][2]
   const int b = blockIdx.x;
   const int C = s0.c + s1.c, cpg = C / GN_GROUPS;
@@ -392,7 +397,29 @@ __global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0,
     for (int t = 0; t < TL; ++t) acc += fold_sm[(static_cast<size_t>(t) * C + g * cpg + cc) * 2 + which];
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // fixed tree: deterministic
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (sub == 0) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which] = acc;
+  if (sub == 0) {
+    if (out != nullptr) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which] = acc;
+    s_tot[o] = acc;
+  }
+  if (coef == nullptr) return;
+  // Per-(sample, channel) scale / shift for consumers that apply the normalisation in their own operand path
+  // (stedm_conv_desc.gn_coef): the SAME arithmetic, in the same precision, as gn_apply_kernel's prologue, so a fused
+  // consumer is bit-identical to gn_apply + plain consumer.
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const double n = static_cast<double>(hw) * cpg;
+    const double mean = s_tot[threadIdx.x * 2] / n;
+    double var = s_tot[threadIdx.x * 2 + 1] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mr[threadIdx.x * 2] = static_cast<float>(mean);
+    s_mr[threadIdx.x * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += FOLD_THREADS) {
+    const int gg = c / cpg;
+    const float a = s_mr[gg * 2 + 1] * gamma[c];
+    coef[static_cast<size_t>(b) * C + c] = make_float2(a, fmaf(-s_mr[gg * 2], a, beta[c]));
+  }
 }
 
 int apply_pix_per_block(int batch, int hw, int C) {
@@ -440,8 +467,10 @@ extern "C" int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int 
 
 extern "C" int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long long rep_stride0, int tps0, int batch0,
                                    const float* tiles1, int c1, int reps1, long long rep_stride1, int tps1, int batch1,
-                                   int batch, double* out, void* stream) {
-  STEDM_REQUIRE(tiles0 && out && (c1 == 0 || tiles1), "gn_fold_tiles: null pointer");
+                                   int batch, double* out, const float* gamma, const float* beta, float eps, int hw,
+                                   float* coef, void* stream) {
+  STEDM_REQUIRE(tiles0 && (out || coef) && (c1 == 0 || tiles1), "gn_fold_tiles: null pointer");
+  STEDM_REQUIRE(coef == nullptr || (gamma && beta && hw > 0), "gn_fold_tiles: coefficients need gamma, beta and hw");
   STEDM_REQUIRE(batch > 0 && c0 > 0 && (c0 + c1) % GN_GROUPS == 0 && reps0 > 0 && tps0 > 0 && batch0 > 0 &&
                     (c1 == 0 || (reps1 > 0 && tps1 > 0 && batch1 > 0)),
                 "gn_fold_tiles: bad shape");
@@ -451,7 +480,8 @@ extern "C" int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long 
   const int tile_lanes = FOLD_THREADS / (C < FOLD_THREADS ? C : FOLD_THREADS);
   const size_t smem = static_cast<size_t>(tile_lanes) * C * 2 * sizeof(double);
   STEDM_REQUIRE(smem <= 48 * 1024, "gn_fold_tiles: %d channels exceed the shared-memory fold buffer", C);
-  gn_fold_tiles_kernel<<<batch, FOLD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(s0, s1, out);
+  gn_fold_tiles_kernel<<<batch, FOLD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      s0, s1, out, gamma, beta, eps, hw, reinterpret_cast<float2*>(coef));
   return check_launch("gn_fold_tiles");
 }
 

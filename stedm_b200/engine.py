@@ -180,11 +180,23 @@ class PackedConv:
                                     pad=PAD_TC)
         return self._twin
 
+    def gn_fusable(self, x0, x1=None, skip=None):
+        """Can this call run with the GroupNorm (+ SiLU) of its input applied inside the kernel (ops.conv gn_coef)?"""
+        if not (self.tc and self.ksize == 3 and self.stride == 1 and self.tc_ok(x0, x1)):
+            return False
+        b, h, w_, c0 = x0.shape
+        cin = c0 + (0 if x1 is None else x1.shape[-1])
+        skip_c = 0 if skip is None else skip[0].shape[-1] + (0 if skip[1] is None else skip[1].shape[-1])
+        return cin % PAD_TC == 0 and ops.conv_gn_fusable(b, h, w_, cin, self.cout, skip_c)
+
     def __call__(self, x0, x1=None, emb=None, residual=None, out_dtype=None, upsample=False, out_nchw=False,
-                 want_stats=False, skip=None):
+                 want_stats=False, skip=None, gn=None):
+        """``gn`` = (coef table, silu): x0 / x1 are the raw inputs of a GroupNorm applied in the kernel's operand path
+        (only after gn_fusable() said yes)."""
         out_dtype = out_dtype or self.prec.act
+        gkw = {} if gn is None else dict(gn_coef=gn[0], gn_silu=gn[1])
         if self.tc and not self.tc_ok(x0, x1):
-            assert skip is None, "callers check tc_ok() before asking for the fused skip convolution"
+            assert skip is None and gn is None, "callers check tc_ok() before asking for a fused skip / GroupNorm"
             out = self._simt_twin()(x0, x1, emb=emb, residual=residual, out_dtype=out_dtype, upsample=upsample,
                                     out_nchw=out_nchw)
             out._gn_tiles = None
@@ -193,10 +205,11 @@ class PackedConv:
             assert self.tc and getattr(self, "has_skip", False) and not upsample and self.stride == 1
             tiles, meta = self._tile_stats(x0, want_stats)
             out = ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
-                           out_dtype=out_dtype, tensor_core=True, stats_out=tiles, skip_x0=skip[0], skip_x1=skip[1])
+                           out_dtype=out_dtype, tensor_core=True, stats_out=tiles, skip_x0=skip[0], skip_x1=skip[1], **gkw)
             out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
             return out
         if self.tc:
+            assert gn is None or (self.stride == 1 and not upsample and not out_nchw)
             if self.stride == 2:
                 assert x1 is None and self.ksize == 3
                 cols = ops.im2col_3x3_s2(x0)            # [B, H/2, W/2, 9*C]: Downsample as a plain GEMM
@@ -221,9 +234,10 @@ class PackedConv:
             tiles, meta = self._tile_stats(x0, want_stats and not out_nchw)
             out = ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
                            out_dtype=out_dtype, tensor_core=True, out_nchw=out_nchw,
-                           cout_store=self.cout_real if out_nchw else 0, stats_out=tiles)
+                           cout_store=self.cout_real if out_nchw else 0, stats_out=tiles, **gkw)
             out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
             return out
+        assert gn is None
         return ops.conv(x0, self.weight, self.bias, self.cout, self.ksize, x1=x1, emb=emb, residual=residual,
                         out_dtype=out_dtype, stride=self.stride, upsample=upsample, out_nchw=out_nchw,
                         tensor_core=False)
@@ -234,6 +248,16 @@ class PackedNorm:
         self.gamma = gn.weight.detach().float().contiguous()
         self.beta = gn.bias.detach().float().contiguous()
         self.eps = eps
+
+    def coefs(self, x0, x1):
+        """Per-(sample, channel) (scale, shift) table of this GroupNorm over [x0 | x1] for a consumer convolution that
+        normalises in its own operand path; None unless the statistics of every source came out of its producer's
+        epilogue (the same condition under which __call__ skips the statistics pass)."""
+        t0 = getattr(x0, "_gn_tiles", None)
+        t1 = getattr(x1, "_gn_tiles", None) if x1 is not None else None
+        if t0 is None or (x1 is not None and t1 is None):
+            return None
+        return ops.gn_fold_tiles(t0, t1, x0.shape[0], coef_for=(self.gamma, self.beta, self.eps, x0.shape[1] * x0.shape[2]))
 
     def __call__(self, x0, x1, silu, out_dtype, stats):
         t0 = getattr(x0, "_gn_tiles", None)
@@ -288,9 +312,34 @@ class PackedResBlock:
         sp = _round_up(_round_up(c0, cpg), PAD_TC)
         return sp if c0 + c1 - sp >= SPLIT_MIN_SHARED else 0
 
-    def __call__(self, x0, x1, emb, pool):
-        a = self.n1(x0, x1, True, self.prec.act, pool.next())
+    def _conv1(self, x0, x1, emb, pool):
+        """conv1(SiLU(GN([x0 | x1]))) + emb, with the fold / split / fusion choices of the tensor-core path."""
         sp = self._split_point(x0, x1)
+        c0 = x0.shape[-1]
+        # GroupNorm + SiLU inside the convolution's operand path: needs the producers' tile statistics and a shape the
+        # kernel takes (both launches of a split must qualify)
+        coef = None
+        if self.c1.tc and ops.GN_FUSION[0]:
+            if sp:      # shared channels [sp, C) at the skip's batch, the rest at the full batch
+                b, h_, w_, _ = x0.shape
+                ok = (ops.conv_gn_fusable(x1.shape[0], h_, w_, c0 + x1.shape[-1] - sp, self.c1.cout) and
+                      ops.conv_gn_fusable(b, h_, w_, sp, self.c1.cout))
+            else:
+                ok = self.c1.gn_fusable(x0, x1)
+            coef = self.n1.coefs(x0, x1) if ok else None
+        if coef is not None:
+            if not sp:
+                return self.c1(x0, x1, emb=emb, want_stats=True, gn=(coef, True))
+            bs = x1.shape[0]
+            w_lo, w_hi = self.c1.split_weights(sp)
+            part = ops.conv(x1[:, :, :, sp - c0:], w_hi, None, self.c1.cout, 3, out_dtype=torch.float32,
+                            tensor_core=True, gn_coef=coef, gn_c_off=sp)
+            tiles, meta = self.c1._tile_stats(x0, True)
+            h = ops.conv(x0, w_lo, self.c1.bias, self.c1.cout, 3, x1=x1[:, :, :, :sp - c0] if sp > c0 else None, emb=emb,
+                         residual=part, out_dtype=self.prec.act, tensor_core=True, stats_out=tiles, gn_coef=coef)
+            h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
+            return h
+        a = self.n1(x0, x1, True, self.prec.act, pool.next())
         if sp:
             bs = x1.shape[0]
             w_lo, w_hi = self.c1.split_weights(sp)
@@ -301,17 +350,26 @@ class PackedResBlock:
             h = ops.conv(a[..., :sp], w_lo, self.c1.bias, self.c1.cout, 3, emb=emb, residual=part,
                          out_dtype=self.prec.act, tensor_core=True, stats_out=tiles)
             h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
-        else:
-            h = self.c1(a, emb=emb, want_stats=True)
-        a = self.n2(h, None, True, self.prec.act, pool.next())
-        if self.fused_skip and self.c2.tc_ok(a):
-            return self.c2(a, want_stats=True, skip=(x0, x1))
+            return h
+        return self.c1(a, emb=emb, want_stats=True)
+
+    def __call__(self, x0, x1, emb, pool):
+        h = self._conv1(x0, x1, emb, pool)
+        fused = self.fused_skip and self.c2.tc_ok(h)
+        skip = (x0, x1) if fused else None
+        coef = None
+        if self.c2.tc and ops.GN_FUSION[0] and self.c2.gn_fusable(h, None, skip):
+            coef = self.n2.coefs(h, None)
+        gn = None if coef is None else (coef, True)
+        a = h if gn is not None else self.n2(h, None, True, self.prec.act, pool.next())
+        if fused:
+            return self.c2(a, want_stats=True, skip=skip, gn=gn)
         if self.skip is not None:
             xs = self.skip(x0, x1)
         else:
             assert x1 is None
             xs = x0
-        return self.c2(a, residual=xs, want_stats=True)
+        return self.c2(a, residual=xs, want_stats=True, gn=gn)
 
 
 class UNetRunner:

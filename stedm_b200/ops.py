@@ -5,6 +5,7 @@ libstedm_b200.so and raises if the library is missing or the tensors are not CUD
 Activations are NHWC; ``F32``/``BF16`` tags follow include/stedm_b200.h.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -103,18 +104,25 @@ def gn_stats(x0, x1, stats=None):
     return stats
 
 
-def gn_fold_tiles(src0, src1, batch, out=None):
+def gn_fold_tiles(src0, src1, batch, out=None, coef_for=None):
     """Fold the per-tile statistics written by the producing convolutions (conv(..., stats_out=...)) into the
     per-sample GroupNorm partials [batch, 1, 32, 2] (double).  src = (tiles fp32 [reps*rep_stride, c, 2], c, reps,
-    rep_stride, tiles_per_sample, batch_of_source); src1 = None for a single-source input."""
-    if out is None:
-        out = torch.empty((batch, 1, 32, 2), device=src0[0].device, dtype=torch.float64)
+    rep_stride, tiles_per_sample, batch_of_source); src1 = None for a single-source input.
+
+    ``coef_for`` = (gamma, beta, eps, hw): instead of the partials, return the per-(sample, channel) (scale, shift)
+    table fp32 [batch, c0+c1, 2] a consumer convolution applies in its own operand path (conv(..., gn_coef=...))."""
     t1, c1, r1, rs1, tps1, b1 = src1 if src1 is not None else (None, 0, 1, 0, 1, 1)
     t0, c0, r0, rs0, tps0, b0 = src0
-    _cuda(t0, t1, out)
+    coef, gamma, beta, eps, hw = None, None, None, 0.0, 0
+    if coef_for is not None:
+        gamma, beta, eps, hw = coef_for
+        coef = torch.empty((batch, c0 + c1, 2), device=t0.device, dtype=torch.float32)
+    elif out is None:
+        out = torch.empty((batch, 1, 32, 2), device=t0.device, dtype=torch.float64)
+    _cuda(t0, t1, out, gamma, beta)
     _call("stedm_gn_fold_tiles", _ptr(t0), c0, r0, rs0, tps0, b0, _ptr(t1), c1, r1, rs1, tps1, b1, batch, _ptr(out),
-          _stream())
-    return out
+          _ptr(gamma), _ptr(beta), float(eps), int(hw), _ptr(coef), _stream())
+    return coef if coef_for is not None else out
 
 
 def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
@@ -137,20 +145,27 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0, skip_x0=None, skip_x1=None):
+         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
-    [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout])."""
-    x0_pix_stride = 0
-    if x0.is_cuda and not x0.is_contiguous():
-        # a channel slice a[..., lo:hi] of a wider NHWC tensor: same pixels, stride(2) channels apart
-        bb, hh, ww, cc = x0.shape
-        ps = x0.stride(2)
-        assert x0.stride(3) == 1 and ps >= cc and x0.stride(1) == ww * ps and x0.stride(0) == hh * ww * ps, x0.stride()
+    [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout]).
+
+    ``gn_coef`` (fp32 [samples, C_norm, 2] from gn_fold_tiles(coef_for=...)): x0 / x1 are the RAW inputs of a GroupNorm
+    (+ SiLU when ``gn_silu``) whose channel ``gn_c_off`` is this convolution's input channel 0; the normalisation runs
+    inside the kernel's operand path (only shapes conv_gn_fusable() accepts)."""
+    def _slice_stride(x):
+        """A channel slice a[..., lo:hi] of a wider NHWC tensor (same pixels, stride(2) channels apart) -> pixel stride."""
+        if x is None or not x.is_cuda or x.is_contiguous():
+            return 0
+        bb, hh, ww, cc = x.shape
+        ps = x.stride(2)
+        assert x.stride(3) == 1 and ps >= cc and x.stride(1) == ww * ps and x.stride(0) == hh * ww * ps, x.stride()
         assert tensor_core, "channel-slice inputs are a tensor-core path feature"
-        x0_pix_stride = ps
-        _cuda(x1, weight, bias, residual, skip_x0, skip_x1)      # x0 itself: CUDA, strided as checked above
-    else:
-        _cuda(x0, x1, weight, bias, residual, skip_x0, skip_x1)
+        return ps
+    x0_pix_stride, x1_pix_stride = _slice_stride(x0), _slice_stride(x1)
+    # strided sources were checked above; everything else must be contiguous CUDA memory
+    _cuda(None if x0_pix_stride else x0, None if x1_pix_stride else x1, weight, bias, residual, skip_x0, skip_x1, gn_coef)
+    if not x0.is_cuda or (x1 is not None and not x1.is_cuda):
+        raise RuntimeError("stedm_b200 ops take CUDA tensors only (no CPU fallback)")
     if emb is not None:  # a column slice of the stacked embedding table: rows strided, columns dense
         assert emb.is_cuda and emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] == cout
         assert emb.shape[0] in (1, x0.shape[0])          # one row per sample, or one row broadcast to all samples
@@ -176,7 +191,11 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     d.cout_store = cout_store if out_nchw else 0
     d.tap_mode, d.phase = (0, 0) if up_phase is None else (1, up_phase)
     d.act = act
-    d.x0_pix_stride = x0_pix_stride
+    d.x0_pix_stride, d.x1_pix_stride = x0_pix_stride, x1_pix_stride
+    if gn_coef is not None:
+        assert tensor_core and gn_coef.dtype == torch.float32 and gn_coef.dim() == 3 and gn_coef.shape[2] == 2
+        assert gn_coef.shape[0] >= b and gn_coef.shape[1] >= gn_c_off + c0 + c1, (gn_coef.shape, b, gn_c_off, c0, c1)
+        d.gn_coef, d.gn_cstride, d.gn_c_off, d.gn_silu = _ptr(gn_coef), gn_coef.shape[1], gn_c_off, 1 if gn_silu else 0
     if residual is not None and residual.shape[0] != b:   # broadcast residual (b % res_batch), tensor-core path
         assert tensor_core and b % residual.shape[0] == 0 and residual.shape[1:] == (oh, ow, cout)
         d.res_batch = residual.shape[0]
@@ -188,7 +207,7 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
         d.skip_x1_batch = 0 if skip_x1 is None or skip_x1.shape[0] == b else skip_x1.shape[0]
         skip_c = d.skip_c0 + d.skip_c1
     out._stats_written = stats_out is not None
-    if tensor_core and SPLIT_K[0] and b * h * w <= SPLITK_MAX_PIXELS:
+    if tensor_core and SPLIT_K[0] and gn_coef is None and b * h * w <= SPLITK_MAX_PIXELS:
         # small launches (few output tiles, deep K): split-K over the idle SMs through a caller-owned workspace.
         # The fused GroupNorm statistics need the single-pass epilogue, so they are dropped for such launches and
         # the consumer falls back to the separate statistics kernel (tensors this small cost nothing to re-read).
@@ -210,6 +229,28 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
             (weight.shape, cout, ksize, c0, c1)
         _call("stedm_conv_simt", C.byref(d), _stream())
     return out
+
+
+_GN_FUSABLE = {}
+GN_FUSION = [os.environ.get("STEDM_GN_FUSION", "1") != "0"]   # A/B switch: GroupNorm + SiLU inside the consumer convolution's operand path
+
+
+def conv_gn_fusable(batch, h, w, cin, cout, skip_c=0):
+    """Does stedm_conv_tc take a 3x3 convolution of this shape with GroupNorm applied in its operand path?  Asked of
+    the library's own planner (stedm_conv_tc_plan with gn_coef set) once per shape."""
+    if not GN_FUSION[0] or SPLIT_K[0]:
+        return False
+    key = (batch, h, w, cin, cout, skip_c)
+    ok = _GN_FUSABLE.get(key)
+    if ok is None:
+        d = ConvDesc()
+        d.c0, d.c1, d.in_dtype, d.batch, d.in_h, d.in_w = cin, 0, BF16, batch, h, w
+        d.ksize, d.stride, d.cout, d.out_dtype = 3, 1, cout, BF16
+        d.skip_c0, d.skip_x0 = skip_c, (1 if skip_c else 0)
+        d.gn_coef, d.gn_cstride, d.gn_silu = 1, cin, 1
+        out8 = (C.c_int32 * 8)()
+        ok = _GN_FUSABLE[key] = _lib.load().stedm_conv_tc_plan(C.byref(d), out8) == 0
+    return ok
 
 
 def gemm_simt(a, b, c, m, n, k, lda, ldb, ldc, b_is_nk, nb, nh, a_strides, b_strides, c_strides, alpha=1.0,

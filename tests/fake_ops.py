@@ -50,8 +50,35 @@ def gn_stats(x0, x1, stats=None):
     return None
 
 
-def gn_fold_tiles(src0, src1, batch, out=None):
-    return None
+GN_FUSION = [True]
+
+
+def conv_gn_fusable(batch, h, w, cin, cout, skip_c=0):
+    """Mirror of the kernel's rule (stedm_conv_tc_plan with gn_coef set): 256-wide channel tiles, whole-row pixel tiles
+    of one sample with room for the halo rows, more than one pixel tile."""
+    if not GN_FUSION[0] or cout % 256 or w < 8 or w > 32 or 128 % w:
+        return False
+    th = 128 // w
+    return th >= 2 and h % th == 0 and h >= th + 2 and batch * h * w > 128
+
+
+def gn_fold_tiles(src0, src1, batch, out=None, coef_for=None):
+    """The stand-in keeps no tile sums: the producers' outputs ride along on the tile buffers (conv sets ``_fake_src``)
+    and the per-(sample, channel) coefficients are computed from them directly."""
+    if coef_for is None:
+        return None
+    gamma, beta, eps, hw = coef_for
+    x = src0[0]._fake_src.float()
+    if src1 is not None:
+        x = torch.cat([x, _bcast(src1[0]._fake_src.float(), x.shape[0])], -1)
+    b, c = x.shape[0], x.shape[-1]
+    assert b == batch and x.shape[1] * x.shape[2] == hw
+    g = x.reshape(b, -1, 32, c // 32)
+    mean = g.mean(dim=(1, 3))
+    rstd = (g.var(dim=(1, 3), unbiased=False) + eps).rsqrt()
+    a = rstd.repeat_interleave(c // 32, 1) * gamma[None]
+    sh = beta[None] - mean.repeat_interleave(c // 32, 1) * a
+    return torch.stack([a, sh], -1).contiguous()
 
 
 def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
@@ -72,9 +99,27 @@ def im2col_3x3_s2(x):
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0, skip_x0=None, skip_x1=None):
+         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True):
+    y = _conv(x0, weight, bias, cout, ksize, x1=x1, emb=emb, residual=residual, out_dtype=out_dtype, stride=stride,
+              upsample=upsample, out_nchw=out_nchw, tensor_core=tensor_core, out=out, cout_store=cout_store,
+              up_phase=up_phase, act=act, skip_x0=skip_x0, skip_x1=skip_x1, gn_coef=gn_coef, gn_c_off=gn_c_off,
+              gn_silu=gn_silu)
+    if stats_out is not None and not out_nchw:
+        stats_out._fake_src = y          # what the epilogue's tile statistics describe
+        y._stats_written = True
+    return y
+
+
+def _conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
+          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None,
+          act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True):
     x = x0 if x1 is None else torch.cat([x0, _bcast(x1, x0.shape[0])], -1)
     cin = x.shape[-1]
+    if gn_coef is not None:   # GroupNorm (+ SiLU) in the operand path: fp32 math, operand rounded to the input dtype
+        assert tensor_core and ksize == 3 and conv_gn_fusable(x.shape[0], x.shape[1], x.shape[2], cin, cout)
+        co = gn_coef[:x.shape[0], gn_c_off:gn_c_off + cin]
+        xn = x.float() * co[:, None, None, :, 0] + co[:, None, None, :, 1]
+        x = (F.silu(xn) if gn_silu else xn).to(x0.dtype)
     y_skip = None
     if skip_x0 is not None:    # fused 1x1 skip conv: its weights are the trailing K columns
         sk = skip_x0 if skip_x1 is None else torch.cat([skip_x0, _bcast(skip_x1, skip_x0.shape[0])], -1)

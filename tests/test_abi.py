@@ -22,12 +22,12 @@ def test_library_exports_header_symbols():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
     lib.stedm_abi_version.restype = ctypes.c_int
-    assert lib.stedm_abi_version() == 2
+    assert lib.stedm_abi_version() == 3
 
 
 def test_conv_desc_layout_matches_header():
     from stedm_b200._lib import ConvDesc
-    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 22 * 4 + 2 * 8 + 2 * 4  # 9 ptrs, int64, 22 int32, 2 ptrs, 2 int32
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 8 + 22 * 4 + 2 * 8 + 6 * 4 + 8  # 9 ptrs, int64, 22 int32, 2 ptrs, 6 int32, 1 ptr
 
 
 def test_sass_is_blackwell_native():

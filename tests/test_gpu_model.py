@@ -241,6 +241,40 @@ def test_bench_geometry_b64_l64_rows_equal_b4_golden_run():
     assert r < BF16_EPS_BAR, r
 
 
+@pytest.mark.parametrize("L,B", [(64, 4), (32, 2)])
+def test_groupnorm_in_operand_path_is_bit_identical_to_separate_apply(L, B):
+    """A guided DDIM step with GroupNorm + SiLU applied inside the consumer convolutions (ops.GN_FUSION, every site the
+    kernel takes: 16x16 / 32x32 maps with >= 256 output channels) equals the step with the separate apply kernel, bit
+    for bit — eps, x_prev and pred_x0."""
+    from stedm_b200 import ops
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    m = build_model(L, n_style=1, precision="bf16")
+    gen = torch.Generator().manual_seed(L + B)
+    x = torch.randn(B, 3, L, L, generator=gen).cuda()
+    cc = torch.randn(B, 3, L, L, generator=gen).cuda()
+    c = {"c_concat": [cc], "c_crossattn": [torch.randn(B, 512, generator=gen).cuda()]}
+    u = {"c_concat": [cc], "c_crossattn": [torch.randn(B, 512, generator=gen).cuda()]}
+    ts = torch.full((B,), 481, dtype=torch.long, device="cuda")
+
+    def run(flag):
+        saved = ops.GN_FUSION[0]
+        ops.GN_FUSION[0] = flag
+        try:
+            n0 = ops.LAUNCHES[0]
+            s = DDIMSampler(m._model, use_cuda_graph=False)
+            s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+            out = s.p_sample_ddim(x, c, ts, index=24, unconditional_guidance_scale=1.5, unconditional_conditioning=u)
+            return out, ops.LAUNCHES[0] - n0
+        finally:
+            ops.GN_FUSION[0] = saved
+
+    (xf, pf), n_f = run(True)
+    (xu, pu), n_u = run(False)
+    print(f"L={L} B={B}: {n_u} launches with separate GroupNorm apply, {n_f} with the fused operand path")
+    assert torch.equal(xf, xu) and torch.equal(pf, pu)
+    assert n_f < n_u
+
+
 def test_cuda_graph_sampler_matches_eager():
     g, _, _, x_T = _small_inputs()
     m = build_model(32, n_style=2, precision="bf16")

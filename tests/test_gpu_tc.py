@@ -282,3 +282,118 @@ def test_conv_tc_channel_slice_input_and_broadcast_residual(ops):
     assert max_abs(nchw(got.cpu()), want) < 3e-3, max_abs(nchw(got.cpu()), want)
     whole = ops.conv(a, tc_w(w).cuda(), b.cuda(), co, 3, out_dtype=torch.float32, tensor_core=True)
     assert max_abs(got, whole) < 1e-4                                 # only the fp32 summation order differs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GroupNorm + SiLU inside the convolution's operand path (stedm_conv_desc.gn_coef)
+# ---------------------------------------------------------------------------------------------------------------------
+def _tile_sums(x_nhwc_bf16):
+    """What a producer's epilogue writes: fp32 (sum, sum of squares) per (128-pixel tile, channel) of its bf16 output."""
+    b, h, w, c = x_nhwc_bf16.shape
+    t = x_nhwc_bf16.float().reshape(b * h * w // 128, 128, c)
+    tiles = torch.stack([t.sum(1), (t * t).sum(1)], -1).contiguous()
+    return (tiles.cuda(), c, 1, tiles.shape[0], h * w // 128, b)
+
+
+GN_CASES = [
+    # B, H, W, c0, c1, x1 batch, cout, silu
+    (4, 16, 16, 1024, 0, 0, 1024, True),     # the U-Net's deep layers: 16x8 tiles + 2 halo rows, 16 channel blocks
+    (2, 32, 32, 512, 0, 0, 512, True),       # 32x4 tiles, 24 KB boxes
+    (4, 16, 16, 512, 256, 2, 512, True),     # concat with a broadcast second source; 24-channel groups straddle blocks
+    (3, 16, 16, 256, 0, 0, 256, False),      # no SiLU, odd sample count
+    (1, 24, 16, 128, 0, 0, 256, True),       # three tiles: the pair's second tile is all out of bounds
+]
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,xb,cout,silu", GN_CASES)
+def test_conv_tc_groupnorm_in_operand_path_is_bit_equal_to_apply_then_conv(ops, B, H, W, c0, c1, xb, cout, silu):
+    """conv(x, gn_coef=...) == conv(gn_apply(x)) bit for bit (same formula, same bf16 rounding, same K order), and both
+    match torch's fp32 GroupNorm + SiLU + conv of the same bf16 operands."""
+    g = torch.Generator().manual_seed(B * 1000 + c0 + c1)
+    C = c0 + c1
+    x0 = (torch.randn(B, H, W, c0, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    x1 = (torch.randn(xb, H, W, c1, generator=g) * 0.7 - 1).to(torch.bfloat16) if c1 else None
+    w = bf(torch.randn(cout, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    bias, emb = torch.randn(cout, generator=g), torch.randn(B, cout, generator=g)
+    res = torch.randn(B, H, W, cout, generator=g).to(torch.bfloat16)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    s0, s1 = _tile_sums(x0), (_tile_sums(x1) if c1 else None)
+    assert ops.conv_gn_fusable(B, H, W, C, cout)
+    coef = ops.gn_fold_tiles(s0, s1, B, coef_for=(gamma.cuda(), beta.cuda(), 1e-5, H * W))
+    folded = ops.gn_fold_tiles(s0, s1, B)
+    x0d, x1d = x0.cuda(), (x1.cuda() if c1 else None)
+    a = ops.gn_apply(x0d, x1d, folded, gamma.cuda(), beta.cuda(), 1e-5, silu, torch.bfloat16, n_chunks=1)
+    kw = dict(emb=emb.cuda(), residual=res.cuda(), out_dtype=torch.bfloat16, tensor_core=True)
+    m_tiles = B * H * W // 128
+    t_ref, t_fus = torch.zeros((m_tiles, cout, 2), device="cuda"), torch.zeros((m_tiles, cout, 2), device="cuda")
+    ref = ops.conv(a, tc_w(w).cuda(), bias.cuda(), cout, 3, stats_out=t_ref, **kw)
+    fus = ops.conv(x0d, tc_w(w).cuda(), bias.cuda(), cout, 3, x1=x1d, stats_out=t_fus, gn_coef=coef, gn_silu=silu, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, fus), float((ref.float() - fus.float()).abs().max())
+    assert torch.equal(t_ref, t_fus)
+    # and against torch: GroupNorm in fp32 on the bf16 inputs, operand rounded to bf16, fp32 convolution
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float().repeat(B // xb, 1, 1, 1)], -1)
+    n = F.group_norm(xin.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    n = bf(F.silu(n) if silu else n)
+    want = F.conv2d(n, w, bias, padding=1) + emb[:, :, None, None] + res.float().permute(0, 3, 1, 2)
+    err = max_abs(nchw(fus.float().cpu()), want)
+    assert err < 0.06 * max(1.0, float(want.abs().max()) / 8), err
+
+
+def test_conv_tc_groupnorm_in_operand_path_with_fused_skip_and_channel_slices(ops):
+    """The ResBlock tail conv3x3(SiLU(GN(h))) + skip1x1([x0 | x1]) with the normalisation in the kernel (the raw skip slabs
+    ride in the same ring, three per set), and the split [h | skip] form: x1 as a channel SLICE of the skip tensor with a
+    coefficient-table offset (gn_c_off) for the shared part."""
+    g = torch.Generator().manual_seed(77)
+    B, Bs, hw, cm, co = 4, 2, 16, 512, 512
+    h = (torch.randn(B, hw, hw, cm, generator=g) * 1.5).to(torch.bfloat16)
+    k0 = torch.randn(B, hw, hw, 192, generator=g).to(torch.bfloat16)
+    k1 = torch.randn(Bs, hw, hw, 64, generator=g).to(torch.bfloat16)
+    w3 = bf(torch.randn(co, cm, 3, 3, generator=g) / math.sqrt(9 * cm))
+    w1 = bf(torch.randn(co, 256, 1, 1, generator=g) / 16)
+    bias = torch.randn(co, generator=g)
+    gamma, beta = torch.randn(cm, generator=g), torch.randn(cm, generator=g)
+    sh = _tile_sums(h)
+    coef = ops.gn_fold_tiles(sh, None, B, coef_for=(gamma.cuda(), beta.cuda(), 1e-5, hw * hw))
+    a = ops.gn_apply(h.cuda(), None, ops.gn_fold_tiles(sh, None, B), gamma.cuda(), beta.cuda(), 1e-5, True,
+                     torch.bfloat16, n_chunks=1)
+    wcat = torch.cat([tc_w(w3), tc_w(w1)], 1).contiguous().cuda()
+    assert ops.conv_gn_fusable(B, hw, hw, cm, co, 256)
+    kw = dict(out_dtype=torch.float32, tensor_core=True, skip_x0=k0.cuda(), skip_x1=k1.cuda())
+    ref = ops.conv(a, wcat, bias.cuda(), co, 3, **kw)
+    fus = ops.conv(h.cuda(), wcat, bias.cuda(), co, 3, gn_coef=coef, **kw)
+    assert torch.equal(ref, fus), float((ref - fus).abs().max())
+    # split concat: GN over [h (512) | s (512, Bs samples)], shared channels [sp, 1024) convolved once per distinct sample
+    s = (torch.randn(Bs, hw, hw, 512, generator=g) + 0.3).to(torch.bfloat16)
+    C, sp = 1024, 576           # 32-channel groups: none straddles, but split one K slab into the skip half
+    wc = bf(torch.randn(co, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    g2, b2 = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ss = _tile_sums(s)
+    coef2 = ops.gn_fold_tiles(sh, ss, B, coef_for=(g2.cuda(), b2.cuda(), 1e-5, hw * hw))
+    a2 = ops.gn_apply(h.cuda(), s.cuda(), ops.gn_fold_tiles(sh, ss, B), g2.cuda(), b2.cuda(), 1e-5, True, torch.bfloat16,
+                      n_chunks=1)
+    wv = wc.permute(0, 2, 3, 1)                                                   # [co, 3, 3, C]
+    w_lo = wv[..., :sp].reshape(co, -1).to(torch.bfloat16).contiguous().cuda()
+    w_hi = wv[..., sp:].reshape(co, -1).to(torch.bfloat16).contiguous().cuda()
+    part_ref = ops.conv(a2[:Bs, :, :, sp:], w_hi, None, co, 3, out_dtype=torch.float32, tensor_core=True)
+    ref2 = ops.conv(a2[..., :sp], w_lo, bias.cuda(), co, 3, residual=part_ref, out_dtype=torch.bfloat16, tensor_core=True)
+    sd = s.cuda()
+    part = ops.conv(sd[:, :, :, sp - cm:], w_hi, None, co, 3, out_dtype=torch.float32, tensor_core=True, gn_coef=coef2,
+                    gn_c_off=sp)
+    assert torch.equal(part, part_ref), float((part - part_ref).abs().max())
+    fus2 = ops.conv(h.cuda(), w_lo, bias.cuda(), co, 3, x1=sd[:, :, :, :sp - cm], residual=part, out_dtype=torch.bfloat16,
+                    tensor_core=True, gn_coef=coef2)
+    assert torch.equal(ref2, fus2), float((ref2.float() - fus2.float()).abs().max())
+
+
+def test_conv_tc_groupnorm_in_operand_path_rejects_unsupported_shapes(ops):
+    """64-wide maps (32 KB boxes), 128-wide channel tiles and maps with several samples per tile are not fusable: the
+    planner says so and a forced call fails with a message instead of computing something else."""
+    assert not ops.conv_gn_fusable(2, 64, 64, 128, 256)     # six 32 KB boxes do not fit beside the weight ring
+    assert not ops.conv_gn_fusable(2, 16, 16, 256, 128)     # BN = 128
+    assert not ops.conv_gn_fusable(4, 8, 8, 256, 256)       # two samples per pixel tile
+    x = torch.zeros(2, 16, 16, 256, dtype=torch.bfloat16, device="cuda")
+    coef = torch.zeros(2, 256, 2, device="cuda")
+    w = torch.zeros(128, 9 * 256, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError, match="gn_coef"):
+        ops.conv(x, w, None, 128, 3, tensor_core=True, gn_coef=coef)

@@ -50,7 +50,8 @@ def main():
             taps = 4 if kw.get("up_phase") is not None else ksize * ksize
             sk = kw.get("skip_x0")
             skc = 0 if sk is None else sk.shape[-1] + (0 if kw.get("skip_x1") is None else kw["skip_x1"].shape[-1])
-            rec.append((e0, e1, b, h, w, c0, c1, cout, taps, kw.get("residual") is not None, kw.get("stats_out") is not None, skc))
+            rec.append((e0, e1, b, h, w, c0, c1, cout, taps, kw.get("residual") is not None, kw.get("stats_out") is not None, skc,
+                        kw.get("gn_coef") is not None))
             return out
 
         ops.conv = timed
@@ -65,16 +66,16 @@ def main():
             ops.conv = orig
         clk = clocks.stop()
     n = len(rec) // reps
-    print(f"{'#':>3s} {'B':>4s} {'HxW':>9s} {'Cin':>10s} {'Cout':>5s} {'taps':>4s} res stats {'ms':>8s} {'TFLOP/s':>8s} {'GFLOP':>8s}")
+    print(f"{'#':>3s} {'B':>4s} {'HxW':>9s} {'Cin':>10s} {'Cout':>5s} {'taps':>4s} res stats gn {'ms':>8s} {'TFLOP/s':>8s} {'GFLOP':>8s}")
     tot_ms = tot_fl = 0.0
     for i in range(n):
         ms = sum(rec[r * n + i][0].elapsed_time(rec[r * n + i][1]) for r in range(reps)) / reps
-        _, _, b, h, w, c0, c1, cout, taps, res, st, skc = rec[i]
+        _, _, b, h, w, c0, c1, cout, taps, res, st, skc, gn = rec[i]
         fl = 2.0 * b * h * w * cout * (taps * (c0 + c1) + skc)
         tot_ms += ms
         tot_fl += fl
         cin = (f"{c0}+{c1}" if c1 else f"{c0}") + (f"|s{skc}" if skc else "")
-        print(f"{i:3d} {b:4d} {h:4d}x{w:<4d} {cin:>10s} {cout:5d} {taps:4d} {int(res):3d} {int(st):5d} {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.1f}")
+        print(f"{i:3d} {b:4d} {h:4d}x{w:<4d} {cin:>10s} {cout:5d} {taps:4d} {int(res):3d} {int(st):5d} {int(gn):2d} {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.1f}")
     print(f"total {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s over {n} launches; clocks {clk}")
 
 
