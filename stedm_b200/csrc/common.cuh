@@ -185,6 +185,29 @@ __device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint3
       : "memory");
 }
 
+// 16-byte shared-memory accesses by 32-bit shared address (a pointer derived from the aligned dynamic-smem base
+// through integer arithmetic makes the compiler fall back to generic LD / ST with 64-bit address math)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// `v` to addr_v when pred, else zeros to addr_z: one of two predicated stores executes (no value selects)
+__device__ __forceinline__ void sts128_or_zero(bool pred, uint32_t addr_v, const uint4& v, uint32_t addr_z) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t.reg .b32 Z;\n\t"
+      "setp.ne.b32 P, %0, 0;\n\t"
+      "mov.b32 Z, 0;\n\t"
+      "@P st.shared.v4.b32 [%1], {%2, %3, %4, %5};\n\t"
+      "@!P st.shared.v4.b32 [%6], {Z, Z, Z, Z};\n\t}\n"
+      ::"r"(static_cast<uint32_t>(pred)), "r"(addr_v), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(addr_z)
+      : "memory");
+}
+
 // ---- PTX: TMA tiled loads (cp.async.bulk.tensor) -----------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

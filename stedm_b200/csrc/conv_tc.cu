@@ -50,11 +50,13 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;
-constexpr int TC_THREADS_XF = 320;  // + 4 transform warps (warps 6-9)
-// XF mode shared-memory operand pool: 2 sets x 3 boxes (raw -> [dx=-1 | dx=0 | dx=+1]) + a weight ring in what is left
+constexpr int TC_THREADS_XF = 352;  // + 4 transform warps (warps 6-9) + the activation producer (warp 10)
+// XF mode shared-memory operand pool: 2 sets x 3 boxes ([dx=-1 | raw -> dx=0 | dx=+1]) + a weight ring in what is left
 constexpr int TC_XF_POOL = 209 * 1024;
 constexpr int TC_XF_SETS = 2;
+constexpr int TC_XF_SLOTS = 3 * TC_XF_SETS;
 constexpr int TC_XF_MAX_NB = 8;
+constexpr int TC_XF_BAR_BYTES = 512;
 
 // STEDM_TC_CLUSTER=0 disables the 2-CTA weight multicast (A/B measurements, debugging)
 static bool g_tc_cluster_enabled = [] {
@@ -117,6 +119,7 @@ struct TcParams {
   int nb;                // weight ring depth (XF: what fits beside the 6 boxes; otherwise Cfg::STAGES)
   int a_pool_bytes;      // XF: 6 * a_buf_bytes
   int log2w;             // XF: W is a power of two
+  int xf_debug;          // timing experiments only (STEDM_XF_DEBUG): 1 = no math, 2 = no outer-box stores, 4 = no work at all
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -143,7 +146,7 @@ struct TcCfg {
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES + OUT_STAGE_BYTES;
   static constexpr int MIN_BLOCKS = (BN >= 256) ? 1 : 2;  // TMEM: 1 x 512 or 2 x <=256 columns per SM
-  static constexpr int SMEM_BYTES_XF = TC_XF_POOL + 1024 + 256 + STATS_BYTES + OUT_STAGE_BYTES;
+  static constexpr int SMEM_BYTES_XF = TC_XF_POOL + 1024 + TC_XF_BAR_BYTES + STATS_BYTES + OUT_STAGE_BYTES;
 };
 
 template <int BN, int CL, bool PAIR, bool HALO, bool XF>
@@ -159,7 +162,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   // Operand area: [activation pool: STAGES slabs of 16 KB, or fewer and larger halo boxes | STAGES weight slabs]
   // (measured 2-3 % faster than [activation | weight] back to back per slot).  XF: [2 sets x 3 boxes | p.nb weight slabs].
   constexpr int POOL_BYTES = XF ? TC_XF_POOL : Cfg::STAGES * Cfg::STAGE_BYTES;
-  constexpr int NA_BARS = XF ? TC_XF_SETS : Cfg::STAGES;     // A ring barriers (XF: one pair per SET of three boxes)
+  constexpr int BAR_BYTES = XF ? TC_XF_BAR_BYTES : 256;
+  constexpr int NF_BARS = XF ? TC_XF_SETS : Cfg::STAGES;     // "activation landed" barriers (XF: one per SET of three boxes)
+  constexpr int NE_BARS = XF ? TC_XF_SLOTS : Cfg::STAGES;    // "activation buffer free" barriers (XF: one per box slot)
   constexpr int NB_BARS = XF ? TC_XF_MAX_NB : Cfg::STAGES;   // weight ring barriers
   const uint32_t b_base = XF ? static_cast<uint32_t>(p.a_pool_bytes) : static_cast<uint32_t>(Cfg::A_POOL);
   const uint32_t nb = XF ? static_cast<uint32_t>(p.nb) : static_cast<uint32_t>(Cfg::STAGES);
@@ -167,16 +172,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto slab_b = [b_base](uint8_t* base, uint32_t s, int) { return base + b_base + s * Cfg::B_BYTES_PAD; };
   // two rings: activation buffers (A) and weight slabs (B), each with full / empty mbarriers
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + POOL_BYTES);
-  uint64_t* empty_a = full_a + NA_BARS;
-  uint64_t* full_b = empty_a + NA_BARS;
+  uint64_t* empty_a = full_a + NF_BARS;
+  uint64_t* full_b = empty_a + NE_BARS;
   uint64_t* empty_b = full_b + NB_BARS;
   uint64_t* tmem_full_bar = empty_b + NB_BARS;         // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::ACC; // [ACC]
   uint64_t* xf_ready = tmem_empty_bar + Cfg::ACC;      // [TC_XF_SETS] (XF only): the set's three boxes are transformed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_ready + TC_XF_SETS);
-  static_assert((2 * NA_BARS + 2 * NB_BARS + 2 * Cfg::ACC + TC_XF_SETS) * 8 + 4 <= 256, "barrier area");
-  float* s_stats = reinterpret_cast<float*>(smem + POOL_BYTES + 256);
-  uint8_t* s_out = smem + POOL_BYTES + 256 + Cfg::STATS_BYTES;
+  uint64_t* full_s = xf_ready + TC_XF_SETS;            // [TC_XF_SLOTS] (XF only): a raw fused-skip slab has landed in the slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(XF ? full_s + TC_XF_SLOTS : xf_ready);
+  static_assert((NF_BARS + NE_BARS + 2 * NB_BARS + 2 * Cfg::ACC + (XF ? TC_XF_SETS + TC_XF_SLOTS : 0)) * 8 + 4 <= BAR_BYTES,
+                "barrier area");
+  float* s_stats = reinterpret_cast<float*>(smem + POOL_BYTES + BAR_BYTES);
+  uint8_t* s_out = smem + POOL_BYTES + BAR_BYTES + Cfg::STATS_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -193,18 +200,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tma_prefetch_desc(&map_s0);
       tma_prefetch_desc(&map_s1);
     }
-    for (int i = 0; i < NA_BARS; ++i) {
-      // PAIR: the leader's full barriers collect both CTAs' producers; its single commit frees the slab in both.
-      // XF: the raw box is consumed by this CTA's own transform warps -> a local barrier with one producer
-      mbar_init(&full_a[i], (PAIR && !XF) ? 2 : 1);
-      mbar_init(&empty_a[i], 1);                // activations are never multicast
-    }
+    // PAIR: the leader's full barriers collect both CTAs' producers; its single commit frees the slab in both.
+    // XF: the raw box is consumed by this CTA's own transform warps -> a local barrier with one producer
+    for (int i = 0; i < NF_BARS; ++i) mbar_init(&full_a[i], (PAIR && !XF) ? 2 : 1);
+    for (int i = 0; i < NE_BARS; ++i) mbar_init(&empty_a[i], 1);  // activations are never multicast
     for (int i = 0; i < NB_BARS; ++i) {
       mbar_init(&full_b[i], PAIR ? 2 : 1);
       mbar_init(&empty_b[i], PAIR ? 1 : CL);    // multicast: released by the MMA commit of every CTA writing into it
     }
-    if constexpr (XF)
+    if constexpr (XF) {
       for (int i = 0; i < TC_XF_SETS; ++i) mbar_init(&xf_ready[i], 8);  // 4 transform warps of each CTA of the pair
+      for (int i = 0; i < TC_XF_SLOTS; ++i) mbar_init(&full_s[i], 2);   // both CTAs' activation producers
+    }
     for (int i = 0; i < Cfg::ACC; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], PAIR ? 256 : 128);  // every epilogue thread (of both CTAs) arrives
@@ -265,16 +272,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
         const int bs1 = (p.skip_x1_batch > 0) ? (b0 % p.skip_x1_batch) : b0;
         if constexpr (XF) {
-          // ONE raw box (the tile's rows + 2 halo rows, horizontal offset 0) per 64-channel block into the middle slot
-          // of a set — the transform warps derive the three horizontally shifted operand boxes from it — then the nine
-          // weight slabs in the order the MMA consumes them: horizontal tap bx, vertical tap g
+          // weights only (the raw activation boxes have their own producer, warp 10, so that their prefetch distance
+          // is not tied to the depth of the weight ring): nine slabs per 64-channel block in the order the MMA consumes
+          // them — horizontal tap bx, vertical tap g — then the fused skip slabs
           for (int cb = 0; cb < c_blks; ++cb) {
-            const bool first = cb < c0_blks;
-            mbar_wait(&empty_a[ia], pa ^ 1);
-            mbar_arrive_expect_tx(&full_a[ia], static_cast<uint32_t>(p.a_buf_bytes));
-            tma_load_4d(smem + (ia * 3 + 1) * p.a_buf_bytes, first ? &map_a0 : &map_a1, &full_a[ia],
-                        (first ? cb : cb - c0_blks) * TC_BK, x0, y0 - 1, first ? b0 : b1);
-            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
             for (int bx = 0; bx < 3; ++bx) {
               int kb = bx * c_blks + cb;
               for (int g = 0; g < 3; ++g, kb += 3 * c_blks) {
@@ -285,23 +286,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             }
           }
-          // fused 1x1 skip input: raw 16 KB slabs of the tile's own pixels, up to three per set (one per box slot)
-          for (int sb = 0; sb < p.skip_blks; sb += 3) {
-            const int n = min(3, p.skip_blks - sb);
-            mbar_wait(&empty_a[ia], pa ^ 1);
-            mbar_arrive_expect_tx(&full_a[ia], static_cast<uint32_t>(n * Cfg::A_BYTES));
-            for (int i = 0; i < n; ++i) {
-              const bool first = sb + i < p.skip_c0_blks;
-              tma_load_4d(smem + (ia * 3 + i) * p.a_buf_bytes, first ? &map_s0 : &map_s1, &full_a[ia],
-                          (first ? sb + i : sb + i - p.skip_c0_blks) * TC_BK, x0, y0, first ? b0 : bs1);
-            }
-            if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
-            for (int i = 0; i < n; ++i) {
-              mbar_wait(&empty_b[ib], pb ^ 1);
-              arrive_full(&full_b[ib], Cfg::B_BYTES);
-              load_b(ib, main_kb + sb + i, n0);
-              if (++ib == nb) { ib = 0; pb ^= 1; }
-            }
+          for (int sb = 0; sb < p.skip_blks; ++sb) {
+            mbar_wait(&empty_b[ib], pb ^ 1);
+            arrive_full(&full_b[ib], Cfg::B_BYTES);
+            load_b(ib, main_kb + sb, n0);
+            if (++ib == nb) { ib = 0; pb ^= 1; }
           }
         } else if constexpr (HALO) {
           // items (64-channel block cb, horizontal tap bx): one activation box of the tile's rows + halo, then the
@@ -376,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================================== MMA issuer =======================================
     if ((!PAIR || cta_rank == 0) && elect_one()) {  // PAIR: only the leader CTA issues (for both)
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
-      uint32_t ia = 0, pa = 0, ib = 0, pb = 0, tile = 0;
+      uint32_t ia = 0, pa = 0, ib = 0, pb = 0, tile = 0, xf_par = 0, sk_par = 0;
       // the 4 MMAs (UMMA_K = 16 bf16 = 32 B -> start address field += 2) of one K slab, then the commit that frees
       // the weight slot (in every CTA that multicasts into it / of the pair) once they have read it
       auto mma_slab = [&](uint32_t tmem_d, uint32_t a_addr, uint32_t slot, uint32_t started) {
@@ -403,8 +392,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
         uint32_t started = 0;
         if constexpr (XF) {
+          // ia = set (0 / 1), pa = the phase of its slot-free barriers (one completion per use of the set); bit `ia` of
+          // xf_par / sk_par = the phase of the set's "transformed" / "skip slab landed" barriers, which complete only on
+          // the uses of that kind.  A box slot is handed back as soon as its three vertical taps are issued.
           for (int cb = 0; cb < p.c_blks; ++cb) {
-            mbar_wait_cluster(&xf_ready[ia], pa);  // both CTAs' transform warps have written the set's three boxes
+            mbar_wait_cluster(&xf_ready[ia], (xf_par >> ia) & 1u);  // both CTAs' transform warps have written the three boxes
+            xf_par ^= 1u << ia;
             tc_fence_after();
             for (int bx = 0; bx < 3; ++bx) {
               const uint32_t a_addr = smem_u32(smem + (ia * 3 + bx) * p.a_buf_bytes);
@@ -415,22 +408,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 started = 1;
                 if (++ib == nb) { ib = 0; pb ^= 1; }
               }
+              release_a(ia * 3 + bx);
             }
-            release_a(ia);
             if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
           }
+          // fused skip slabs: raw, one per box slot, each with its own "landed" barrier (six in flight)
           for (int sb = 0; sb < p.skip_blks; sb += 3) {
             const int n = min(3, p.skip_blks - sb);
-            mbar_wait_cluster(&xf_ready[ia], pa);
-            tc_fence_after();
-            for (int i = 0; i < n; ++i) {
-              mbar_wait(&full_b[ib], pb);
-              tc_fence_after();
-              mma_slab(tmem_d, smem_u32(smem + (ia * 3 + i) * p.a_buf_bytes), ib, started);
-              started = 1;
-              if (++ib == nb) { ib = 0; pb ^= 1; }
+            for (int i = 0; i < 3; ++i) {
+              if (i < n) {
+                mbar_wait(&full_s[ia * 3 + i], (sk_par >> ia) & 1u);
+                mbar_wait(&full_b[ib], pb);
+                tc_fence_after();
+                mma_slab(tmem_d, smem_u32(smem + (ia * 3 + i) * p.a_buf_bytes), ib, started);
+                started = 1;
+                if (++ib == nb) { ib = 0; pb ^= 1; }
+              }
+              release_a(ia * 3 + i);   // every slot barrier completes once per use of the set, used or not
             }
-            release_a(ia);
+            sk_par ^= 1u << ia;
             if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
           }
         } else if constexpr (HALO) {
@@ -474,6 +470,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         else umma_commit(&tmem_full_bar[acc]);
       }
     }
+  } else if (XF && warp == 10) {
+    // ============================ raw activation producer (XF only) =================================
+    // ONE raw box (the tile's rows + 2 halo rows, horizontal offset 0) per 64-channel block into the MIDDLE slot of a
+    // set, as soon as the MMA has released that slot (after the previous use's second horizontal tap); the fused skip
+    // input as raw 16 KB slabs of the tile's own pixels, up to three per set.
+    if constexpr (XF) {
+      if (elect_one()) {
+        uint32_t is = 0, ps = 0;
+        for (int work = cluster_id; work < p.num_work; work += num_clusters) {
+          const int tile_id = work / p.ksplit;
+          const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
+          const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
+          const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
+          const int bs1 = (p.skip_x1_batch > 0) ? (b0 % p.skip_x1_batch) : b0;
+          for (int cb = 0; cb < p.c_blks; ++cb) {
+            const bool first = cb < p.c0_blks;
+            mbar_wait(&empty_a[is * 3 + 1], ps ^ 1);
+            mbar_arrive_expect_tx(&full_a[is], static_cast<uint32_t>(p.a_buf_bytes));
+            tma_load_4d(smem + (is * 3 + 1) * p.a_buf_bytes, first ? &map_a0 : &map_a1, &full_a[is],
+                        (first ? cb : cb - p.c0_blks) * TC_BK, x0, y0 - 1, first ? b0 : b1);
+            if (++is == TC_XF_SETS) { is = 0; ps ^= 1; }
+          }
+          for (int sb = 0; sb < p.skip_blks; sb += 3) {
+            const int n = min(3, p.skip_blks - sb);
+            for (int i = 0; i < 3; ++i) {
+              const uint32_t slot = is * 3 + i;
+              mbar_wait(&empty_a[slot], ps ^ 1);   // also: the slot's previous "landed" phase is complete and consumed
+              if (i < n) {                         // straight to the leader's MMA thread: no transform on this path
+                const bool first = sb + i < p.skip_c0_blks;
+                mbar_arrive_expect_tx_cluster(&full_s[slot], Cfg::A_BYTES, 0);
+                tma_load_4d_2sm(smem + slot * p.a_buf_bytes, first ? &map_s0 : &map_s1, &full_s[slot],
+                                (first ? sb + i : sb + i - p.skip_c0_blks) * TC_BK, x0, y0, first ? b0 : bs1);
+              } else {
+                mbar_arrive_cluster(&full_s[slot], 0);   // unused slot of the last group: keep its phase in step
+              }
+            }
+            if (++is == TC_XF_SETS) { is = 0; ps ^= 1; }
+          }
+        }
+      }
+    }
   } else if (XF && warp >= 6) {
     // ============================ GroupNorm + SiLU transform (XF only) ==============================
     // 128 threads: thread -> (16-byte chunk j = 8 channels, pixel lane); per set: read the raw box (middle slot, as
@@ -485,73 +522,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if constexpr (XF) {
       const int tt = static_cast<int>(threadIdx.x) - 192;
       const int j = tt & 7, pl = tt >> 3;
-      const int W = p.W, wmask = p.W - 1, box_px = p.a_buf_bytes >> 7;
-      uint32_t ia = 0, pa = 0;
+      const int wmask = p.W - 1, log2w = p.log2w, H = p.H, n_it = (p.a_buf_bytes >> 7) / 16;  // box pixels % 16 == 0
+      const bool silu = p.gn_silu != 0;
+      const uint32_t smem_base = smem_u32(smem), box = static_cast<uint32_t>(p.a_buf_bytes);
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t is = 0, ps = 0, xf_par = 0;
+      // (scale, shift) rows of this thread's 8 channels for the tile of work item `w` (the all-out-of-bounds tile of an
+      // odd tile count reads sample 0's: its results are never stored)
+      auto coef_row = [&](int w) {
+        const int m0 = (((w / p.ksplit) / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
+        const int b0 = m0 < p.M ? m0 / p.HW : 0;
+        return reinterpret_cast<const float4*>(p.gn_coef + (static_cast<size_t>(b0) * p.gn_cstride + p.gn_c_off + j * 8) * 2);
+      };
+      // the next block's coefficients — of this tile or of the first block of the next one — are always in flight while
+      // the current block is transformed (an exposed L2 round trip per tile was measured at 5 % of a 512-channel launch)
+      const float4* cp = coef_row(cluster_id);
+      float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;
+      if (cluster_id < p.num_work) { k0 = __ldg(cp); k1 = __ldg(cp + 1); k2 = __ldg(cp + 2); k3 = __ldg(cp + 3); }
       for (int work = cluster_id; work < p.num_work; work += num_clusters) {
         const int tile_id = work / p.ksplit;
         const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
-        const int y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
-        const bool tile_ok = m0 < p.M;   // the all-out-of-bounds tile of an odd tile count: no coefficients to read
-        const float* crow = p.gn_coef + (static_cast<size_t>(tile_ok ? b0 : 0) * p.gn_cstride + p.gn_c_off + j * 8) * 2;
+        const int y0 = (m0 / p.W) % p.H;
         for (int cb = 0; cb < p.c_blks; ++cb) {
-          // (scale, shift) of this thread's 8 channels, fetched while the box is in flight
-          const float4* cp = reinterpret_cast<const float4*>(crow + static_cast<size_t>(cb) * (TC_BK * 2));
-          const float4 k0 = __ldg(cp), k1 = __ldg(cp + 1), k2 = __ldg(cp + 2), k3 = __ldg(cp + 3);
-          const float ca[8] = {k0.x, k0.z, k1.x, k1.z, k2.x, k2.z, k3.x, k3.z};
-          const float cs[8] = {k0.y, k0.w, k1.y, k1.w, k2.y, k2.w, k3.y, k3.w};
-          mbar_wait(&full_a[ia], pa);
-          uint8_t* v0 = smem + (ia * 3) * p.a_buf_bytes;
-          uint8_t* v1 = v0 + p.a_buf_bytes;
-          uint8_t* v2 = v1 + p.a_buf_bytes;
+          // h = y / 2 = fma(x, a / 2, s / 2) — exact, so silu(y) = h * tanh(h) + h is bit-identical to silu_f(fma(x, a, s))
+          const float ca[8] = {0.5f * k0.x, 0.5f * k0.z, 0.5f * k1.x, 0.5f * k1.z, 0.5f * k2.x, 0.5f * k2.z, 0.5f * k3.x, 0.5f * k3.z};
+          const float cs[8] = {0.5f * k0.y, 0.5f * k0.w, 0.5f * k1.y, 0.5f * k1.w, 0.5f * k2.y, 0.5f * k2.w, 0.5f * k3.y, 0.5f * k3.w};
+          if (cb + 1 < p.c_blks) {
+            cp += TC_BK * 2 / 4;
+            k0 = __ldg(cp); k1 = __ldg(cp + 1); k2 = __ldg(cp + 2); k3 = __ldg(cp + 3);
+          } else if (work + num_clusters < p.num_work) {
+            cp = coef_row(work + num_clusters);
+            k0 = __ldg(cp); k1 = __ldg(cp + 1); k2 = __ldg(cp + 2); k3 = __ldg(cp + 3);
+          }
+          mbar_wait(&empty_a[is * 3], ps ^ 1);      // the outer slots: free once the MMA has read their previous use
+          mbar_wait(&empty_a[is * 3 + 2], ps ^ 1);
+          mbar_wait(&full_a[is], (xf_par >> is) & 1u);   // the raw box has landed in the middle slot
+          xf_par ^= 1u << is;
+          // px advances by 16 per iteration, so the swizzle phases (px & 7, (px +- 1) & 7) are loop invariants; the
+          // wrap-around destinations of the padding columns (px -+ (W - 1), W % 8 == 0) share them
+          const uint32_t a1 = smem_base + (is * 3 + 1) * box + pl * 128u + (static_cast<uint32_t>(j ^ (pl & 7)) << 4);
+          const uint32_t a0 = smem_base + (is * 3) * box + (static_cast<uint32_t>(j ^ ((pl + 1) & 7)) << 4);
+          const uint32_t a2 = smem_base + (is * 3 + 2) * box + (static_cast<uint32_t>(j ^ ((pl - 1) & 7)) << 4);
 #pragma unroll 2
-          for (int px = pl; px < box_px; px += 16) {
-            const int r = px >> p.log2w, x = px & wmask;
-            const bool row_ok = static_cast<unsigned>(y0 - 1 + r) < static_cast<unsigned>(p.H);
-            const uint32_t off = static_cast<uint32_t>(px) * 128u + (static_cast<uint32_t>(j ^ (px & 7)) << 4);
-            const uint4 u = *reinterpret_cast<const uint4*>(v1 + off);
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok) {
-              float v[8];
-              float2 f;
-              f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
-              f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
-              f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
-              f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+          for (int it = 0; it < ((p.xf_debug & 4) ? 0 : n_it); ++it) {
+            const int px = pl + 16 * it;
+            const int r = px >> log2w, x = px & wmask;
+            const bool row_ok = static_cast<unsigned>(y0 - 1 + r) < static_cast<unsigned>(H);
+            const uint4 u = lds128(a1 + it * 2048u);
+            float v[8];
+            float2 f;
+            f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+            f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+            f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+            f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+            if (!(p.xf_debug & 1)) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float y = fmaf(v[i], ca[i], cs[i]);
-                v[i] = p.gn_silu ? silu_f(y) : y;
+                const float h = fmaf(v[i], ca[i], cs[i]);
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+                v[i] = silu ? fmaf(h, t, h) : h + h;
               }
-              o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                             pack_bf16x2(v[6], v[7]));
             }
-            *reinterpret_cast<uint4*>(v1 + off) = o;
-            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-            {  // dx = -1 box: operand pixel (r, x') = source pixel (r, x' - 1): this value lands at x + 1; column 0 is padding
-              const bool has = x + 1 < W;
-              const int q = has ? px + 1 : px - wmask;
-              *reinterpret_cast<uint4*>(v0 + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(j ^ (q & 7)) << 4)) =
-                  has ? o : zero;
-            }
-            {  // dx = +1 box: this value lands at x - 1; column W - 1 is padding
-              const bool has = x >= 1;
-              const int q = has ? px - 1 : px + wmask;
-              *reinterpret_cast<uint4*>(v2 + static_cast<uint32_t>(q) * 128u + (static_cast<uint32_t>(j ^ (q & 7)) << 4)) =
-                  has ? o : zero;
-            }
+            uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+            if (!row_ok) o = zero;    // rows outside the image are the convolution's padding
+            sts128(a1 + it * 2048u, o);
+            // dx = -1 box: operand pixel (r, x') = source pixel (r, x' - 1): this value lands at x + 1; column 0 is padding
+            if (p.xf_debug & 2) continue;
+            sts128_or_zero(x != wmask, a0 + static_cast<uint32_t>(px + 1) * 128u, o, a0 + static_cast<uint32_t>(px - wmask) * 128u);
+            // dx = +1 box: this value lands at x - 1; column W - 1 is padding
+            sts128_or_zero(x != 0, a2 + static_cast<uint32_t>(px - 1) * 128u, o, a2 + static_cast<uint32_t>(px + wmask) * 128u);
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           __syncwarp();
-          if (lane == 0) mbar_arrive_release_cluster(&xf_ready[ia], 0);
-          if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
+          if (lane == 0) mbar_arrive_release_cluster(&xf_ready[is], 0);
+          if (++is == TC_XF_SETS) { is = 0; ps ^= 1; }
         }
-        // fused-skip sets hold raw slabs that go to the MMA untouched: just pass the TMA completion on
-        for (int sb = 0; sb < p.skip_blks; sb += 3) {
-          mbar_wait(&full_a[ia], pa);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_release_cluster(&xf_ready[ia], 0);
-          if (++ia == TC_XF_SETS) { ia = 0; pa ^= 1; }
-        }
+        // the fused-skip slabs go from TMA to the MMA untouched: only keep the set rotation in step
+        for (int sb = 0; sb < p.skip_blks; sb += 3)
+          if (++is == TC_XF_SETS) { is = 0; ps ^= 1; }
       }
     }
   } else {
@@ -888,6 +939,8 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
     p.a_pool_bytes = TC_XF_SETS * 3 * p.a_buf_bytes;
     p.nb = (TC_XF_POOL - p.a_pool_bytes) / Cfg::B_BYTES_PAD;
     if (p.nb > TC_XF_MAX_NB) p.nb = TC_XF_MAX_NB;
+    static const int nb_cap = [] { const char* e = getenv("STEDM_XF_NB"); return e ? atoi(e) : 0; }();  // A/B: shallower ring
+    if (nb_cap >= 3 && p.nb > nb_cap) p.nb = nb_cap;
     if (p.nb < 3 || p.a_buf_bytes < Cfg::A_BYTES) {
       set_error("conv_tc: halo box of %d B leaves no room for the weight ring in GroupNorm-fused mode", p.a_buf_bytes);
       return ERR_ARG;
@@ -1214,6 +1267,8 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   }
   p.gn_coef = d->gn_coef; p.gn_cstride = d->gn_cstride; p.gn_c_off = d->gn_c_off; p.gn_silu = d->gn_silu;
   p.nb = 0; p.a_pool_bytes = 0; p.log2w = 0;
+  static const int xf_debug = [] { const char* e = getenv("STEDM_XF_DEBUG"); return e ? atoi(e) : 0; }();
+  p.xf_debug = xf_debug;
   while ((1 << p.log2w) < W) ++p.log2w;
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {

@@ -232,7 +232,12 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
 
 
 _GN_FUSABLE = {}
-GN_FUSION = [os.environ.get("STEDM_GN_FUSION", "1") != "0"]   # A/B switch: GroupNorm + SiLU inside the consumer convolution's operand path
+# GroupNorm + SiLU inside the consumer convolution's operand path (stedm_conv_desc.gn_coef).  Bit-identical to the separate
+# apply kernel and 13 % fewer launches, but measured 1.4 % SLOWER end to end on the same box (65.5 vs 66.45 images/s,
+# tools/gpu_ab_bench.sh, round 2): every activation element is transformed once per output-channel tile and halo row
+# (x5 at 1024 channels) inside a power-capped tensor-core kernel, while the tensors of the 16x16 / 32x32 sites it covers
+# are L2-resident for the stand-alone kernel anyway.  Opt-in: STEDM_GN_FUSION=1.
+GN_FUSION = [os.environ.get("STEDM_GN_FUSION", "0") == "1"]
 
 
 def conv_gn_fusable(batch, h, w, cin, cout, skip_c=0):

@@ -242,13 +242,16 @@ def test_bench_geometry_b64_l64_rows_equal_b4_golden_run():
 
 
 @pytest.mark.parametrize("L,B", [(64, 4), (32, 2)])
-def test_groupnorm_in_operand_path_is_bit_identical_to_separate_apply(L, B):
+def test_groupnorm_in_operand_path_matches_separate_apply(L, B):
     """A guided DDIM step with GroupNorm + SiLU applied inside the consumer convolutions (ops.GN_FUSION, every site the
-    kernel takes: 16x16 / 32x32 maps with >= 256 output channels) equals the step with the separate apply kernel, bit
-    for bit — eps, x_prev and pred_x0."""
-    from stedm_b200 import ops
+    kernel takes: 16x16 / 32x32 maps with >= 256 output channels) against the step with the separate apply kernel.
+    With the 1x1 skip convolutions as separate launches both variants run the same K order and the step is BIT-EQUAL;
+    with them folded into the 3x3 convolution's K loop the unfused launch walks K tap-major for the layers with many skip
+    slabs, the fused one block-major — the same sum in another fp32 order (bound: 2e-3 of max |x|)."""
+    from stedm_b200 import engine, ops
     from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
     m = build_model(L, n_style=1, precision="bf16")
+    unet = m._model.model.diffusion_model
     gen = torch.Generator().manual_seed(L + B)
     x = torch.randn(B, 3, L, L, generator=gen).cuda()
     cc = torch.randn(B, 3, L, L, generator=gen).cuda()
@@ -268,11 +271,23 @@ def test_groupnorm_in_operand_path_is_bit_identical_to_separate_apply(L, B):
         finally:
             ops.GN_FUSION[0] = saved
 
-    (xf, pf), n_f = run(True)
-    (xu, pu), n_u = run(False)
-    print(f"L={L} B={B}: {n_u} launches with separate GroupNorm apply, {n_f} with the fused operand path")
-    assert torch.equal(xf, xu) and torch.equal(pf, pu)
-    assert n_f < n_u
+    saved_skip = engine.FUSE_SKIP[0]
+    try:
+        engine.FUSE_SKIP[0] = False
+        unet.invalidate_packed()
+        (xf, pf), n_f = run(True)
+        (xu, pu), n_u = run(False)
+        print(f"L={L} B={B}: {n_u} launches with separate GroupNorm apply, {n_f} with the fused operand path")
+        assert torch.equal(xf, xu) and torch.equal(pf, pu)
+        assert n_f < n_u
+    finally:
+        engine.FUSE_SKIP[0] = saved_skip
+        unet.invalidate_packed()
+    (xf, _), _ = run(True)
+    (xu, _), _ = run(False)
+    r = rel_err(xf, xu)
+    print(f"L={L} B={B}: fused vs separate GroupNorm with fused skip convolutions, rel err {r:.3e}")
+    assert r < 2e-3
 
 
 def test_cuda_graph_sampler_matches_eager():
@@ -413,6 +428,7 @@ def test_ddpm_ancestral_sampler_matches_reference_golden(monkeypatch):
     print(f"bf16 ancestral 5-step rel err {r:.3e}")
     assert r < BF16_EPS_BAR
     # p_sample at t = 0 adds no noise (ddpm.py:1103)
+    monkeypatch.undo()
     t0 = torch.zeros(2, dtype=torch.long, device="cuda")
     a = mb._model.p_sample(x_T.cuda(), cond, t0)
     b = mb._model.p_sample(x_T.cuda(), cond, t0)
