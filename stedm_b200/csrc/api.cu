@@ -39,7 +39,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, const uint32_t* elem_strides) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled is unavailable (driver too old or no CUDA device)");
@@ -54,7 +54,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (box[i] == 0 || box[i] > 256) {
       set_error("tensor map box dim %d = %u out of range", i, box[i]);
       return ERR_ARG;

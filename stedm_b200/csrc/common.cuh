@@ -452,7 +452,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
+// elem_strides (optional): traversal stride per dimension — a box of box[i] elements then loads every elem_strides[i]-th
+// one, i.e. ceil(box[i] / elem_strides[i]) elements (the stride-2 gather of a strided convolution).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 }  // namespace stedm

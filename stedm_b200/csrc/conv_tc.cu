@@ -99,6 +99,7 @@ struct TcParams {
   int m_pad;            // rows of one workspace slice (all tiles, including the out-of-bounds one)
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
+  int cs;                // input pixels per output pixel (2 for the stride-2 Downsample convolution: strided TMA boxes)
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
   int act;               // STEDM_ACT_*: applied to acc + bias + emb, before the residual
   // fused 1x1 skip convolution (ResBlock skip_connection / nin_shortcut): extra K slabs after the k x k taps, read at
@@ -333,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           int ta = tap / n_t, tb = tap - ta * n_t;                                // tap (ta, tb): dy = dyf + ta, dx = dxf + tb
           for (int kb = kb0; kb < kb1; ++kb) {
             const CUtensorMap* amap;
-            int ach, ab, cx = x0, cy = y0;
+            int ach, ab, cx = p.cs * x0, cy = p.cs * y0;
             if (kb < main_kb) {
               const bool first = cb < c0_blks;
               amap = first ? &map_a0 : &map_a1;
@@ -856,55 +857,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
-// Split-K second pass: out = epilogue(sum over splits of the fp32 partial tiles).  One thread = 8 channels of one pixel.
+// Split-K second pass: out = epilogue(sum over splits of the fp32 partial tiles, in split order: deterministic).
+// Block = one 128-pixel tile x 16 output channels, thread = (pixel row, 8-channel octet): the ksplit partial loads of a
+// thread are independent and issued together (this pass is latency-bound: its launches have at most a few dozen tiles).
+// When the consumer is a GroupNorm the block also reduces the tile's per-channel sum / sum of squares in a fixed order,
+// exactly what the single-pass epilogue publishes — a split launch keeps the statistics pass folded into its producer.
+constexpr int SKF_CH = 16;
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
-  const int groups = p.cout / 8;
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= static_cast<size_t>(p.M) * groups) return;
-  const int m = static_cast<int>(i / groups), n = static_cast<int>(i % groups) * 8;
+  __shared__ float s_red[TC_BM][SKF_CH][2];
+  const int tile = blockIdx.x, n0 = blockIdx.y * SKF_CH;
+  const int r = threadIdx.x >> 1, oct = threadIdx.x & 1, n = n0 + oct * 8;
+  const int m = tile * TC_BM + r;
+  const bool live = m < p.M && n < p.cout;
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  for (int s = 0; s < p.ksplit; ++s) {  // fixed order: deterministic
-    const float4* wp = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(s) * p.m_pad + m) * p.cout + n);
-    const float4 a = wp[0], b = wp[1];
-    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-  }
-  const int b = m / p.HW;
+  if (live) {
+    const float* wp = p.ws + static_cast<size_t>(m) * p.cout + n;
+    const size_t ss = static_cast<size_t>(p.m_pad) * p.cout;
+    int s = 0;
+    for (; s + 4 <= p.ksplit; s += 4) {   // fixed order: deterministic; 8 independent 16-byte loads in flight
+      float4 a[4], b[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (p.bias) v[j] += p.bias[n + j];
-    if (p.emb) v[j] += p.emb[static_cast<size_t>(b) * p.emb_stride + n + j];
-    if (p.act == STEDM_ACT_GELU) v[j] = gelu_erf(v[j]);
-  }
-  size_t o = static_cast<size_t>(m) * p.cout + n;
-  if (p.tap_mode == 1) {
-    const int pix = m - b * p.HW, y = pix / p.W, x = pix - y * p.W;
-    o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
-  }
-  if (p.residual) {
-    const size_t o_res = p.res_rows > 0 ? static_cast<size_t>(m % p.res_rows) * p.cout + n : o;
+      for (int u = 0; u < 4; ++u) {
+        a[u] = *reinterpret_cast<const float4*>(wp + (s + u) * ss);
+        b[u] = *reinterpret_cast<const float4*>(wp + (s + u) * ss + 4);
+      }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[o_res + j]
-                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[o_res + j]);
-  }
-  if (p.out_nchw) {
-    const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+      for (int u = 0; u < 4; ++u) {
+        v[0] += a[u].x; v[1] += a[u].y; v[2] += a[u].z; v[3] += a[u].w;
+        v[4] += b[u].x; v[5] += b[u].y; v[6] += b[u].z; v[7] += b[u].w;
+      }
+    }
+    for (; s < p.ksplit; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(wp + s * ss), b = *reinterpret_cast<const float4*>(wp + s * ss + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    const int b = m / p.HW;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (n + j >= p.cout_store) continue;
-      if (p.out_dtype == DT_F32) static_cast<float*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = v[j];
-      else static_cast<__nv_bfloat16*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+      float add = p.bias ? p.bias[n + j] : 0.f;
+      if (p.emb) add += p.emb[static_cast<size_t>(b) * p.emb_stride + n + j];
+      v[j] += add;
+      if (p.act == STEDM_ACT_GELU) v[j] = gelu_erf(v[j]);
     }
-  } else if (p.out_dtype == DT_BF16) {
-    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  } else {
-    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
-    op[0] = make_float4(v[0], v[1], v[2], v[3]);
-    op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    size_t o = static_cast<size_t>(m) * p.cout + n;
+    if (p.tap_mode == 1) {
+      const int pix = m - b * p.HW, y = pix / p.W, x = pix - y * p.W;
+      o = ((static_cast<size_t>(b) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout + n;
+    }
+    if (p.residual) {
+      const size_t o_res = p.res_rows > 0 ? static_cast<size_t>(m % p.res_rows) * p.cout + n : o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] += (p.res_dtype == DT_F32) ? static_cast<const float*>(p.residual)[o_res + j]
+                                        : __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[o_res + j]);
+    }
+    if (p.out_nchw) {
+      const size_t base = static_cast<size_t>(b) * p.cout_store * p.HW + (m - b * p.HW);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n + j >= p.cout_store) continue;
+        if (p.out_dtype == DT_F32) static_cast<float*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = v[j];
+        else static_cast<__nv_bfloat16*>(p.out)[base + static_cast<size_t>(n + j) * p.HW] = __float2bfloat16_rn(v[j]);
+      }
+    } else if (p.out_dtype == DT_BF16) {
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    } else {
+      float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]);
+      op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
+  if (p.stats_out == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = live ? v[j] : 0.f;
+    s_red[r][oct * 8 + j][0] = x;
+    s_red[r][oct * 8 + j][1] = x * x;
+  }
+  __syncthreads();
+  // 32 outputs (16 channels x {sum, sumsq}) x 8 threads: fixed strided partition + fixed shuffle tree = deterministic
+  const int o = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int ch = o >> 1, which = o & 1;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int l = sub; l < TC_BM; l += 8) acc += s_red[l][ch][which];
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0 && n0 + ch < p.cout && tile * TC_BM < p.M)
+    p.stats_out[(static_cast<size_t>(p.stats_tile_base + tile) * p.cout + n0 + ch) * 2 + which] = acc;
 }
 
 int tc_num_sms() {
@@ -971,15 +1015,16 @@ int launch_tc_impl(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO, XF>, ma0, ma1, mw, ms0, ms1, p);
+  TcParams pk = p;
+  if (p.ksplit > 1) pk.stats_out = nullptr;   // split launches publish the tile statistics from the finish pass
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, PAIR, HALO, XF>, ma0, ma1, mw, ms0, ms1, pk);
   if (e != cudaSuccess) {
     set_error("conv_tc: launch failed: %s", cudaGetErrorString(e));
     return ERR_CUDA;
   }
   int rc = check_launch("conv_tc");
   if (rc == 0 && p.ksplit > 1) {
-    const size_t items = static_cast<size_t>(p.M) * (p.cout / 8);
-    splitk_finish_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(p);
+    splitk_finish_kernel<<<dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((p.cout + SKF_CH - 1) / SKF_CH)), 256, 0, stream>>>(p);
     rc = check_launch("conv_tc split-K finish");
   }
   return rc;
@@ -1022,7 +1067,8 @@ TcPlan tc_plan(long long M, int cout, int num_kb, bool want_stats) {
   t.ksplit = 1;
   t.kb_per_split = num_kb;
   t.ws_bytes = 0;
-  if (g_tc_splitk_enabled && !want_stats && t.bn >= 64 && tiles * 2 <= max_clusters && num_kb >= 8) {
+  (void)want_stats;   // the split-K finish pass publishes the GroupNorm tile statistics too
+  if (g_tc_splitk_enabled && t.bn >= 64 && tiles * 2 <= max_clusters && num_kb >= 8) {
     int ks = max_clusters / tiles;
     if (ks > num_kb / 4) ks = num_kb / 4;
     if (ks >= 2) {
@@ -1038,7 +1084,8 @@ TcPlan tc_plan(long long M, int cout, int num_kb, bool want_stats) {
 
 extern "C" long long stedm_conv_tc_workspace_bytes(const stedm_conv_desc* d) {
   if (d == nullptr || d->cout < 16 || d->cout % 16 != 0 || d->batch <= 0) return 0;
-  const long long M = static_cast<long long>(d->batch) * d->in_h * d->in_w;
+  const int st = d->stride == 2 ? 2 : 1;
+  const long long M = static_cast<long long>(d->batch) * (d->in_h / st) * (d->in_w / st);
   const int taps = d->tap_mode == 1 ? 4 : d->ksize * d->ksize;
   const int num_kb = taps * ((d->c0 + d->c1 + TC_BK - 1) / TC_BK) + (d->skip_x0 ? (d->skip_c0 + d->skip_c1) / TC_BK : 0);
   return static_cast<long long>(tc_plan(M, d->cout, num_kb, d->stats_out != nullptr).ws_bytes);
@@ -1058,8 +1105,10 @@ struct TcLaunch {
 int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
   STEDM_REQUIRE(d != nullptr, "conv_tc: null descriptor");
   STEDM_REQUIRE(d->in_dtype == DT_BF16, "conv_tc: operands must be bf16");
-  STEDM_REQUIRE(d->stride == 1 && d->upsample == 0,
-                "conv_tc: stride / upsample are handled by im2col_3x3_s2 / upsample_nearest2x");
+  STEDM_REQUIRE(d->upsample == 0, "conv_tc: nearest upsampling runs as four sub-pixel phase convolutions (tap_mode 1)");
+  STEDM_REQUIRE(d->stride == 1 || (d->stride == 2 && d->ksize == 3 && d->tap_mode == 0 && d->c1 == 0 && d->skip_x0 == nullptr &&
+                                   d->gn_coef == nullptr && d->in_h % 2 == 0 && d->in_w % 2 == 0 && d->x0_pix_stride == 0),
+                "conv_tc: stride 2 (openaimodel.py:164-166) takes one dense 3x3 source with even height and width");
   STEDM_REQUIRE(!d->out_nchw || (d->residual == nullptr && d->cout_store >= 0 && d->cout_store <= d->cout),
                 "conv_tc: NCHW output takes no residual and needs cout_store <= cout");
   STEDM_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv_tc: ksize %d unsupported", d->ksize);
@@ -1073,7 +1122,9 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
                 "conv_tc: channel counts must be multiples of 64 (8 for a plain GEMM) (%d, %d)", d->c0, d->c1);
   STEDM_REQUIRE(d->cout >= 16 && d->cout % 16 == 0, "conv_tc: cout %d must be a multiple of 16", d->cout);
   STEDM_REQUIRE(d->act == STEDM_ACT_NONE || d->act == STEDM_ACT_GELU, "conv_tc: unknown activation %d", d->act);
-  const int H = d->in_h, W = d->in_w, B = d->batch;
+  // GEMM rows = OUTPUT pixels: for the stride-2 convolution the maps below are tiled over the half-resolution output and
+  // the TMA boxes walk the input with a traversal stride of 2 (the gather happens in the TMA unit, no im2col tensor)
+  const int H = d->in_h / d->stride, W = d->in_w / d->stride, B = d->batch;
   STEDM_REQUIRE(B > 0 && H > 0 && W > 0, "conv_tc: bad shape");
   // tile geometry: 128 consecutive pixels of the flattened (b, y, x) index must form a TMA box
   int tw, th, tb;
@@ -1132,7 +1183,7 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
                   d->gn_c_off + ctot);
     halo = 1;
     halo_na = TC_XF_SETS;
-  } else if (g_tc_halo_enabled && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
+  } else if (g_tc_halo_enabled && d->stride == 1 && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
       plan.ksplit == 1 && skip_blks * 5 <= taps * c_blks) {
     halo_bytes = (th + n_t - 1) * W * TC_BK * 2;
     const int stages = tc_stages(plan.bn, plan.pair);
@@ -1167,7 +1218,8 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
     const int rc = tc_prepare(d, &L);
     if (rc) return rc;
   }
-  const int H = d->in_h, W = d->in_w, B = d->batch;
+  const int cs = d->stride;                                  // 2: strided boxes over the full-resolution input
+  const int H = d->in_h / cs, W = d->in_w / cs, B = d->batch;  // output map = GEMM rows
   const int tw = L.tw, th = L.th, tb = L.tb, x1b = L.x1b;
   const long long M = L.M;
   const int ctot = L.ctot, taps = L.taps, c_blks = L.c_blks, skip_c = L.skip_c, skip_blks = L.skip_blks;
@@ -1177,14 +1229,17 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
 
   CUtensorMap ma0, ma1, mw;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(d->c0), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->c0), static_cast<uint64_t>(d->in_w), static_cast<uint64_t>(d->in_h),
                               static_cast<uint64_t>(B)};
     // x0 may be a channel slice of a wider NHWC tensor: its pixels are x0_pix_stride channels apart
     const uint64_t ps0 = d->x0_pix_stride > 0 ? d->x0_pix_stride : d->c0;
     STEDM_REQUIRE(ps0 >= static_cast<uint64_t>(d->c0) && ps0 % 8 == 0, "conv_tc: bad x0 pixel stride %d", d->x0_pix_stride);
-    const uint64_t str[3] = {ps0 * 2, static_cast<uint64_t>(W) * ps0 * 2, static_cast<uint64_t>(H) * W * ps0 * 2};
-    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw), abox_h, static_cast<uint32_t>(tb)};
-    int rc = make_tmap_bf16(&ma0, d->x0, 4, dims, str, box);
+    const uint64_t str[3] = {ps0 * 2, static_cast<uint64_t>(d->in_w) * ps0 * 2,
+                             static_cast<uint64_t>(d->in_h) * d->in_w * ps0 * 2};
+    // stride 2: a box of 2 tw x 2 th input pixels traversed with stride 2 = the tile's tw x th sampling positions
+    const uint32_t box[4] = {TC_BK, static_cast<uint32_t>(tw * cs), abox_h * cs, static_cast<uint32_t>(tb)};
+    const uint32_t est[4] = {1, static_cast<uint32_t>(cs), static_cast<uint32_t>(cs), 1};
+    int rc = make_tmap_bf16(&ma0, d->x0, 4, dims, str, box, est);
     if (rc) return rc;
   }
   if (d->c1 > 0) {
@@ -1256,6 +1311,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
+  p.cs = cs;
   p.act = d->act;
   p.skip_blks = skip_blks; p.skip_c0_blks = skip_c > 0 ? d->skip_c0 / TC_BK : 0; p.skip_x1_batch = skip_x1b;
   p.halo = halo; p.n_t = n_t; p.na = halo_na; p.a_buf_bytes = halo_bytes; p.a_row_bytes = W * TC_BK * 2;

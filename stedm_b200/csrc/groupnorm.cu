@@ -352,30 +352,30 @@ struct FoldSrc {
   long long rep_stride;  // in tiles
 };
 
-// One block per sample.  Pass 1: thread <-> (tile lane, channel): per-channel (sum, sumsq) over the sample's tiles with
-// coalesced float2 loads (consecutive threads = consecutive channels of one tile row), accumulated in double in tile
-// order.  Pass 2: 64 outputs (32 groups x {sum, sumsq}) x 4 threads fold the channels of a group and the tile lanes in
-// a fixed order.  (The first version walked tiles with 16 lanes per output: 4-byte loads 1 KB apart, 18 us per launch
-// x 38 launches = 3.6 % of a guided step.)
-constexpr int FOLD_THREADS = 256;
+// One block per (sample, group): thread <-> (tile lane, channel of the group): (sum, sumsq) over the sample's tiles with
+// float2 loads accumulated in double in tile order, then a fixed-order fold over tile lanes and the group's channels.
+// (History: 16 lanes per output walking tiles with 4-byte loads 1 KB apart took 18 us per launch; one block per SAMPLE
+// with coalesced loads 8 us at batch 64+ but 25 us at batch 1-2 — two blocks on the whole GPU; per (sample, group) blocks
+// keep the launch short at every batch.)
+constexpr int FOLD_THREADS = 128;
 __global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0, FoldSrc s1, double* __restrict__ out,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, float eps, int hw,
                                                                      float2* __restrict__ coef) {
-  __shared__ double s_tot[2 * GN_GROUPS];
-  __shared__ float s_mr[2 * GN_GROUPS];
-  extern __shared__ double fold_sm[];  // [tile lanes][C][2]
-  const int b = blockIdx.x;
+  __shared__ double s_part[FOLD_THREADS][2];
+  __shared__ float s_mr[2];
+  const int b = blockIdx.x, g = blockIdx.y;
   const int C = s0.c + s1.c, cpg = C / GN_GROUPS;
-  const int cl = C < FOLD_THREADS ? C : FOLD_THREADS;  // channel lanes
-  const int TL = FOLD_THREADS / cl;                    // tile lanes
+  const int cl = cpg < FOLD_THREADS ? cpg : FOLD_THREADS;   // channel lanes (cpg <= 128 on the path: C <= 4096)
+  const int TL = FOLD_THREADS / cl;                         // tile lanes
   const int tl = threadIdx.x / cl, c_lane = threadIdx.x - tl * cl;
+  double a0 = 0.0, a1 = 0.0;
   if (tl < TL) {
-    for (int ch = c_lane; ch < C; ch += cl) {
+    for (int cc = c_lane; cc < cpg; cc += cl) {
+      const int ch = g * cpg + cc;
       const FoldSrc& s = (ch < s0.c) ? s0 : s1;
       const int lc = (ch < s0.c) ? ch : ch - s0.c;
       const int bs = b % s.batch;
-      double a0 = 0.0, a1 = 0.0;
       for (int r = 0; r < s.reps; ++r) {
         const float* base = s.tiles + ((static_cast<size_t>(r) * s.rep_stride + static_cast<size_t>(bs) * s.tps) * s.c + lc) * 2;
 #pragma unroll 4
@@ -385,40 +385,35 @@ __global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0,
           a1 += static_cast<double>(v.y);
         }
       }
-      fold_sm[(static_cast<size_t>(tl) * C + ch) * 2] = a0;
-      fold_sm[(static_cast<size_t>(tl) * C + ch) * 2 + 1] = a1;
     }
   }
+  s_part[threadIdx.x][0] = a0;
+  s_part[threadIdx.x][1] = a1;
   __syncthreads();
-  const int o = threadIdx.x >> 2, sub = threadIdx.x & 3;  // 64 outputs x 4 threads
-  const int g = o >> 1, which = o & 1;
-  double acc = 0.0;
-  for (int cc = sub; cc < cpg; cc += 4)
-    for (int t = 0; t < TL; ++t) acc += fold_sm[(static_cast<size_t>(t) * C + g * cpg + cc) * 2 + which];
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // fixed tree: deterministic
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (sub == 0) {
-    if (out != nullptr) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + which] = acc;
-    s_tot[o] = acc;
+  if (threadIdx.x < 2) {   // fixed order over the block's partials: deterministic
+    double acc = 0.0;
+    for (int i = 0; i < FOLD_THREADS; ++i) acc += s_part[i][threadIdx.x];
+    s_part[0][threadIdx.x] = acc;   // (thread t only reads column t: no hazard with the other thread's store)
+    if (out != nullptr) out[(static_cast<size_t>(b) * GN_GROUPS + g) * 2 + threadIdx.x] = acc;
   }
   if (coef == nullptr) return;
   // Per-(sample, channel) scale / shift for consumers that apply the normalisation in their own operand path
   // (stedm_conv_desc.gn_coef): the SAME arithmetic, in the same precision, as gn_apply_kernel's prologue, so a fused
   // consumer is bit-identical to gn_apply + plain consumer.
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
+  if (threadIdx.x == 0) {
     const double n = static_cast<double>(hw) * cpg;
-    const double mean = s_tot[threadIdx.x * 2] / n;
-    double var = s_tot[threadIdx.x * 2 + 1] / n - mean * mean;
+    const double mean = s_part[0][0] / n;
+    double var = s_part[0][1] / n - mean * mean;
     var = var < 0.0 ? 0.0 : var;
-    s_mr[threadIdx.x * 2] = static_cast<float>(mean);
-    s_mr[threadIdx.x * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    s_mr[0] = static_cast<float>(mean);
+    s_mr[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += FOLD_THREADS) {
-    const int gg = c / cpg;
-    const float a = s_mr[gg * 2 + 1] * gamma[c];
-    coef[static_cast<size_t>(b) * C + c] = make_float2(a, fmaf(-s_mr[gg * 2], a, beta[c]));
+  for (int cc = threadIdx.x; cc < cpg; cc += FOLD_THREADS) {
+    const int c = g * cpg + cc;
+    const float a = s_mr[1] * gamma[c];
+    coef[static_cast<size_t>(b) * C + c] = make_float2(a, fmaf(-s_mr[0], a, beta[c]));
   }
 }
 
@@ -476,11 +471,7 @@ extern "C" int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long 
                 "gn_fold_tiles: bad shape");
   FoldSrc s0{tiles0, c0, reps0, tps0, batch0, rep_stride0};
   FoldSrc s1{tiles1, c1, c1 ? reps1 : 1, c1 ? tps1 : 1, c1 ? batch1 : 1, rep_stride1};
-  const int C = c0 + c1;
-  const int tile_lanes = FOLD_THREADS / (C < FOLD_THREADS ? C : FOLD_THREADS);
-  const size_t smem = static_cast<size_t>(tile_lanes) * C * 2 * sizeof(double);
-  STEDM_REQUIRE(smem <= 48 * 1024, "gn_fold_tiles: %d channels exceed the shared-memory fold buffer", C);
-  gn_fold_tiles_kernel<<<batch, FOLD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  gn_fold_tiles_kernel<<<dim3(batch, GN_GROUPS), FOLD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       s0, s1, out, gamma, beta, eps, hw, reinterpret_cast<float2*>(coef));
   return check_launch("gn_fold_tiles");
 }

@@ -211,11 +211,13 @@ class PackedConv:
         if self.tc:
             assert gn is None or (self.stride == 1 and not upsample and not out_nchw)
             if self.stride == 2:
+                # Downsample (openaimodel.py:164-166): the stride-2 gather happens in the TMA unit (boxes traversed with
+                # element stride 2 over the full-resolution input) — no im2col tensor is written
                 assert x1 is None and self.ksize == 3
-                cols = ops.im2col_3x3_s2(x0)            # [B, H/2, W/2, 9*C]: Downsample as a plain GEMM
-                tiles, meta = self._tile_stats(cols, want_stats)
-                out = ops.conv(cols, self.weight, self.bias, self.cout, 1, emb=emb, residual=residual,
-                               out_dtype=out_dtype, tensor_core=True, stats_out=tiles)
+                b, h, w_, _ = x0.shape
+                tiles, meta = self._tile_stats(x0.new_empty((b, h // 2, w_ // 2, 0)), want_stats)
+                out = ops.conv(x0, self.weight, self.bias, self.cout, 3, emb=emb, residual=residual,
+                               out_dtype=out_dtype, tensor_core=True, stats_out=tiles, stride=2)
                 out._gn_tiles = meta if getattr(out, "_stats_written", False) else None
                 return out
             if upsample and self.phase_weights is not None:

@@ -95,6 +95,21 @@ class DDIMSampler(object):
         time_range = list(reversed(range(0, timesteps))) if ddim_use_original_steps else np.flip(timesteps)
         total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
         stepper = _GuidedStepper(self, cond, unconditional_conditioning, unconditional_guidance_scale, shape)
+        # The whole loop as ONE CUDA graph (ddim.py:139-160 unrolled: every U-Net pass, the fused guidance + DDIM update
+        # and nothing else — no per-step copy, clone, fill or launch from Python): whenever a step does not depend on
+        # host-side state, i.e. the plain eta = 0 sampler without callbacks, in-painting mask or codebook snapping.
+        if (stepper.use_graph and mask is None and callback is None and img_callback is None and not quantize_denoised
+                and not ddim_use_original_steps and noise_dropout == 0. and img.is_cuda
+                and not np.any(np.asarray(self.ddim_sigmas[:total_steps]) != 0)):
+            out = stepper.run_loop_graph(img.float().contiguous(), [int(t) for t in time_range], total_steps, log_every_t)
+            if out is not None:
+                img, logged = out
+                for x_i, p_i in logged:
+                    intermediates["x_inter"].append(x_i)
+                    intermediates["pred_x0"].append(p_i)
+                for _ in range(total_steps):      # the reference draws randn every step, also at sigma = 0 (ddim.py:206):
+                    noise_like(shape, device, False)   # keep the generator where the reference leaves it
+                return img, intermediates
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
@@ -215,6 +230,53 @@ class _GuidedStepper:
         ent["graph"].replay()
         ops.LAUNCHES[0] += ent["launches"]
         return ent["eps"].clone()
+
+    def run_loop_graph(self, x_T, steps, total_steps, log_every_t):
+        """All ``len(steps)`` guided steps captured in one CUDA graph, cached on the U-Net module per (shapes, schedule,
+        guidance) signature and replayed with fresh x_T / conditioning.  Returns (x_0, [(x, pred_x0) logged steps]) as
+        fresh tensors, or None on the first call for a signature (the caller runs that loop eagerly: lazy kernel
+        attribute setup and the per-timestep embedding cache must not happen under capture)."""
+        s, unet = self.s, self.unet
+        sched = tuple((_f32(s.ddim_alphas[i]), _f32(s.ddim_alphas_prev[i]), _f32(s.ddim_sqrt_one_minus_alphas[i]))
+                      for i in range(total_steps))
+        key = ("loop", tuple(x_T.shape), tuple(self.c_concat.shape), tuple(self.context.shape), unet.precision,
+               self.guided, self.shared, self.scale, self.phi, tuple(steps), sched, log_every_t)
+        cache = unet.__dict__.setdefault("_graph_cache", {})
+        ent = cache.get(key)
+        if ent is None:
+            warm = cache.setdefault(("warm",) + key, [0])
+            if warm[0] < 1:
+                warm[0] += 1
+                return None
+            runner = unet.runner()
+            rows = [runner.time_embedding_row(t, x_T.device) for t in steps]     # cached by the eager warm-up loop
+            ent = {"x": x_T.clone(), "cc": self.c_concat.clone(), "ctx": self.context.clone(),
+                   "t": torch.zeros((x_T.shape[0] * (2 if self.guided and not self.shared else 1),), dtype=torch.long,
+                                    device=x_T.device),
+                   "graph": torch.cuda.CUDAGraph()}
+            n0 = ops.LAUNCHES[0]
+            with torch.cuda.graph(ent["graph"]):
+                emb_style = runner.style_embedding(ent["ctx"])
+                x, logged = ent["x"], []
+                for i, row in enumerate(rows):
+                    index = total_steps - i - 1
+                    x2 = torch.cat([x, x], 0) if (self.guided and not self.shared) else x
+                    eps = unet.forward_split(x2, ent["cc"], ent["t"], ent["ctx"], uniform_t=True, emb=(row, emb_style))
+                    e_c, e_u = (eps[:self.b], eps[self.b:]) if self.guided else (eps, None)
+                    a_t, a_prev, sq1m = sched[index]
+                    x, pred_x0 = ops.cfg_ddim_step(e_c, e_u, x, a_t, a_prev, 0.0, sq1m, cfg_scale=self.scale, phi=self.phi)
+                    if index % log_every_t == 0 or index == total_steps - 1:
+                        logged.append((x, pred_x0))
+                ent["out"], ent["logged"] = x, logged
+            ent["launches"] = ops.LAUNCHES[0] - n0
+            ops.LAUNCHES[0] = n0                      # capture enqueued nothing; replays are counted below
+            cache[key] = ent
+        ent["x"].copy_(x_T)
+        ent["cc"].copy_(self.c_concat)
+        ent["ctx"].copy_(self.context)
+        ent["graph"].replay()
+        ops.LAUNCHES[0] += ent["launches"]
+        return ent["out"].clone(), [(a.clone(), b.clone()) for a, b in ent["logged"]]
 
     def step(self, x, t, index, temperature=1., noise_dropout=0., repeat_noise=False, uniform_t=False,
              use_original_steps=False, quantize_denoised=False, t_value=None):

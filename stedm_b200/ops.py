@@ -17,15 +17,19 @@ _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
 LAUNCHES = [0]  # number of native kernel launches issued through this module (bench.py's gpu_launches)
 SPLITK_MAX_PIXELS = 148 * 128 * 4  # above this the output tiles alone fill the persistent grid: never split-K
-# Split-K changes the fp32 summation order as a function of how many tiles a launch has, i.e. of the batch size:
-# it trades the bit-exact batch/rank-shard invariance of the default path for small-batch latency.  Opt-in.
-SPLIT_K = [False]
+# Split-K for launches whose output tiles would leave more than half of the SMs idle (small per-GPU batches — the
+# reference ships 2-8 images per GPU, conf/location/cluster.yaml:3-5): the K loop is split across the idle SMs into fp32
+# partial tiles that a second pass sums IN SPLIT ORDER (deterministic), applying the epilogue and the fused GroupNorm
+# tile statistics once.  On by default: the library's planner decides per launch (stedm_conv_tc_workspace_bytes > 0).
+# It changes the fp32 summation order as a function of how many tiles a launch has, i.e. of the batch size: results stay
+# within fp32 reassociation of the single-pass path, but a sample is bit-identical across batch sizes / rank shards only
+# among launches planned the same way (always true for per-rank batches >= 16 at latent 64; tests pin the single-pass
+# path with SPLIT_K[0] = False).
+SPLIT_K = [os.environ.get("STEDM_SPLIT_K", "1") != "0"]
 
 
 def enable_split_k(flag=True):
-    """Latency mode for small batches (BASELINE configs[4]): split the K loop of launches with few output tiles
-    across the idle SMs.  Results stay within fp32 reassociation of the default path but are no longer bit-identical
-    across batch sizes, so it is off by default."""
+    """Split-K for launches with few output tiles (latency mode for small batches); see SPLIT_K."""
     SPLIT_K[0] = bool(flag)
 
 
@@ -145,7 +149,7 @@ def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True):
+         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True, split_k=True):
     """Implicit-GEMM convolution of NHWC ``[x0 | x1]``.  ``tensor_core`` selects stedm_conv_tc (bf16 weights
     [cout][k*k*cin]) or stedm_conv_simt (fp32 weights [k*k*cin][cout]).
 
@@ -207,18 +211,13 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
         d.skip_x1_batch = 0 if skip_x1 is None or skip_x1.shape[0] == b else skip_x1.shape[0]
         skip_c = d.skip_c0 + d.skip_c1
     out._stats_written = stats_out is not None
-    if tensor_core and SPLIT_K[0] and gn_coef is None and b * h * w <= SPLITK_MAX_PIXELS:
-        # small launches (few output tiles, deep K): split-K over the idle SMs through a caller-owned workspace.
-        # The fused GroupNorm statistics need the single-pass epilogue, so they are dropped for such launches and
-        # the consumer falls back to the separate statistics kernel (tensors this small cost nothing to re-read).
-        d.stats_out = None
-        need = _lib.load().stedm_conv_tc_workspace_bytes(C.byref(d))
+    if tensor_core and split_k and SPLIT_K[0] and gn_coef is None and b * oh * ow <= SPLITK_MAX_PIXELS:
+        # few output tiles and a deep K loop: split-K over the idle SMs through a caller-owned workspace (the finish pass
+        # applies the epilogue and publishes the GroupNorm tile statistics)
+        need = _splitk_workspace_bytes(d)
         if need > 0:
             ws = torch.empty((need,), device=x0.device, dtype=torch.uint8)
             d.workspace, d.workspace_bytes = _ptr(ws), need
-            out._stats_written = False
-        else:
-            d.stats_out = _ptr(stats_out)
     if tensor_core:
         ntaps = 4 if up_phase is not None else ksize * ksize
         assert weight.dtype == torch.bfloat16 and weight.numel() == cout * (ntaps * (c0 + c1) + skip_c), \
@@ -229,6 +228,18 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
             (weight.shape, cout, ksize, c0, c1)
         _call("stedm_conv_simt", C.byref(d), _stream())
     return out
+
+
+_SPLITK_WS = {}
+
+
+def _splitk_workspace_bytes(d):
+    """stedm_conv_tc_workspace_bytes, cached per launch geometry (the planner is a pure function of these fields)."""
+    key = (d.batch, d.in_h, d.in_w, d.c0, d.c1, d.cout, d.ksize, d.stride, d.tap_mode, d.skip_c0 + d.skip_c1 if d.skip_x0 else 0)
+    need = _SPLITK_WS.get(key)
+    if need is None:
+        need = _SPLITK_WS[key] = int(_lib.load().stedm_conv_tc_workspace_bytes(C.byref(d)))
+    return need
 
 
 _GN_FUSABLE = {}
@@ -242,9 +253,8 @@ GN_FUSION = [os.environ.get("STEDM_GN_FUSION", "0") == "1"]
 
 def conv_gn_fusable(batch, h, w, cin, cout, skip_c=0):
     """Does stedm_conv_tc take a 3x3 convolution of this shape with GroupNorm applied in its operand path?  Asked of
-    the library's own planner (stedm_conv_tc_plan with gn_coef set) once per shape."""
-    if not GN_FUSION[0] or SPLIT_K[0]:
-        return False
+    the library's own planner (stedm_conv_tc_plan with gn_coef set) once per shape.  A capability query: whether the
+    engine USES the fused path is GN_FUSION's business."""
     key = (batch, h, w, cin, cout, skip_c)
     ok = _GN_FUSABLE.get(key)
     if ok is None:

@@ -54,13 +54,15 @@ class PackedLinear:
                 if rows % 128 == 0 or 128 % rows == 0:
                     shape = (1, rows // 128, 128) if rows % 128 == 0 else (1, 1, rows)
                     out = ops.conv(x.view(*shape, c), self.weight, self.bias, self.n, 1, out_dtype=od, tensor_core=True,
-                                   act=act, residual=None if residual is None else residual.view(*shape, self.n))
+                                   split_k=False, act=act,
+                                   residual=None if residual is None else residual.view(*shape, self.n))
                     return out.view(b, h, w_, self.n)
                 if self._simt_weight is None:
                     self._simt_weight = self._w32.t().contiguous()
                 return ops.conv(x, self._simt_weight, self.bias, self.n, 1, out_dtype=od, tensor_core=False, act=act,
                                 residual=residual)
-        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=od, tensor_core=self.tc, act=act,
+        # split_k=False: an image's style feature is bit-identical whatever batch / chunk it is embedded in
+        return ops.conv(x, self.weight, self.bias, self.n, 1, out_dtype=od, tensor_core=self.tc, split_k=False, act=act,
                         residual=residual)
 
 

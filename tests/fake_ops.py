@@ -99,7 +99,7 @@ def im2col_3x3_s2(x):
 
 def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out_dtype=None, stride=1,
          upsample=False, out_nchw=False, tensor_core=True, out=None, cout_store=0, up_phase=None, stats_out=None,
-         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True):
+         act=0, skip_x0=None, skip_x1=None, gn_coef=None, gn_c_off=0, gn_silu=True, split_k=True):
     y = _conv(x0, weight, bias, cout, ksize, x1=x1, emb=emb, residual=residual, out_dtype=out_dtype, stride=stride,
               upsample=upsample, out_nchw=out_nchw, tensor_core=tensor_core, out=out, cout_store=cout_store,
               up_phase=up_phase, act=act, skip_x0=skip_x0, skip_x1=skip_x1, gn_coef=gn_coef, gn_c_off=gn_c_off,

@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--latents", type=int, nargs="+", default=[64, 128])
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 4, 16, 64, 256])
+    ap.add_argument("--no-torch", action="store_true", help="native columns only")
     a = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
@@ -56,6 +57,7 @@ def main():
             ctx = torch.randn(B, 512, generator=g).cuda()
             t = torch.full((B,), 481, dtype=torch.long, device="cuda")
             reps = 3 if B * (L / 64) ** 2 >= 64 else 10
+            from stedm_b200 import ops as _ops
             with torch.no_grad():
                 native = time_ms(lambda: unet.forward_split(x, cc, t, ctx), reps)
                 graph = torch.cuda.CUDAGraph()                  # the sampler replays the pass from a cached graph
@@ -63,22 +65,27 @@ def main():
                     unet.forward_split(x, cc, t, ctx)
                 replay = time_ms(graph.replay, reps)
                 del graph
-                from stedm_b200 import ops as _ops            # opt-in latency mode: split-K for launches with few tiles
-                _ops.enable_split_k(True)
+                _ops.enable_split_k(False)                      # single-pass K loops (bit-identical across batch sizes)
                 graph = torch.cuda.CUDAGraph()
                 unet.forward_split(x, cc, t, ctx)
                 with torch.cuda.graph(graph):
                     unet.forward_split(x, cc, t, ctx)
                 splitk = time_ms(graph.replay, reps)
-                _ops.enable_split_k(False)
+                _ops.enable_split_k(True)
                 del graph
                 xc = torch.cat([x, cc], 1)
-                ref32 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    ref16 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
+                ref32 = ref16 = float("nan")
+                if not a.no_torch:
+                    for _ in range(8):                              # let cuDNN's algorithm choice settle
+                        O.unet_forward(sd, xc, t, ctx)
+                    ref32 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        for _ in range(8):
+                            O.unet_forward(sd, xc, t, ctx)
+                        ref16 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), reps)
             tf = B * GFLOP_L64 * (L / 64) ** 2 / replay
             print(f"{L:6d} {B:5d} | {native:14.3f} {replay:8.3f} {tf:8.1f} | {ref32:13.3f} {ref16:13.3f} | "
-                  f"{ref32 / replay:6.2f} {ref16 / replay:6.2f}   split-K graph {splitk:8.3f} ms", flush=True)
+                  f"{ref32 / replay:6.2f} {ref16 / replay:6.2f}   single-pass-K graph {splitk:8.3f} ms", flush=True)
 
 
 if __name__ == "__main__":

@@ -28,6 +28,23 @@ def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
+def _no_split_k():
+    """Context: force the single-pass K loop (the latency mode's split-K changes the fp32 summation order with the
+    number of output tiles, i.e. with the batch; bit-equality across batch sizes is a property of the throughput path)."""
+    import contextlib
+    from stedm_b200 import ops
+
+    @contextlib.contextmanager
+    def ctx():
+        saved = ops.SPLIT_K[0]
+        ops.SPLIT_K[0] = False
+        try:
+            yield
+        finally:
+            ops.SPLIT_K[0] = saved
+    return ctx()
+
+
 def _small_inputs():
     g = load_golden("small_b2_l32")
     seg, style, x_T = O.synthetic_batch(2, 128, 2, 0)
@@ -177,29 +194,18 @@ def test_batch_shard_invariance():
     g, _, _, x_T = _small_inputs()
     m = build_model(32, n_style=2, precision="bf16")
     tt = torch.full((2,), 481, dtype=torch.long, device="cuda")
-    full = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
-    for r in range(2):
-        cond = {"c_concat": [torch.from_numpy(g["c_concat"][r:r + 1]).cuda()],
-                "c_crossattn": [torch.from_numpy(g["c_crossattn"][r:r + 1]).cuda()]}
-        part = m._model.apply_model(x_T[r:r + 1].cuda(), tt[:1], cond)
-        assert torch.equal(part[0], full[r])
-
-
-def _no_split_k():
-    """Context: force the single-pass K loop (the latency mode's split-K changes the fp32 summation order with the
-    number of output tiles, i.e. with the batch; bit-equality across batch sizes is a property of the throughput path)."""
-    import contextlib
-    from stedm_b200 import ops
-
-    @contextlib.contextmanager
-    def ctx():
-        saved = ops.SPLIT_K[0]
-        ops.SPLIT_K[0] = False
-        try:
-            yield
-        finally:
-            ops.SPLIT_K[0] = saved
-    return ctx()
+    with _no_split_k():      # (the planner splits K differently for 1 and 2 samples: compare like with like)
+        full = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
+        for r in range(2):
+            cond = {"c_concat": [torch.from_numpy(g["c_concat"][r:r + 1]).cuda()],
+                    "c_crossattn": [torch.from_numpy(g["c_crossattn"][r:r + 1]).cuda()]}
+            part = m._model.apply_model(x_T[r:r + 1].cuda(), tt[:1], cond)
+            assert torch.equal(part[0], full[r])
+    # default planning (split-K where few tiles leave SMs idle): the same sums in another fp32 order
+    auto = m._model.apply_model(x_T.cuda(), tt, _cond(g, "c_crossattn"))
+    r = rel_err(auto, full)
+    print(f"split-K (default at this batch) vs single-pass eps rel err {r:.3e}")
+    assert r < BF16_EPS_BAR and rel_err(auto, g["eps_c_481"]) < BF16_EPS_BAR     # bf16 rounding noise, like any reordering
 
 
 def test_bench_geometry_b64_l64_rows_equal_b4_golden_run():
@@ -271,7 +277,8 @@ def test_groupnorm_in_operand_path_matches_separate_apply(L, B):
         finally:
             ops.GN_FUSION[0] = saved
 
-    saved_skip = engine.FUSE_SKIP[0]
+    saved_skip, saved_k = engine.FUSE_SKIP[0], ops.SPLIT_K[0]
+    ops.SPLIT_K[0] = False        # fused launches never split K: compare against single-pass unfused launches
     try:
         engine.FUSE_SKIP[0] = False
         unet.invalidate_packed()
@@ -285,6 +292,7 @@ def test_groupnorm_in_operand_path_matches_separate_apply(L, B):
         unet.invalidate_packed()
     (xf, _), _ = run(True)
     (xu, _), _ = run(False)
+    ops.SPLIT_K[0] = saved_k
     r = rel_err(xf, xu)
     print(f"L={L} B={B}: fused vs separate GroupNorm with fused skip convolutions, rel err {r:.3e}")
     assert r < 2e-3
@@ -298,11 +306,26 @@ def test_cuda_graph_sampler_matches_eager():
     m._model.use_cuda_graph = False
     z0, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw)
     m._model.use_cuda_graph = True
+    m._model.model.diffusion_model.__dict__.pop("_graph_cache", None)
     try:
-        z1, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw)
+        z1, i1 = m._model.sample_log(_cond(g, "c_crossattn"), **kw)     # first call per signature: eager warm-up
+        z2, i2 = m._model.sample_log(_cond(g, "c_crossattn"), **kw)     # captures the whole 20-step loop, replays it
+        kw3 = dict(kw, x_T=(x_T * 0.5).cuda())
+        z3, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw3)     # replay with another x_T
+        cache = m._model.model.diffusion_model.__dict__["_graph_cache"]
+        assert any(k[0] == "loop" for k in cache if isinstance(k, tuple) and k and k[0] == "loop")
     finally:
         m._model.use_cuda_graph = False
-    assert torch.equal(z0, z1)
+    z3e, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw3)
+    assert torch.equal(z0, z1) and torch.equal(z0, z2) and torch.equal(z3, z3e)
+    assert len(i2["x_inter"]) == len(i1["x_inter"]) and all(torch.equal(a, b) for a, b in zip(i1["pred_x0"], i2["pred_x0"]))
+    # per-step path (a caller-driven loop, or any option that needs host-side work per step) still uses the per-pass graph
+    m._model.use_cuda_graph = True
+    try:
+        z4, _ = m._model.sample_log(_cond(g, "c_crossattn"), **dict(kw, img_callback=lambda p, i: None))
+    finally:
+        m._model.use_cuda_graph = False
+    assert torch.equal(z0, z4)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
@@ -323,6 +346,8 @@ def test_shared_trunk_is_bit_identical(precision):
                                unconditional_conditioning=unc)
 
     saved = engine.SPLIT_CONCAT[0]
+    from stedm_b200 import ops as _ops
+    saved_k, _ops.SPLIT_K[0] = _ops.SPLIT_K[0], False      # the trunk runs at B, the two-pass reference at 2B
     try:
         engine.SPLIT_CONCAT[0] = False
         two_pass, shared = step(False), step(True)
@@ -331,6 +356,7 @@ def test_shared_trunk_is_bit_identical(precision):
         split = step(True)
     finally:
         engine.SPLIT_CONCAT[0] = saved
+        _ops.SPLIT_K[0] = saved_k
     r = rel_err(split[0], two_pass[0])
     print(f"{precision} split-concat guided step vs unsplit rel err {r:.3e}")
     assert r < (1e-5 if precision == "fp32" else 5e-3)

@@ -105,6 +105,35 @@ def test_conv_tc_stride2_via_im2col(ops):
     assert max_abs(nchw(got.cpu()), want) < 2e-3
 
 
+@pytest.mark.parametrize("B,cin,cout,H,W", [(2, 128, 128, 32, 32), (3, 64, 512, 64, 64), (1, 192, 64, 16, 32),
+                                            (2, 512, 512, 32, 32), (1, 64, 128, 256, 256)])
+def test_conv_tc_stride2_gather_in_the_tma_unit(ops, B, cin, cout, H, W):
+    """Downsample (openaimodel.py:164-166: 3x3, stride 2, pad 1) inside conv_tc: tensor-map boxes traversed with element
+    stride 2 sample the tile's input positions, out-of-bounds coordinate -1 is the padding; equal to the im2col + GEMM
+    form bit for bit (same K order) and to torch."""
+    g = torch.Generator().manual_seed(B * 7 + cin)
+    x = bf(torch.randn(B, cin, H, W, generator=g))
+    w = bf(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    b = torch.randn(cout, generator=g)
+    emb = torch.randn(B, cout, generator=g)
+    want = F.conv2d(x, w, b, stride=2, padding=1) + emb[:, :, None, None]
+    xd = nhwc(x).to(torch.bfloat16).cuda()
+    m_tiles = B * (H // 2) * (W // 2) // 128
+    stats = torch.zeros((max(1, m_tiles), cout, 2), device="cuda") if ((H // 2) * (W // 2)) % 128 == 0 and cout % 64 == 0 else None
+    got = ops.conv(xd, tc_w(w).cuda(), b.cuda(), cout, 3, stride=2, emb=emb.cuda(), out_dtype=torch.float32,
+                   tensor_core=True, stats_out=stats, split_k=False)
+    assert tuple(got.shape) == (B, H // 2, W // 2, cout)
+    assert max_abs(nchw(got.cpu()), want) < 3e-3, max_abs(nchw(got.cpu()), want)
+    ref = ops.conv(ops.im2col_3x3_s2(xd), tc_w(w).cuda(), b.cuda(), cout, 1, emb=emb.cuda(), out_dtype=torch.float32,
+                   tensor_core=True, split_k=False)
+    assert torch.equal(got, ref)
+    auto = ops.conv(xd, tc_w(w).cuda(), b.cuda(), cout, 3, stride=2, emb=emb.cuda(), out_dtype=torch.float32, tensor_core=True)
+    assert max_abs(auto, got) < 1e-4 * max(1.0, float(want.abs().max()))
+    if stats is not None:
+        t = nhwc(want).reshape(-1, 128, cout)
+        assert max_abs(stats[..., 0].cpu(), t.sum(1)) < 0.05
+
+
 def test_conv_tc_rejects_unsupported(ops):
     x = torch.zeros(1, 12, 12, 64, device="cuda", dtype=torch.bfloat16)   # width 12 does not tile 128 pixels
     w = torch.zeros(64, 9 * 64, device="cuda", dtype=torch.bfloat16)
@@ -217,22 +246,27 @@ def test_conv_tc_split_k_small_batch(ops, B, hw, cin, cout, k):
     emb = torch.randn(B, cout, generator=g)
     want = F.conv2d(x, w, b, padding=k // 2) + res + emb[:, :, None, None]
     xd, wd = nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda()
-    from stedm_b200 import _lib
-    import ctypes
-    ops.enable_split_k(True)
-    try:
-        got = ops.conv(xd, wd, b.cuda(), cout, k, emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(),
-                       out_dtype=torch.float32, tensor_core=True)
-    finally:
-        ops.enable_split_k(False)
-    assert got._stats_written is False
+    assert ops.SPLIT_K[0], "split-K is the default for launches with few output tiles"
+    got = ops.conv(xd, wd, b.cuda(), cout, k, emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(),
+                   out_dtype=torch.float32, tensor_core=True)
     assert max_abs(nchw(got.cpu()), want) < 3e-3
-    # the same launch with split-K disabled by withholding the workspace is covered by the other tests; here check
-    # that a statistics request forces the single-pass path
-    tiles = torch.empty((max(1, B * hw * hw // 128), cout, 2), device="cuda")
+    single = ops.conv(xd, wd, b.cuda(), cout, k, emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(),
+                      out_dtype=torch.float32, tensor_core=True, split_k=False)
+    assert max_abs(got, single) < 1e-4 * max(1.0, float(want.abs().max()))   # the same sum in another fp32 order
+    again = ops.conv(xd, wd, b.cuda(), cout, k, emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(),
+                     out_dtype=torch.float32, tensor_core=True)
+    assert torch.equal(got, again)                                            # fixed-order reduce: deterministic
+    # the finish pass publishes the GroupNorm tile statistics of a split launch, like the single-pass epilogue
     if (hw * hw) % 128 == 0:
+        m_tiles = B * hw * hw // 128
+        tiles, tiles1 = torch.zeros((m_tiles, cout, 2), device="cuda"), torch.zeros((m_tiles, cout, 2), device="cuda")
         got2 = ops.conv(xd, wd, b.cuda(), cout, k, out_dtype=torch.float32, tensor_core=True, stats_out=tiles)
-        assert max_abs(nchw(got2.cpu()), F.conv2d(x, w, b, padding=k // 2)) < 3e-3
+        ops.conv(xd, wd, b.cuda(), cout, k, out_dtype=torch.float32, tensor_core=True, stats_out=tiles1, split_k=False)
+        assert got2._stats_written
+        want2 = F.conv2d(x, w, b, padding=k // 2)
+        assert max_abs(nchw(got2.cpu()), want2) < 3e-3
+        t = nhwc(want2).reshape(m_tiles, 128, cout)
+        assert max_abs(tiles[..., 0].cpu(), t.sum(1)) < 0.05 and max_abs(tiles, tiles1) < 0.05
 
 
 @pytest.mark.parametrize("B,hw,cmid,cs0,cs1,co,sb", [
@@ -326,7 +360,7 @@ def test_conv_tc_groupnorm_in_operand_path_is_bit_equal_to_apply_then_conv(ops, 
     kw = dict(emb=emb.cuda(), residual=res.cuda(), out_dtype=torch.bfloat16, tensor_core=True)
     m_tiles = B * H * W // 128
     t_ref, t_fus = torch.zeros((m_tiles, cout, 2), device="cuda"), torch.zeros((m_tiles, cout, 2), device="cuda")
-    ref = ops.conv(a, tc_w(w).cuda(), bias.cuda(), cout, 3, stats_out=t_ref, **kw)
+    ref = ops.conv(a, tc_w(w).cuda(), bias.cuda(), cout, 3, stats_out=t_ref, split_k=False, **kw)
     fus = ops.conv(x0d, tc_w(w).cuda(), bias.cuda(), cout, 3, x1=x1d, stats_out=t_fus, gn_coef=coef, gn_silu=silu, **kw)
     torch.cuda.synchronize()
     assert torch.equal(ref, fus), float((ref.float() - fus.float()).abs().max())
@@ -360,7 +394,7 @@ def test_conv_tc_groupnorm_in_operand_path_with_fused_skip_and_channel_slices(op
     wcat = torch.cat([tc_w(w3), tc_w(w1)], 1).contiguous().cuda()
     assert ops.conv_gn_fusable(B, hw, hw, cm, co, 256)
     kw = dict(out_dtype=torch.float32, tensor_core=True, skip_x0=k0.cuda(), skip_x1=k1.cuda())
-    ref = ops.conv(a, wcat, bias.cuda(), co, 3, **kw)
+    ref = ops.conv(a, wcat, bias.cuda(), co, 3, split_k=False, **kw)
     fus = ops.conv(h.cuda(), wcat, bias.cuda(), co, 3, gn_coef=coef, **kw)
     assert torch.equal(ref, fus), float((ref - fus).abs().max())
     # split concat: GN over [h (512) | s (512, Bs samples)], shared channels [sp, 1024) convolved once per distinct sample
@@ -375,8 +409,9 @@ def test_conv_tc_groupnorm_in_operand_path_with_fused_skip_and_channel_slices(op
     wv = wc.permute(0, 2, 3, 1)                                                   # [co, 3, 3, C]
     w_lo = wv[..., :sp].reshape(co, -1).to(torch.bfloat16).contiguous().cuda()
     w_hi = wv[..., sp:].reshape(co, -1).to(torch.bfloat16).contiguous().cuda()
-    part_ref = ops.conv(a2[:Bs, :, :, sp:], w_hi, None, co, 3, out_dtype=torch.float32, tensor_core=True)
-    ref2 = ops.conv(a2[..., :sp], w_lo, bias.cuda(), co, 3, residual=part_ref, out_dtype=torch.bfloat16, tensor_core=True)
+    part_ref = ops.conv(a2[:Bs, :, :, sp:], w_hi, None, co, 3, out_dtype=torch.float32, tensor_core=True, split_k=False)
+    ref2 = ops.conv(a2[..., :sp], w_lo, bias.cuda(), co, 3, residual=part_ref, out_dtype=torch.bfloat16, tensor_core=True,
+                    split_k=False)
     sd = s.cuda()
     part = ops.conv(sd[:, :, :, sp - cm:], w_hi, None, co, 3, out_dtype=torch.float32, tensor_core=True, gn_coef=coef2,
                     gn_c_off=sp)
