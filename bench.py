@@ -15,6 +15,7 @@ LDM_Diffusion.predict-style calls with pinned HOST buffers, H2D and D2H inside t
 Python and cannot be installed offline: pytorch_lightning / taming / omegaconf are absent) on a bounded sample.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -130,9 +131,11 @@ def build_model(latent, n_style, precision):
 # ----------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores, bounded sample
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(latent, n_style, sample_batch=1, sample_steps=1, sd=None):
-    """Times cond x2 + `sample_steps` guided DDIM steps + decode for `sample_batch` images on all host threads and
-    scales the loop to DDIM-50: images/s = B / (t_cond + 50 * t_step + t_decode)."""
+def cpu_reference_sample(latent, n_style, sample_batch=1, sample_steps=None, sd=None):
+    """One pass of the reference's algorithm (oracle port) for `sample_batch` images on all host threads: conditioning x2,
+    guided DDIM steps (all DDIM_STEPS of them when ``sample_steps`` is None — then images/s is plain measured wall time —
+    otherwise the first `sample_steps`, with the loop time scaled to DDIM_STEPS and the result marked as extrapolated),
+    VQ decode, uint8."""
     from oracle import stedm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     P = 4 * latent
@@ -140,41 +143,53 @@ def cpu_reference_sample(latent, n_style, sample_batch=1, sample_steps=1, sd=Non
         from tests.util import oracle_state_dict
         sd = oracle_state_dict(build_model(latent, n_style, "bf16")._model)
     seg, style, x_T = O.synthetic_batch(sample_batch, P, n_style, seed=11)
+    n_steps = DDIM_STEPS if sample_steps is None else sample_steps
     with torch.no_grad():
         t0 = time.perf_counter()
         cond = O.get_conditioning(sd, seg, style)
         unc = O.get_conditioning(sd, seg, torch.zeros_like(style) - 2)
         t1 = time.perf_counter()
-        z, _ = O.ddim_sample(sd, cond, unc, x_T, S=DDIM_STEPS, cfg_scale=CFG_SCALE, max_steps=sample_steps)
+        z, _ = O.ddim_sample(sd, cond, unc, x_T, S=DDIM_STEPS, cfg_scale=CFG_SCALE, max_steps=n_steps)
         t2 = time.perf_counter()
         img = O.decode_first_stage(sd, z)
         O.to_uint8(img)
         t3 = time.perf_counter()
-    t_cond, t_step, t_dec = t1 - t0, (t2 - t1) / sample_steps, t3 - t2
-    per_batch = t_cond + DDIM_STEPS * t_step + t_dec
-    return dict(value=sample_batch / per_batch, seconds_measured=t3 - t0, t_cond=t_cond, t_ddim_step=t_step,
-                t_decode=t_dec, cores=torch.get_num_threads(),
-                sample=(f"batch {sample_batch} at {P}x{P}: conditioning x2 + {sample_steps} of {DDIM_STEPS} guided DDIM "
-                        f"steps (2 U-Net passes each) + VQ decode, loop time scaled x{DDIM_STEPS}/{sample_steps}"))
+    t_cond, t_loop, t_dec = t1 - t0, t2 - t1, t3 - t2
+    per_batch = t_cond + t_loop * (DDIM_STEPS / n_steps) + t_dec
+    full = n_steps == DDIM_STEPS
+    what = (f"all {DDIM_STEPS} guided DDIM steps (2 U-Net passes each), measured wall time" if full else
+            f"{n_steps} of {DDIM_STEPS} guided DDIM steps (2 U-Net passes each), loop time scaled x{DDIM_STEPS}/{n_steps}")
+    return dict(value=sample_batch / per_batch, seconds_measured=t3 - t0, seconds_per_pass=per_batch, t_cond=t_cond,
+                t_ddim_loop=t_loop, t_decode=t_dec, cores=torch.get_num_threads(), extrapolated=not full,
+                sample=f"batch {sample_batch} at {P}x{P}: conditioning x2 + {what} + VQ decode")
 
 
 def run_reference_arm(args, emit):
+    """`--impl reference`: the reference's own algorithm (oracle port, fp32, every host thread) on the native arm's
+    workload, each step = ONE FULL pass (conditioning x2 + DDIM-50 with guidance + decode) for a batch of `--ref-batch`
+    images, timed wall clock — ms_per_step x steps is what the run actually took."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, last = [], None
-    sd = None
     from tests.util import oracle_state_dict
     sd = oracle_state_dict(build_model(args.latent, args.n_style, "bf16")._model)
+    secs, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(args.latent, args.n_style, 1, 1, sd)
+        # untimed warm-up passes (thread pool, allocator, oneDNN primitive caches) run 2 of the 50 DDIM steps; every
+        # TIMED pass is the full loop
+        last = cpu_reference_sample(args.latent, args.n_style, args.ref_batch, 2 if i < args.warmup else None, sd)
         if i >= args.warmup:
-            vals.append(last["value"])
-    v = float(np.mean(vals))
+            secs.append(last["seconds_per_pass"])
+    ms = 1000.0 * float(np.mean(secs))
+    v = args.ref_batch / (ms / 1000.0)
+    cfg = workload_config(args)
+    cfg["batch_per_gpu"] = args.ref_batch      # what this arm ran: the CPU path at the native arm's batch would take hours
+    cfg["workload"] = cfg["workload"].replace(f"batch {args.batch} per GPU", f"batch {args.ref_batch} on the host CPU")
+    cfg["parallelism"] = f"{last['cores']} host threads, no GPU"
     line = {"metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args),
+            "config": cfg,
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": last["cores"], "kind": "port",
                              "sample": last["sample"]},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,6 +223,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the U-Net pass eagerly instead of replaying the "
                                                             "CUDA graph cached per shape (measured: +2 %% at B=64)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true", help="no HER2 / 512^2 / torch-eager side measurements")
+    ap.add_argument("--ref-batch", type=int, default=1, dest="ref_batch",
+                    help="images per pass of the CPU reference arm (a full DDIM-50 pass per step)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -287,9 +305,34 @@ def main():
         ms = timed(resident_step, args.steps)
         launches = ops.LAUNCHES[0] - l0
         clk = clocks.stop() if rank == 0 else None
-        e2e_step()
+        u8_last = e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
+        # rank 0's shard = global samples 0..B-1 with the same seeds at every N: the digest must not depend on N
+        digest = hashlib.sha256(u8_last.cpu().numpy().tobytes()).hexdigest() if rank == 0 else None
+        strong = None
+        if world > 1 and B % world == 0:
+            # strong scaling: ONE global batch of B images split over the ranks (rank r takes samples r*B/N ...)
+            bs = B // world
+            sh = synthetic_batch(bs, P, args.n_style, rank * bs)
+            sdev = [t.to(dev) for t in sh]
+            part = [torch.empty((bs, P, P, 3), dtype=torch.uint8, device=dev) for _ in range(world)]
+
+            def strong_step():
+                u8 = m.generate(m.prepare_batch((sdev[0], sdev[1].clone(), None, sdev[2], None)), x_T=sdev[3])
+                dist.all_gather(part, u8)
+                return u8
+
+            for _ in range(max(3, args.warmup)):
+                strong_step()
+            ms_s = timed(strong_step, args.steps)
+            strong = {"global_batch": B, "batch_per_gpu": bs, "value": B * args.steps / (ms_s / 1000.0), "unit": "images/s",
+                      "ms_per_step": ms_s / args.steps}
         roof = kernel_roofline(m, devb, B, L, args) if rank == 0 else None
+        secondary = None
+        if rank == 0 and world == 1 and not args.skip_secondary and (B, L, args.n_style) == (64, 64, 1):
+            del m
+            torch.cuda.empty_cache()
+            secondary = secondary_measurements(dev, args)
 
     if world > 1:
         dist.destroy_process_group()
@@ -306,12 +349,114 @@ def main():
             "e2e": {"value": n_img / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "unet_step_ms": roof.pop("unet_step_ms"), "unet_step_frac_of_peak": roof.pop("unet_step_frac"),
-            "roofline": roof}
+            "roofline": roof, "images_sha256": digest}
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if secondary is not None:
+        line["secondary"] = secondary
     if world == 1 and not args.skip_cpu_baseline:
-        cb = cpu_reference_sample(L, args.n_style, 1, 1)
+        cb = cpu_reference_sample(L, args.n_style, 1, 2)      # bounded: 2 guided steps of 50, scaled (the reference arm
+        # of this script, --impl reference, times full DDIM-50 passes)
         line["cpu_baseline"] = {"value": cb["value"], "unit": "images/s", "cores": cb["cores"], "kind": "port",
                                 "sample": cb["sample"]}
     emit(line)
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the dominant kernel's 1024->1024 3x3 @16x16
+    launch on 128 samples, read from the newest committed `ncu --set full` summary profiles/rNN_ncu_full_conv_tc.csv
+    (first kernel row; algorithmic bytes of that launch: 153 MB = 67 MB input + 19 MB weights + 67 MB output)."""
+    import csv
+    import glob
+    import re
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_conv_tc.csv")) if re.search(r"r\d+_ncu_full_conv_tc\.csv$", f)]
+    if not files:
+        return None
+    try:
+        with open(sorted(files)[-1], newline="") as fh:
+            rows = list(csv.reader(fh))
+        head, units, first = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = head.index(name)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            tot += float(first[i]) * scale
+        return tot
+    except Exception:
+        return None
+
+
+def secondary_measurements(dev, args):
+    """Driver-visible side numbers (rank 0, N = 1 only; each a short run after the headline measurement):
+    BASELINE configs[2] (HER2-style N = 10 style images per sample), configs[3] geometry on one GPU (512^2, latent 128),
+    and configs[4]'s kernel bar: the U-Net eps step of the reference's algorithm under torch eager (cuDNN / cuBLAS, TF32
+    as predict_diff.py:68 sets, and bf16 autocast) on this same B200 next to the native pass."""
+    out = {}
+
+    def run_cfg(latent, n_style, batch, steps):
+        P = 4 * latent
+        mm = build_model(latent, n_style, args.precision).to(dev).eval()
+        mm._model.use_cuda_graph = not args.no_graph
+        b = [t.to(dev) for t in synthetic_batch(batch, P, n_style, 0)]
+        fn = lambda: mm.generate(mm.prepare_batch((b[0], b[1].clone(), None, b[2], None)), x_T=b[3])
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return mm, {"value": batch / (ms / 1000.0), "unit": "images/s", "ms_per_step": ms, "batch": batch, "image": P,
+                    "style_images_per_sample": n_style, "steps": steps, "warmup": 3}
+
+    mm, out["her2_n10_256"] = run_cfg(64, 10, 64, 2)
+    # configs[4]: one U-Net eps pass, native (graph replay, as the sampler runs it) vs torch eager on the same GPU
+    from oracle import stedm_oracle as O
+    from tests.util import oracle_state_dict
+    unet = mm._model.model.diffusion_model
+    sd = {k: v.to(dev) for k, v in oracle_state_dict(mm._model).items() if k.startswith(O.UNET)}
+    g = torch.Generator().manual_seed(5)
+    Bq = 64
+    x, cc = torch.randn(Bq, 3, 64, 64, generator=g).to(dev), torch.randn(Bq, 3, 64, 64, generator=g).to(dev)
+    ctx, t = torch.randn(Bq, 512, generator=g).to(dev), torch.full((Bq,), 481, dtype=torch.long, device=dev)
+
+    def time_ms(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    with torch.no_grad():
+        native = time_ms(lambda: unet.forward_split(x, cc, t, ctx), 5, 10)
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cudnn.benchmark = True
+        xc = torch.cat([x, cc], 1)
+        eager32 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), 12, 10)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            eager16 = time_ms(lambda: O.unet_forward(sd, xc, t, ctx), 12, 10)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = tf32
+    out["torch_eager_b200"] = {"what": "one U-Net eps pass, batch 64, latent 64 (217.29 GFLOP per sample): the reference's "
+                                       "UNetModel.forward restated functionally (oracle, pinned bit-equal to the reference on "
+                                       "CPU) under torch eager on this GPU, 12 warm-up passes, vs the native pass",
+                               "native_ms": native, "torch_tf32_ms": eager32, "torch_bf16_autocast_ms": eager16,
+                               "speedup_vs_tf32": eager32 / native, "speedup_vs_bf16_autocast": eager16 / native}
+    del mm, unet, sd
+    torch.cuda.empty_cache()
+    mm, out["catch_512"] = run_cfg(128, 1, 64, 1)
+    del mm
+    torch.cuda.empty_cache()
+    return out
 
 
 def kernel_roofline(m, devb, B, L, args):
@@ -379,7 +524,7 @@ def kernel_roofline(m, devb, B, L, args):
             # dram__bytes_read.sum + dram__bytes_write.sum of the 1024->1024 3x3 @16x16 (128 samples) launch from the
             # committed `ncu --set full` capture profiles/r01_ncu_full_conv_tc.csv, row 1 (algorithmic bytes: 153 MB =
             # 67 MB input + 19 MB weights + 67 MB output; part of the input is still L2-resident from its producer)
-            "traffic": 131.3e6 if (B == 64 and L == 64) else None,
+            "traffic": ncu_traffic_bytes() if (B == 64 and L == 64) else None,
             "launches_timed": len(big), "avg_launch_ms": big_ms / max(1, len(big)),
             "algorithmic_flops_per_launch": big_fl / max(1, len(big)),
             "all_tc_conv": {"launches": len(rec), "ms": tot_ms, "tflops": tot_fl / (tot_ms / 1e3) / 1e12 if tot_ms else 0.0,
