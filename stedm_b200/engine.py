@@ -598,13 +598,13 @@ class DecoderRunner:
         # q, k, v 1x1 convs stacked into one GEMM: output channels [q | k | v]
         wq = torch.cat([at.q.weight, at.k.weight, at.v.weight], 0)
         bq = torch.cat([at.q.bias, at.k.bias, at.v.bias], 0)
-        if prec.tc:
-            # tensor-core path: separate dense q, k and (channel-major) v^T tensors feed two GEMMs per sample
+        self.att_qkv = PackedConv(wq, bq, prec)
+        if prec.tc and not ops.attention_tc_supported(at.q.weight.shape[0], 0, heads=1):
+            # widths the flash kernel does not take: separate dense q, k and (channel-major) v^T tensors feed two
+            # tensor-core GEMMs per sample around a row softmax
             self.att_q = PackedConv(at.q.weight, at.q.bias, prec)
             self.att_k = PackedConv(at.k.weight, at.k.bias, prec)
             self.att_v = PackedConv(at.v.weight, at.v.bias, prec)
-        else:
-            self.att_qkv = PackedConv(wq, bq, prec)
         self.att_proj = PackedConv(at.proj_out.weight, at.proj_out.bias, prec)
         self.att_c = at.q.weight.shape[0]
         self.mid2 = res(d.mid.block_2)
@@ -649,11 +649,16 @@ class DecoderRunner:
         a = self.att_norm(x, None, False, prec.act, pool.next())
         scale = float(Cc) ** -0.5
         if prec.tc and not (tc_geometry_ok(1, H, W) and T % 16 == 0):
-            # a map the tensor-core kernel cannot tile (e.g. 96 x 96): materialised attention on CUDA cores
-            q, k, v = self.att_q(a), self.att_k(a), self.att_v(a)
-            outs = [ops.attention_simt(q[i:i + 1], k[i:i + 1], v[i:i + 1], 1, Cc, T, 0, 0, 0, Cc, Cc, scale, prec.act)
-                    for i in range(B)]
+            # a map the tensor-core kernels cannot tile (e.g. 96 x 96): materialised attention on CUDA cores
+            qkv = self.att_qkv(a)
+            outs = [ops.attention_simt(qkv[i:i + 1], qkv[i:i + 1], qkv[i:i + 1], 1, Cc, T, 0, Cc, 2 * Cc, 3 * Cc, Cc, scale,
+                                       prec.act) for i in range(B)]
             o = outs[0] if B == 1 else torch.cat(outs, 0)
+        elif prec.tc and ops.attention_tc_supported(Cc, T, heads=1):
+            # flash attention for the single 512-wide head: q | k | v from ONE 1x1 convolution, no T x T tensor, one
+            # launch for the whole batch (stedm_attention_tc's wide kernel)
+            qkv = self.att_qkv(a).view(B, T, 3 * Cc)
+            o = ops.attention_tc(qkv, qkv, qkv, 1, Cc, T, (T * 3 * Cc, Cc, 3 * Cc), scale, q_off=0, k_off=Cc, v_off=2 * Cc)
         elif prec.tc:
             # d = 512 is too wide for one CTA's TMEM (S + O accumulators), so the decoder attention runs as two
             # tensor-core GEMMs per sample on the implicit-GEMM kernel: S = Q K^T (K as the "weight" [T][C]) into a

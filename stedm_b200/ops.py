@@ -313,9 +313,10 @@ def attention_simt(q_src, k_src, v_src, heads, head_dim, tokens, q_off, k_off, v
     return out
 
 
-def attention_tc_supported(head_dim, tokens):
-    """Shapes the fused tcgen05 attention kernel takes (stedm_attention_tc)."""
-    return head_dim in (64, 128)
+def attention_tc_supported(head_dim, tokens, heads=None):
+    """Shapes the fused tcgen05 attention kernels take (stedm_attention_tc): 64 / 128 channels per head, or ONE 512-wide
+    head (the VAE decoder's AttnBlock: the wide kernel splits the output channels over two CTAs)."""
+    return head_dim in (64, 128) or (head_dim == 512 and heads == 1)
 
 
 def attention_tc(q, k, v, heads, head_dim, tokens, strides, scale, q_off=0, k_off=0, v_off=0, mask_diag=False,

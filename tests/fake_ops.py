@@ -156,7 +156,7 @@ def _conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, ou
     return _nhwc(y).to(out_dtype or x0.dtype)
 
 
-def attention_tc_supported(head_dim, tokens):
+def attention_tc_supported(head_dim, tokens, heads=None):
     return False
 
 

@@ -179,6 +179,54 @@ def test_attention_tc_legacy_layout(ops, heads, ch, T, B):
     assert err < 2e-2 * max(1.0, float(want.abs().max())), err
 
 
+@pytest.mark.parametrize("B,T,Tkv", [(2, 1024, 0), (1, 4096, 0), (3, 200, 0), (2, 256, 77)])
+def test_attention_tc_wide_single_head_d512(ops, B, T, Tkv):
+    """The VAE decoder's AttnBlock (model.py:178-202: one head, d = 512, scale 512^-1/2) on the wide flash kernel — Q
+    resident, K / V streamed in 64-channel slabs, output channels split over two CTAs, no T x T tensor: against fp32
+    softmax(q k^T / sqrt(d)) v of the same bf16-rounded q | k | v buffer; ragged T (keys masked, rows not stored) and a
+    separate key / value length."""
+    g = torch.Generator().manual_seed(T + B)
+    C = 512
+    qkv = bf(torch.randn(B, T, 3 * C, generator=g))
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    buf = qkv.to(torch.bfloat16).cuda()
+    scale = C ** -0.5
+    if Tkv:
+        kv = bf(torch.randn(B, Tkv, 2 * C, generator=g))
+        k, v = kv[..., :C], kv[..., C:]
+        kvd = kv.to(torch.bfloat16).cuda()
+        got = ops.attention_tc(buf, kvd, kvd, 1, C, T, (T * 3 * C, C, 3 * C), scale, q_off=0, k_off=0, v_off=C,
+                               tokens_kv=Tkv, kv_strides=(Tkv * 2 * C, C, 2 * C))
+    else:
+        got = ops.attention_tc(buf, buf, buf, 1, C, T, (T * 3 * C, C, 3 * C), scale, q_off=0, k_off=C, v_off=2 * C)
+    torch.cuda.synchronize()
+    # peaky logits too: scale q up for half of the samples' rows so that the running maximum keeps moving
+    w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) * scale, dim=-1)
+    want = torch.einsum("bts,bsc->btc", w, v)
+    assert tuple(got.shape) == (B, T, C)
+    err = max_abs(got.float().cpu(), want)
+    assert err < 2e-2 * max(1.0, float(want.abs().max())), err
+    assert ops.attention_tc_supported(512, T, heads=1) and not ops.attention_tc_supported(512, T, heads=2)
+
+
+def test_attention_tc_wide_moving_maximum(ops):
+    """Online softmax with a maximum that keeps growing along the keys (the O rescale path in TMEM) and rows whose
+    maximum never moves after the first tile (the warp-uniform skip)."""
+    g = torch.Generator().manual_seed(9)
+    B, T, C = 1, 512, 512
+    q = bf(torch.randn(B, T, C, generator=g))
+    k = bf(torch.randn(B, T, C, generator=g) * torch.linspace(0.2, 3.0, T)[None, :, None])   # later keys: larger logits
+    k[:, :, :] = torch.where(torch.arange(T)[None, :, None] < 128, k, k)                   # (first tile unchanged)
+    q[:, :64] *= 0.0                                                                        # flat rows: maximum 0 everywhere
+    v = bf(torch.randn(B, T, C, generator=g))
+    buf = torch.cat([q, k, v], -1).to(torch.bfloat16).cuda()
+    got = ops.attention_tc(buf, buf, buf, 1, C, T, (T * 3 * C, C, 3 * C), C ** -0.5, q_off=0, k_off=C, v_off=2 * C)
+    w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) * C ** -0.5, dim=-1)
+    want = torch.einsum("bts,bsc->btc", w, v)
+    err = max_abs(got.float().cpu(), want)
+    assert err < 2e-2 * max(1.0, float(want.abs().max())), err
+
+
 def test_softmax_rows_scaled_bf16(ops):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(300, 1000, generator=g) * 3
