@@ -56,7 +56,8 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
             objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    # (the arch flags on the link line keep nvcc from adding an empty default-arch cubin: the library is sm_100a only)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

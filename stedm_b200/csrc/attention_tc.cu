@@ -280,10 +280,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int AW_D = 512;              // head dim (q / k channels)
 constexpr int AW_OD = 256;             // output channels per CTA
-constexpr int AW_RING = 4;
+#ifndef STEDM_AW_P_TMEM
+#define STEDM_AW_P_TMEM 1   // P (bf16 probabilities) stays in TMEM, aliased over the S buffer it came from, and feeds the
+#endif                      // P V product as a TMEM A operand: no 32 KB staging buffer -> a six-slab K / V ring
+constexpr bool AW_P_TMEM = STEDM_AW_P_TMEM != 0;
+constexpr int AW_RING = AW_P_TMEM ? 6 : 4;
 constexpr int AW_SLAB = AT_BN * 128;   // 16 KB: 128 rows x 64 bf16
 constexpr int AW_Q_BYTES = AT_BM * AW_D * 2;
-constexpr int AW_P_BYTES = AT_BM * AT_BN * 2;
+constexpr int AW_P_BYTES = AW_P_TMEM ? 0 : AT_BM * AT_BN * 2;
 constexpr int AW_SMEM_BYTES = AW_Q_BYTES + AW_RING * AW_SLAB + AW_P_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -384,9 +388,13 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           const uint32_t sv = smem_u32(s_ring + slot * AW_SLAB);
 #pragma unroll
           for (int kk = 0; kk < AT_BN / 16; ++kk) {
-            const uint32_t poff = (kk / 4) * AW_SLAB + (kk % 4) * 32;
             const uint64_t vdesc = umma_desc_mn_sw128(sv + kk * 16 * 128, AW_SLAB, 1024);
-            umma_bf16(tmem_o + d * 64, umma_desc_sw128(smem_u32(s_p) + poff), vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            if constexpr (AW_P_TMEM) {   // A = P from TMEM: 16 keys = 8 packed columns of the S buffer P was written over
+              umma_bf16_ts(tmem_o + d * 64, tmem_base + (j & 1) * 128 + kk * 8, vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            } else {
+              const uint32_t poff = (kk / 4) * AW_SLAB + (kk % 4) * 32;
+              umma_bf16(tmem_o + d * 64, umma_desc_sw128(smem_u32(s_p) + poff), vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&r_empty[slot]);
           if (++slot == AW_RING) { slot = 0; ph ^= 1; }
@@ -450,16 +458,22 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           l_tile += __low2float(h2) + __high2float(h2);   // the sum of what the P V product actually consumes
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        uint8_t* slab = s_p + (c / 64) * AW_SLAB + (row / 8) * 1024 + (row % 8) * 128;
+        if constexpr (AW_P_TMEM) {
+          // columns [c / 2, c / 2 + 16) of this S buffer: all of them were read by this or an earlier chunk
+          tmem_st16(tmem_s + lane_addr + c / 2, pk);
+        } else {
+          uint8_t* slab = s_p + (c / 64) * AW_SLAB + (row / 8) * 1024 + (row % 8) * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c % 64) / 8 + g) ^ (row % 8);
-          *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = ((c % 64) / 8 + g) ^ (row % 8);
+            *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         }
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      fence_proxy_async_smem();
+      if constexpr (AW_P_TMEM) tmem_st_wait();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
