@@ -501,7 +501,8 @@ def kernel_roofline(m, devb, B, L, args):
         taps = 4 if kw.get("up_phase") is not None else ksize * ksize   # executed taps (folded upsample: 4, not 9)
         sk = kw.get("skip_x0")      # fused 1x1 skip convolution: extra K columns
         skc = 0 if sk is None else sk.shape[-1] + (0 if kw.get("skip_x1") is None else kw["skip_x1"].shape[-1])
-        rec.append((a, b, 2.0 * bsz * h * w * cout * (taps * (c0 + c1) + skc), cout))
+        st = kw.get("stride", 1)                                        # stride 2: GEMM rows = output pixels
+        rec.append((a, b, 2.0 * bsz * (h // st) * (w // st) * cout * (taps * (c0 + c1) + skc), cout))
         return out
 
     ops.conv = timed_conv

@@ -620,8 +620,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool valid = m < p.M;
       const int b = valid ? m / p.HW : 0;
       const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
-      mbar_wait(&tmem_full_bar[acc], acc_ph);
-      tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
       // NHWC offset (elements) of output row mm at channel 0 (tap_mode 1: pixel (y, x) of this sub-pixel phase lands at
       // (2y + py, 2x + px) of the [B, 2H, 2W, C] output)
@@ -631,7 +629,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         return ((static_cast<size_t>(bb) * 2 * p.H + 2 * y + p.py) * (2 * p.W) + 2 * x + p.px) * p.cout;
       };
       const size_t o_row = valid ? row_offset(m) : 0;
-      uint8_t* stg = s_out + quad * (32 * 64);  // this warp's staging rows
+      const uint32_t stg = smem_u32(s_out) + quad * (32 * 64);  // this warp's staging rows (32-bit shared address: LDS / STS)
       // rows this lane stores after the transpose: (lane / 4) + 8 i of the warp's 32, i < 4
       size_t roff[4];
       bool rok[4];
@@ -641,10 +639,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         rok[i] = mm < p.M;
         roff[i] = rok[i] ? row_offset(mm) : 0;
       }
+      // bf16 residual (identity skip): a thread reads its own pixel row, and the tensor was written layers ago — the
+      // chunk's 64 bytes are requested ONE CHUNK AHEAD (the first chunk before the wait for the accumulator), so the
+      // DRAM / L2 latency overlaps the previous chunk's work instead of stalling every chunk (ncu source page, round 2:
+      // 14 % of all stall samples of the 128 -> 128 launch sat on the first use of the loaded residual)
+      constexpr bool RES_PF = CH == 32;
+      const bool res_bf16 = RES_PF && valid && p.residual != nullptr && p.res_dtype == DT_BF16 && p.ksplit == 1 && !p.out_nchw;
+      const __nv_bfloat16* res_row = nullptr;
+      if (res_bf16)
+        res_row = static_cast<const __nv_bfloat16*>(p.residual) +
+                  (p.res_rows > 0 ? static_cast<size_t>(m % p.res_rows) * p.cout : o_row);
+      uint4 rnx[4];
+      auto load_res = [&](int nn) {
+        if (res_bf16 && nn < p.cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_row + nn);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rnx[k] = __ldg(rp + k);
+        }
+      };
+      load_res(n_base);
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN; c += CH) {
         const int n = n_base + c;
         if (n >= p.cout) break;  // partially filled last channel tile (cout % BN != 0): nothing to store
+        uint4 rcur[4];
+        if constexpr (RES_PF) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rcur[k] = rnx[k];
+          if (c + CH < BN) load_res(n + CH);
+        }
         float v[CH], add[CH];
         if constexpr (CH == 32) {
           uint32_t r[32];
@@ -717,7 +742,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + o_res);
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
-              const uint4 u = rp[j / 8];
+              uint4 u;
+              if constexpr (RES_PF) u = res_bf16 ? rcur[j / 8] : rp[j / 8];
+              else u = rp[j / 8];
               float2 f;
               f = unpack_bf16x2(u.x); v[j] += f.x; v[j + 1] += f.y;
               f = unpack_bf16x2(u.y); v[j + 2] += f.x; v[j + 3] += f.y;
@@ -758,16 +785,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (p.out_dtype == DT_BF16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              sts128(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                     make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = (lane >> 2) + 8 * i;
               if (rok[i])
                 *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + roff[i] + n + jj * 8) =
-                    *reinterpret_cast<const uint4*>(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+                    lds128(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
             }
             __syncwarp();
           } else {
@@ -775,15 +802,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int h = 0; h < 2; ++h) {  // 16 fp32 channels = 64 B per pass
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                    make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+                sts128(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(__float_as_uint(v[16 * h + 4 * j]), __float_as_uint(v[16 * h + 4 * j + 1]),
+                                  __float_as_uint(v[16 * h + 4 * j + 2]), __float_as_uint(v[16 * h + 4 * j + 3])));
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rr = (lane >> 2) + 8 * i;
                 if (rok[i])
-                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + roff[i] + n + 16 * h + jj * 4) =
-                      *reinterpret_cast<const float4*>(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+                  *reinterpret_cast<uint4*>(static_cast<float*>(p.out) + roff[i] + n + 16 * h + jj * 4) =
+                      lds128(stg + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
               }
               __syncwarp();
             }

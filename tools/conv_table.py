@@ -46,6 +46,8 @@ def main():
             out = orig(x0, weight, bias, cout, ksize, **kw)
             e1.record()
             b, h, w, c0 = x0.shape
+            st = kw.get("stride", 1)
+            h, w = h // st, w // st                                      # stride 2: GEMM rows = output pixels
             c1 = 0 if kw.get("x1") is None else kw["x1"].shape[-1]
             taps = 4 if kw.get("up_phase") is not None else ksize * ksize
             sk = kw.get("skip_x0")
