@@ -99,6 +99,10 @@ struct TcParams {
   int m_pad;            // rows of one workspace slice (all tiles, including the out-of-bounds one)
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
+  // 2-D pixel tiles (3x3 convolutions on maps at least 32 wide): a tile is 16 columns x 8 rows of one sample instead of
+  // 128 consecutive pixels, so that the halo box (10 x 16 pixels, 20 KB) carries 25 % extra rows whatever the map width —
+  // full-row tiles need 2 x (W = 64) or cannot use halo boxes at all (W >= 128)
+  int tile2d, txs, tps;  // flag, tiles per tile row (W / 16), tiles per sample (H * W / 128)
   int cs;                // input pixels per output pixel (2 for the stride-2 Downsample convolution: strided TMA boxes)
   int tap_mode, py, px;  // tap_mode 1: 2x2 sub-pixel phase (py, px) of nearest-x2-upsample + 3x3 conv
   int act;               // STEDM_ACT_*: applied to acc + bias + emb, before the residual
@@ -124,6 +128,32 @@ struct TcParams {
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
+
+// Origin (sample, row, column) of pixel tile `t` and the linear NHWC pixel index of its row `r`.
+__device__ __forceinline__ void tc_tile_origin(const TcParams& p, int t, int& b0, int& y0, int& x0) {
+  if (p.tile2d) {
+    b0 = t / p.tps;
+    const int r = t - b0 * p.tps, ty = r / p.txs;
+    y0 = ty * 8;
+    x0 = (r - ty * p.txs) * 16;
+  } else {
+    const int m0 = t * TC_BM;
+    x0 = m0 % p.W;
+    y0 = (m0 / p.W) % p.H;
+    b0 = m0 / p.HW;
+  }
+}
+// row r of tile t -> linear pixel index (b * H + y) * W + x, or -1 past the end of the tensor
+__device__ __forceinline__ int tc_tile_pixel(const TcParams& p, int t, int r) {
+  if (p.tile2d) {
+    if (t * TC_BM >= p.M) return -1;     // the all-out-of-bounds tile of an odd tile count
+    int b0, y0, x0;
+    tc_tile_origin(p, t, b0, y0, x0);
+    return (b0 * p.H + y0 + (r >> 4)) * p.W + x0 + (r & 15);
+  }
+  const int m = t * TC_BM + r;
+  return m < p.M ? m : -1;
+}
 
 // PAIR: cta_group::2 — the two CTAs of a cluster form one 256 x BN MMA tile (128 pixel rows each); each CTA stages
 // only its HALF of the weight slab and the tensor core reads both halves, so the bytes that must enter an SM per
@@ -268,8 +298,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tile_id = work / p.ksplit, split = work - tile_id * p.ksplit;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int n0 = (tile_id % p.n_tiles) * BN;
-        const int m0 = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM;
-        const int x0 = m0 % p.W, y0 = (m0 / p.W) % p.H, b0 = m0 / p.HW;
+        int x0, y0, b0;
+        tc_tile_origin(p, (tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank), b0, y0, x0);
         const int b1 = (p.x1_batch > 0) ? (b0 % p.x1_batch) : b0;
         const int bs1 = (p.skip_x1_batch > 0) ? (b0 % p.skip_x1_batch) : b0;
         if constexpr (XF) {
@@ -616,8 +646,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t acc = tile % Cfg::ACC, acc_ph = (tile / Cfg::ACC) & 1;
       const int tile_id = work / p.ksplit, split = work - tile_id * p.ksplit;
       const int n_base = (tile_id % p.n_tiles) * BN;
-      const int m = ((tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank)) * TC_BM + row;
-      const bool valid = m < p.M;
+      const int m_tile_idx = (tile_id / p.n_tiles) * CL + static_cast<int>(cta_rank);
+      const int m_px = tc_tile_pixel(p, m_tile_idx, row);   // linear pixel index of this thread's accumulator row
+      const bool valid = m_px >= 0;
+      const int m = valid ? m_px : p.M;                     // (split-K workspace rows use the linear tile layout)
       const int b = valid ? m / p.HW : 0;
       const float* emb_row = p.emb ? p.emb + static_cast<size_t>(b) * p.emb_stride : nullptr;
       const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16);
@@ -635,8 +667,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       bool rok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int mm = m - lane + (lane >> 2) + 8 * i;
-        rok[i] = mm < p.M;
+        const int mm = tc_tile_pixel(p, m_tile_idx, quad * 32 + (lane >> 2) + 8 * i);
+        rok[i] = mm >= 0;
         roff[i] = rok[i] ? row_offset(mm) : 0;
       }
       // bf16 residual (identity skip): a thread reads its own pixel row, and the tensor was written layers ago — the
@@ -722,7 +754,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
         if (p.ksplit > 1) {  // split-K: raw fp32 partial tile -> workspace; splitk_finish_kernel applies the epilogue
-          float4* wp = reinterpret_cast<float4*>(p.ws + (static_cast<size_t>(split) * p.m_pad + m) * p.cout + n);
+          float4* wp = reinterpret_cast<float4*>(
+              p.ws + (static_cast<size_t>(split) * p.m_pad + m_tile_idx * TC_BM + row) * p.cout + n);
 #pragma unroll
           for (int j = 0; j < CH; j += 4) wp[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           continue;
@@ -1124,7 +1157,7 @@ namespace {
 // Everything stedm_conv_tc decides before it touches the device: argument checks, tile geometry, channel tile /
 // cluster / split-K plan and the halo-mode choice (also exported as stedm_conv_tc_plan for CPU-side tests).
 struct TcLaunch {
-  int tw, th, tb, x1b;
+  int tw, th, tb, x1b, tile2d;
   long long M;
   int ctot, taps, c_blks, skip_c, skip_blks, n_t, halo, halo_na, halo_bytes;
   TcPlan plan;
@@ -1195,6 +1228,20 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
   int halo = 0, halo_na = 0, halo_bytes = 0;
   // (fused-skip slabs take a whole box-sized ring slot each: with many of them the shallower ring costs more than the
   //  halo saves — measured break-even near one skip slab per five tap slabs)
+  // 2-D pixel tiles (16 columns x 8 rows) for the 3x3 convolutions on maps at least 32 wide: the halo box then carries
+  // 2 extra rows per 8 whatever the width (full-row tiles: 2 per 4 at W = 32, 2 per 2 at W = 64, no halo mode from W = 128)
+  // OPT-IN (STEDM_TC_TILE2D=1, read per call so tests can toggle it): measured on the bench workload it does not pay —
+  // the 64 x 64 layers are unchanged (0.526 / 0.241 ms vs 0.530 / 0.236), the sub-pixel phase convolutions at 32 x 32 and
+  // the decoder's 128 -> 128 at 256 x 256 lose 5-8 % (a tile's stores and residual reads become eight 4 KB runs instead
+  // of one 32 KB run), only the 256 -> 128 at 256 x 256 gains 7 % (profiles/r02_tile2d_ab.txt)
+  const char* t2e = getenv("STEDM_TC_TILE2D");
+  const bool tile2d_enabled = t2e != nullptr && t2e[0] == '1';
+  int tile2d = 0;
+  if (tile2d_enabled && g_tc_halo_enabled && d->ksize == 3 && d->stride == 1 && W >= 32 && W % 16 == 0 && H % 8 == 0 &&
+      plan.ksplit == 1 && d->gn_coef == nullptr && skip_blks * 5 <= taps * c_blks) {
+    tile2d = 1;
+    tw = 16; th = 8; tb = 1;
+  }
   if (d->gn_coef != nullptr) {
     // GroupNorm (+ SiLU) in the operand path: built on the CTA-pair halo pipeline with 256-wide channel tiles
     plan.ksplit = 1;
@@ -1211,15 +1258,15 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
                   d->gn_c_off + ctot);
     halo = 1;
     halo_na = TC_XF_SETS;
-  } else if (g_tc_halo_enabled && d->stride == 1 && d->ksize == 3 && tb == 1 && th >= 2 && tw == W && W >= 8 && H >= th + n_t - 1 &&
-      plan.ksplit == 1 && skip_blks * 5 <= taps * c_blks) {
-    halo_bytes = (th + n_t - 1) * W * TC_BK * 2;
+  } else if (g_tc_halo_enabled && d->stride == 1 && d->ksize == 3 && tb == 1 && th >= 2 && (tw == W || tile2d) && W >= 8 &&
+             H >= th + n_t - 1 && plan.ksplit == 1 && skip_blks * 5 <= taps * c_blks) {
+    halo_bytes = (th + n_t - 1) * tw * TC_BK * 2;
     const int stages = tc_stages(plan.bn, plan.pair);
     halo_na = stages * TC_BM * TC_BK * 2 / halo_bytes;
     if (halo_na > stages) halo_na = stages;
     halo = halo_na >= 2 && halo_bytes % 1024 == 0;
   }
-  L->tw = tw; L->th = th; L->tb = tb; L->x1b = x1b; L->M = M;
+  L->tw = tw; L->th = th; L->tb = tb; L->x1b = x1b; L->M = M; L->tile2d = tile2d;
   L->ctot = ctot; L->taps = taps; L->c_blks = c_blks; L->skip_c = skip_c; L->skip_blks = skip_blks;
   L->n_t = n_t; L->halo = halo; L->halo_na = halo_na; L->halo_bytes = halo_bytes; L->plan = plan;
   return 0;
@@ -1342,7 +1389,8 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   p.cs = cs;
   p.act = d->act;
   p.skip_blks = skip_blks; p.skip_c0_blks = skip_c > 0 ? d->skip_c0 / TC_BK : 0; p.skip_x1_batch = skip_x1b;
-  p.halo = halo; p.n_t = n_t; p.na = halo_na; p.a_buf_bytes = halo_bytes; p.a_row_bytes = W * TC_BK * 2;
+  p.halo = halo; p.n_t = n_t; p.na = halo_na; p.a_buf_bytes = halo_bytes; p.a_row_bytes = tw * TC_BK * 2;
+  p.tile2d = L.tile2d; p.txs = W / 16; p.tps = H * W / TC_BM;
   p.res_rows = 0;
   if (d->residual != nullptr && d->res_batch > 0 && d->res_batch != B) {
     STEDM_REQUIRE(d->tap_mode == 0 && B % d->res_batch == 0, "conv_tc: residual batch %d does not divide the batch %d",

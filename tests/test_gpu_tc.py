@@ -54,7 +54,29 @@ CASES = [
     (1, 16, 32, 192, 64, 3),      # non-square map, three channel blocks, BN=64
     (1, 8, 16, 64, 64, 3),        # H < tile rows + halo: falls back to one slab per tap
     (2, 64, 64, 128, 128, 3),     # 64x2 tiles + 2 halo rows (32 KB boxes, two per ring), BN=128 CTA pairs
+    (1, 16, 128, 64, 128, 3),     # 128-wide map: full-row tiles, one slab per tap
+    (1, 8, 256, 64, 64, 3),       # 256-wide map, BN=64
+    (1, 128, 128, 64, 16, 3),     # image-head shape: BN=16 on a 128-wide map
 ]
+
+
+@pytest.fixture()
+def tile2d():
+    """The opt-in 2-D pixel tiling (16 x 8 pixel tiles + halo boxes on maps at least 32 wide): STEDM_TC_TILE2D is read per call."""
+    import os
+    old = os.environ.get("STEDM_TC_TILE2D")
+    os.environ["STEDM_TC_TILE2D"] = "1"
+    yield
+    if old is None:
+        os.environ.pop("STEDM_TC_TILE2D", None)
+    else:
+        os.environ["STEDM_TC_TILE2D"] = old
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k", [(2, 32, 32, 128, 512, 3), (2, 64, 64, 128, 128, 3), (1, 16, 128, 64, 128, 3),
+                                              (1, 8, 256, 64, 64, 3), (1, 128, 128, 64, 16, 3), (3, 64, 32, 192, 256, 3)])
+def test_conv_tc_2d_tiles_match_fp32(ops, tile2d, B, H, W, cin, cout, k):
+    test_conv_tc_matches_fp32(ops, B, H, W, cin, cout, k)
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,k", CASES)
@@ -90,6 +112,33 @@ def test_conv_tc_concat_emb_residual(ops, k):
                        x1=nhwc(x1).to(torch.bfloat16).cuda(), emb=emb, residual=nhwc(res).to(res_dt).cuda(),
                        out_dtype=torch.float32, tensor_core=True)
         assert max_abs(nchw(got.cpu()), want) < 2e-3
+
+
+@pytest.mark.parametrize("hw", [32, 64])
+def test_conv_tc_2d_tiles_concat_emb_residual_stats(ops, tile2d, hw):
+    """The 2-D pixel tiles (maps at least 32 wide) with everything the epilogue does: two-source concat with a broadcast
+    second source, embedding rows, bf16 residual (requested a chunk ahead), bf16 NHWC output through the staging
+    transpose, GroupNorm tile statistics — against torch, and bit-equal to the full-row tiling (STEDM_TC_TILE2D=0 is a
+    load-time switch, so the reference here is the same convolution run as one 3x3 tap-major GEMM over im2col'ed rows...
+    which has another K order; compare with tolerance instead and pin the statistics)."""
+    g = torch.Generator().manual_seed(hw)
+    B, c0, c1, co = 4, 128, 64, 256
+    x0, x1 = bf(torch.randn(B, c0, hw, hw, generator=g)), bf(torch.randn(2, c1, hw, hw, generator=g))
+    w = bf(torch.randn(co, c0 + c1, 3, 3, generator=g) / math.sqrt((c0 + c1) * 9))
+    b, emb = torch.randn(co, generator=g), torch.randn(B, co, generator=g)
+    res = bf(torch.randn(B, co, hw, hw, generator=g))
+    want = F.conv2d(torch.cat([x0, torch.cat([x1, x1], 0)], 1), w, b, padding=1) + emb[:, :, None, None] + res
+    m_tiles = B * hw * hw // 128
+    stats = torch.zeros((m_tiles, co, 2), device="cuda")
+    got = ops.conv(nhwc(x0).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), co, 3, x1=nhwc(x1).to(torch.bfloat16).cuda(),
+                   emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(), out_dtype=torch.bfloat16, tensor_core=True,
+                   stats_out=stats)
+    assert max_abs(nchw(got.float().cpu()), want) < 2 ** -8 * float(want.abs().max()) + 3e-3     # bf16 output rounding
+    # per-sample channel sums from the tile statistics (whatever pixels a tile holds, a sample owns hw*hw/128 of them)
+    per_sample = stats.cpu().double().reshape(B, hw * hw // 128, co, 2).sum(1)
+    assert max_abs(per_sample[..., 0], want.double().sum((2, 3))) < 0.5
+    rel = ((per_sample[..., 1] - (want.double() ** 2).sum((2, 3))).abs() / (want.double() ** 2).sum((2, 3))).max()
+    assert float(rel) < 1e-3
 
 
 def test_conv_tc_stride2_via_im2col(ops):
