@@ -175,6 +175,16 @@ def test_vq_nearest(ops):
     cb2 = torch.cat([cb[:100], cb[:100]], 0)
     _, idx2 = ops.vq_nearest(z.cuda(), cb2.cuda(), return_indices=True)
     assert int(idx2.max()) < 100
+    # ragged pixel count (not a multiple of the 4 pixels a warp scans together), 4-channel codebook, NaN pixel -> code 0
+    z3 = torch.randn(1, 4, 7, 5, generator=g) * 3
+    cb3 = torch.randn(300, 4, generator=g) * 2
+    want3, idx3w = O.vq_quantize(z3, cb3)
+    zq3, idx3 = ops.vq_nearest(z3.cuda(), cb3.cuda(), return_indices=True)
+    assert (idx3.cpu().long() == idx3w).float().mean() > 0.97 and tuple(zq3.shape) == (1, 4, 7, 5)
+    zn = z.clone()
+    zn[0, :, 3, 4] = float("nan")
+    _, idxn = ops.vq_nearest(zn.cuda(), cb.cuda(), return_indices=True)
+    assert int(idxn[3 * 32 + 4]) == 0 and int(idxn.max()) < 8192 and int(idxn.min()) >= 0
 
 
 def test_spatial_rescale(ops):
