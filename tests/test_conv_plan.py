@@ -67,7 +67,10 @@ def test_split_k_needs_a_workspace_and_disables_halo():
     assert plan(**small)["ksplit"] == 1 and plan(**small)["halo"] == 1   # no workspace: single pass
     p = plan(**small, workspace=1 << 30)
     assert p["ksplit"] > 1 and p["halo"] == 0
-    assert plan(**small, workspace=1 << 30, stats=True)["ksplit"] == 1   # fused statistics need the single pass
+    # fused GroupNorm statistics no longer force the single pass: the split-K finish pass publishes them (round 2)
+    assert plan(**small, workspace=1 << 30, stats=True)["ksplit"] > 1
+    # a launch whose tiles already fill the grid is never split
+    assert plan(B=64, H=16, W=16, c0=1024, cout=1024, k=3, workspace=1 << 30)["ksplit"] == 1
 
 
 @pytest.mark.parametrize("kw,msg", [
