@@ -319,6 +319,17 @@ __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t ct
       : "memory");
 }
 
+// the TMEM-A-operand form for a CTA pair (each CTA's P lives at the same TMEM address in its own tensor memory)
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Named barrier among a subset of the CTA's warps (id 0 is __syncthreads' barrier).
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
