@@ -319,6 +319,19 @@ def test_cuda_graph_sampler_matches_eager():
     z3e, _ = m._model.sample_log(_cond(g, "c_crossattn"), **kw3)
     assert torch.equal(z0, z1) and torch.equal(z0, z2) and torch.equal(z3, z3e)
     assert len(i2["x_inter"]) == len(i1["x_inter"]) and all(torch.equal(a, b) for a, b in zip(i1["pred_x0"], i2["pred_x0"]))
+    # logged intermediates come out of the captured loop too (ddim.py:155-157: index % log_every_t == 0 or the first step)
+    kw5 = dict(kw, log_every_t=5)
+    m._model.use_cuda_graph = False
+    _, ie = m._model.sample_log(_cond(g, "c_crossattn"), **kw5)
+    m._model.use_cuda_graph = True
+    try:
+        m._model.sample_log(_cond(g, "c_crossattn"), **kw5)
+        _, ig = m._model.sample_log(_cond(g, "c_crossattn"), **kw5)
+    finally:
+        m._model.use_cuda_graph = False
+    assert len(ig["x_inter"]) == len(ie["x_inter"]) == 6 and len(ig["pred_x0"]) == 6
+    assert all(torch.equal(a, b) for a, b in zip(ie["x_inter"], ig["x_inter"]))
+    assert all(torch.equal(a, b) for a, b in zip(ie["pred_x0"], ig["pred_x0"]))
     # per-step path (a caller-driven loop, or any option that needs host-side work per step) still uses the per-pass graph
     m._model.use_cuda_graph = True
     try:

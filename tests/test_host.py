@@ -166,3 +166,30 @@ def test_predict_checkpoint_resolution(tmp_path):
     with pytest.raises(FileNotFoundError):
         resolve_checkpoint(load_config([f"location.result_dir={tmp_path}", "+ckpt_name=other.ckpt"]))
     assert resolve_checkpoint(load_config([f"location.result_dir={tmp_path}"])) is None
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_ncu_summary():
+    """bench.py's roofline.traffic is parsed from profiles/rNN_ncu_full_conv_tc.csv (dram read + write of the dominant
+    kernel's first captured launch), not a pasted literal."""
+    import importlib.util
+    import os
+    from tests.util import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.ncu_traffic_bytes()
+    assert t is not None and 1.0e8 < t < 2.5e8, t          # algorithmic bytes of that launch: 153 MB
+
+
+def test_strong_scaling_split_keeps_per_sample_noise():
+    """One global batch split over N ranks (bench.py's strong_scaling block): rank r's synthetic inputs are the global
+    samples [r*B/N, (r+1)*B/N) — x_T is keyed by global sample index, so the union over ranks equals the 1-rank batch."""
+    import importlib.util
+    import os
+    from tests.util import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    full = bench.synthetic_batch(8, 32, 1, 0)[3]
+    parts = [bench.synthetic_batch(2, 32, 1, r * 2)[3] for r in range(4)]
+    assert torch.equal(torch.cat(parts, 0), full)
