@@ -529,3 +529,71 @@ def test_conv_tc_groupnorm_in_operand_path_rejects_unsupported_shapes(ops):
     w = torch.zeros(128, 9 * 256, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError, match="gn_coef"):
         ops.conv(x, w, None, 128, 3, tensor_core=True, gn_coef=coef)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# out-of-bounds canaries (compute-sanitizer is not available on the GPU pool): outputs are views into larger buffers
+# filled with a sentinel; the kernels of this round must leave everything outside their outputs untouched
+# ---------------------------------------------------------------------------------------------------------------------
+def _guarded(shape, dtype, pad=4096):
+    n = 1
+    for s_ in shape:
+        n *= s_
+    buf = torch.full((n + 2 * pad,), 12345.0 if dtype.is_floating_point else 77, dtype=dtype, device="cuda")
+    return buf, buf[pad:pad + n].view(*shape), pad
+
+
+def _untouched(buf, pad, dtype):
+    ref = 12345.0 if dtype.is_floating_point else 77
+    ref = torch.tensor(ref, dtype=dtype).item()
+    return bool((buf[:pad] == ref).all()) and bool((buf[-pad:] == ref).all())
+
+
+def test_round2_kernels_do_not_write_outside_their_outputs(ops):
+    g = torch.Generator().manual_seed(31)
+    # (1) split-K convolution with statistics: partial workspace, finish pass, odd sample count
+    B, hw, cin, cout = 3, 16, 512, 256
+    x = torch.randn(B, hw, hw, cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(cout, 9 * cin, generator=g) / 70).to(torch.bfloat16).cuda()
+    obuf, out, pad = _guarded((B, hw, hw, cout), torch.bfloat16)
+    sbuf, stats, spad = _guarded((B * hw * hw // 128, cout, 2), torch.float32)
+    ops.conv(x, w, None, cout, 3, out_dtype=torch.bfloat16, tensor_core=True, out=out, stats_out=stats)
+    torch.cuda.synchronize()
+    assert _untouched(obuf, pad, torch.bfloat16) and _untouched(sbuf, spad, torch.float32)
+    assert bool(torch.isfinite(out.float()).all()) and bool(torch.isfinite(stats).all()) and float(stats[..., 1].min()) >= 0
+    # (2) GroupNorm in the operand path: output + statistics + coefficient table
+    t = x.float().reshape(B * hw * hw // 128, 128, cin)
+    src = (torch.stack([t.sum(1), (t * t).sum(1)], -1).contiguous(), cin, 1, B * hw * hw // 128, hw * hw // 128, B)
+    coef = ops.gn_fold_tiles(src, None, B, coef_for=(torch.ones(cin, device="cuda"), torch.zeros(cin, device="cuda"), 1e-5, hw * hw))
+    assert tuple(coef.shape) == (B, cin, 2) and bool(torch.isfinite(coef).all())
+    obuf, out, pad = _guarded((B, hw, hw, cout), torch.bfloat16)
+    sbuf, stats, spad = _guarded((B * hw * hw // 128, cout, 2), torch.float32)
+    ops.conv(x, w, None, cout, 3, out_dtype=torch.bfloat16, tensor_core=True, out=out, stats_out=stats, gn_coef=coef)
+    torch.cuda.synchronize()
+    assert _untouched(obuf, pad, torch.bfloat16) and _untouched(sbuf, spad, torch.float32)
+    # (3) stride-2 convolution
+    obuf, out, pad = _guarded((B, hw // 2, hw // 2, cout), torch.float32)
+    ops.conv(x, w, None, cout, 3, stride=2, out_dtype=torch.float32, tensor_core=True, out=out)
+    torch.cuda.synchronize()
+    assert _untouched(obuf, pad, torch.float32) and bool(torch.isfinite(out).all())
+
+
+def test_attention_tc_wide_ragged_tokens_write_only_their_rows(ops):
+    """T = 300 (three query tiles: the CTA pair of the last one has an all-out-of-range partner), output rows >= T of the
+    padded buffer and everything around it stay untouched."""
+    B, T, C = 2, 300, 512
+    g = torch.Generator().manual_seed(3)
+    qkv = (torch.randn(B, T, 3 * C, generator=g) * 0.7).to(torch.bfloat16).cuda()
+    import ctypes as Cc
+    from stedm_b200 import _lib
+    obuf, out, pad = _guarded((B, T, C), torch.bfloat16)
+    lib = _lib.load()
+    es = 2
+    rc = lib.stedm_attention_tc(qkv.data_ptr(), qkv.data_ptr() + C * es, qkv.data_ptr() + 2 * C * es, out.data_ptr(), B, 1, T, C,
+                                T * 3 * C, C, 3 * C, C ** -0.5, T * C, 0, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    assert _untouched(obuf, pad, torch.bfloat16)
+    q, k, v = (t_.float().cpu() for t_ in qkv.split(C, dim=-1))
+    want = torch.einsum("bts,bsc->btc", torch.softmax(torch.einsum("btc,bsc->bts", q, k) * C ** -0.5, -1), v)
+    assert max_abs(out.float().cpu(), want) < 2e-2 * max(1.0, float(want.abs().max()))
