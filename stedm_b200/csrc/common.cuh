@@ -196,6 +196,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 // `v` to addr_v when pred, else zeros to addr_z: one of two predicated stores executes (no value selects)
 __device__ __forceinline__ void sts128_or_zero(bool pred, uint32_t addr_v, const uint4& v, uint32_t addr_z) {
   asm volatile(

@@ -816,12 +816,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           // contiguous bytes (2 whole sectors).  16-byte slots are XOR-swizzled: 4 wavefronts per access, the minimum.
           const int jj = lane & 3;
           if (p.out_dtype == DT_BF16) {
+            if (p.stats_out != nullptr && !valid) {     // rows past the end of the tensor count as zeros in the statistics
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
                      make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
             __syncwarp();
+            if (p.stats_out != nullptr) {
+              // GroupNorm statistics of the tensor being written, taken from the STAGED bf16 tile: the values the
+              // consumer will actually normalise, and 16 conflict-free LDS.32 + 4 shuffles per lane instead of the
+              // 62-shuffle transposing reduction (25 % of this warp's stall samples on the 128-wide channel tiles).
+              // lane -> (channel pair cp, half of the 32 rows); the halves walk rows of opposite parity (rows r and
+              // r + 1 sit on disjoint banks: a 64-byte row covers 16 of the 32 banks)
+              const int cp = lane & 15, rh = lane >> 4;
+              const uint32_t cbase = stg + static_cast<uint32_t>(cp & 3) * 4;
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = rh * 16 + (rh ? (i ^ 1) : i);
+                const float2 f = unpack_bf16x2(lds32(cbase + r * 64 + (((cp >> 2) ^ ((r >> 1) & 3)) << 4)));
+                s0 += f.x; s1 += f.y;
+                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+              }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              if (lane < 16)
+                *reinterpret_cast<float4*>(&s_stats[((quad * BN) + c + 2 * cp) * 2]) = make_float4(s0, q0, s1, q1);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = (lane >> 2) + 8 * i;
@@ -868,7 +893,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
         if constexpr (CH == 32) {
-          if (p.stats_out != nullptr) {
+          if (p.stats_out != nullptr && !(p.out_dtype == DT_BF16 && !p.out_nchw)) {   // (bf16 NHWC: done from the staged tile)
             // GroupNorm statistics of the tensor being written (K7's statistics pass folded into its producer):
             // per-channel sum and sum of squares over this warp's 32 pixel rows; lane L ends up with channel c + L
             float sq[32];
@@ -994,7 +1019,8 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
   if (p.stats_out == nullptr) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float x = live ? v[j] : 0.f;
+    // (the statistics describe the STORED tensor: bf16-rounded values when the output is bf16, as in the single-pass epilogue)
+    const float x = live ? (p.out_dtype == DT_BF16 ? __bfloat162float(__float2bfloat16_rn(v[j])) : v[j]) : 0.f;
     s_red[r][oct * 8 + j][0] = x;
     s_red[r][oct * 8 + j][1] = x * x;
   }

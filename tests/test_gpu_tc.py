@@ -134,11 +134,13 @@ def test_conv_tc_2d_tiles_concat_emb_residual_stats(ops, tile2d, hw):
                    emb=emb.cuda(), residual=nhwc(res).to(torch.bfloat16).cuda(), out_dtype=torch.bfloat16, tensor_core=True,
                    stats_out=stats)
     assert max_abs(nchw(got.float().cpu()), want) < 2 ** -8 * float(want.abs().max()) + 3e-3     # bf16 output rounding
-    # per-sample channel sums from the tile statistics (whatever pixels a tile holds, a sample owns hw*hw/128 of them)
+    # per-sample channel sums from the tile statistics (whatever pixels a tile holds, a sample owns hw*hw/128 of them):
+    # statistics of the stored bf16 tensor
+    gs = nchw(got.float().cpu()).double()
     per_sample = stats.cpu().double().reshape(B, hw * hw // 128, co, 2).sum(1)
-    assert max_abs(per_sample[..., 0], want.double().sum((2, 3))) < 0.5
-    rel = ((per_sample[..., 1] - (want.double() ** 2).sum((2, 3))).abs() / (want.double() ** 2).sum((2, 3))).max()
-    assert float(rel) < 1e-3
+    assert max_abs(per_sample[..., 0], gs.sum((2, 3))) < 2e-2
+    rel = ((per_sample[..., 1] - (gs ** 2).sum((2, 3))).abs() / (gs ** 2).sum((2, 3))).max()
+    assert float(rel) < 1e-5
 
 
 def test_conv_tc_stride2_via_im2col(ops):
@@ -320,9 +322,12 @@ def test_conv_tc_fused_groupnorm_statistics(ops, cout, hw, B):
     y = ops.conv(nhwc(x).to(torch.bfloat16).cuda(), tc_w(w).cuda(), b.cuda(), cout, 3, residual=nhwc(res).to(torch.bfloat16).cuda(),
                  out_dtype=torch.bfloat16, tensor_core=True, stats_out=tiles)
     want_y = F.conv2d(x, w, b, padding=1) + res
+    assert max_abs(nchw(y.float().cpu()), want_y) < 2 ** -8 * float(want_y.abs().max()) + 3e-3
+    # the statistics describe the STORED (bf16-rounded) tensor — the values the GroupNorm will normalise
+    ys = nchw(y.float().cpu()).double()
     sums = tiles.cpu().double().reshape(B, hw * hw // 128, cout, 2).sum(1)              # per sample, per channel
-    assert max_abs(sums[..., 0], want_y.double().sum((2, 3))) < 0.05
-    assert float(((sums[..., 1] - (want_y.double() ** 2).sum((2, 3))).abs() / (want_y.double() ** 2).sum((2, 3))).max()) < 1e-3
+    assert max_abs(sums[..., 0], ys.sum((2, 3))) < 5e-3
+    assert float(((sums[..., 1] - (ys ** 2).sum((2, 3))).abs() / (ys ** 2).sum((2, 3))).max()) < 1e-5
     folded = ops.gn_fold_tiles((tiles, cout, 1, m_tiles, hw * hw // 128, B), None, B)
     gamma, beta = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
     got = ops.gn_apply(y, None, folded, gamma.cuda(), beta.cuda(), 1e-5, True, torch.float32, n_chunks=1)
