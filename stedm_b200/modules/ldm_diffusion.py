@@ -40,6 +40,11 @@ class LDM_Diffusion(torch.nn.Module):
         self._model = S_ZSS_DM(encoder="swin_v2_t", sampling_cfg=cfg.style_sampling, agg_cfg=cfg.style_agg, cfg=cfg,
                                precision=precision, **ldm_dict)
         self.register_module("model", self._model)
+        # The whole DDIM loop of a predict batch is captured as ONE CUDA graph per (batch shape, schedule, guidance)
+        # signature and replayed (stedm_b200.ldm.models.diffusion.ddim): decisive at the per-GPU batches the reference
+        # ships (2-8 images, conf/location/cluster.yaml:3-5).  `+cuda_graph=false` in the config falls back to
+        # launching every kernel from Python.
+        self._model.use_cuda_graph = bool(getattr(cfg, "cuda_graph", True)) if not hasattr(cfg, "get") else bool(cfg.get("cuda_graph", True))
         self.predict_dir = None
         self.writer = None      # optional stedm_b200.utils.image_writer.AsyncImageWriter (overlapped D2H + PNG encode)
 
