@@ -230,7 +230,7 @@ def test_attention_tc_legacy_layout(ops, heads, ch, T, B):
     assert err < 2e-2 * max(1.0, float(want.abs().max())), err
 
 
-@pytest.mark.parametrize("B,T,Tkv", [(2, 1024, 0), (1, 4096, 0), (3, 200, 0), (2, 256, 77)])
+@pytest.mark.parametrize("B,T,Tkv", [(2, 1024, 0), (1, 4096, 0), (3, 200, 0), (2, 256, 77), (2, 100, 0), (1, 128, 300)])
 def test_attention_tc_wide_single_head_d512(ops, B, T, Tkv):
     """The VAE decoder's AttnBlock (model.py:178-202: one head, d = 512, scale 512^-1/2) on the wide flash kernel — Q
     resident, K / V streamed in 64-channel slabs, output channels split over two CTAs, no T x T tensor: against fp32
