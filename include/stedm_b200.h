@@ -84,6 +84,13 @@ int stedm_gn_fold_tiles(const float* tiles0, int c0, int reps0, long long rep_st
                         double* out, const float* gamma, const float* beta, float eps, int hw, float* coef,
                         void* stream);
 
+/* Row broadcast + per-sample embedding add (+ GroupNorm tile statistics): out[m][n] = src[m % src_rows][n] + emb[(m / hw) *
+ * emb_stride + n], src fp32 [src_rows][c], out bf16 / fp32 [rows_out][c], stats_out optional fp32 [rows_out / 128][c][2].
+ * Replaces the second evaluation of ResBlockStyle.in_layers (openaimodel.py:291-297, 268-287) for the unconditional half of
+ * a guided batch: the convolution output is the same for both halves, only the style embedding added to it differs. */
+int stedm_rows_add_emb(const float* src, long long src_rows, const float* emb, int emb_stride, void* out, int out_dtype,
+                       long long rows_out, int hw, int c, float* stats_out, void* stream);
+
 /* ----------------------------------------------------------------------------------------------------
  * K1/K2/K3/K4/K9/K10  Convolution as implicit GEMM, M = B*Ho*Wo pixels, N = Cout, K = k*k*(c0+c1).
  * Replaces nn.Conv2d 3x3 / 1x1 and nn.Conv1d k=1 call sites: openaimodel.py:120, 164-166, 217, 243, 254, 326, 334,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "stedm_gn_stats": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "stedm_gn_apply": [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, i32, vp, i32, vp],
     "stedm_gn_fold_tiles": [vp, i32, i32, i64, i32, i32, vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, f32, i32, vp, vp],
+    "stedm_rows_add_emb": [vp, i64, vp, i32, vp, i32, i64, i32, i32, vp, vp],
     "stedm_conv_tc": [C.POINTER(ConvDesc), vp],
     "stedm_conv_tc_workspace_bytes": [C.POINTER(ConvDesc)],
     "stedm_conv_tc_plan": [C.POINTER(ConvDesc), C.POINTER(C.c_int32)],

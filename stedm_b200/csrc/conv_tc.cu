@@ -96,6 +96,7 @@ struct TcParams {
   int ksplit;           // split-K factor (1 = off): work item = (tile, K range); partials go to `ws`
   int kb_per_split;     // K slabs per split
   float* ws;            // split-K workspace: fp32 [ksplit][m_pad][cout]
+  int ws_rows;          // > 0 (stedm_rows_add_emb): the source has ws_rows rows, output row m reads row m % ws_rows
   int m_pad;            // rows of one workspace slice (all tiles, including the out-of-bounds one)
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
@@ -959,7 +960,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
   if (live) {
-    const float* wp = p.ws + static_cast<size_t>(m) * p.cout + n;
+    const float* wp = p.ws + static_cast<size_t>(p.ws_rows > 0 ? m % p.ws_rows : m) * p.cout + n;
     const size_t ss = static_cast<size_t>(p.m_pad) * p.cout;
     int s = 0;
     for (; s + 4 <= p.ksplit; s += 4) {   // fixed order: deterministic; 8 independent 16-byte loads in flight
@@ -1300,6 +1301,28 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
 
 }  // namespace
 
+// out[m][n] = round(src[m % src_rows][n] + emb[(m / hw) * emb_stride + n]) (+ the per-(128-row tile, channel) statistics
+// a GroupNorm consumer folds): the split-K finish pass with one "partial" and a row broadcast.  Used where a convolution's
+// input is shared by the G halves of a guided batch and only the per-sample embedding differs (ResBlockStyle's first
+// convolution, openaimodel.py:291-297 after :278-287): the convolution runs once per distinct input, this pass expands it.
+extern "C" int stedm_rows_add_emb(const float* src, long long src_rows, const float* emb, int emb_stride, void* out,
+                                  int out_dtype, long long rows_out, int hw, int c, float* stats_out, void* stream) {
+  STEDM_REQUIRE(src && emb && out && src_rows > 0 && rows_out > 0 && hw > 0 && c > 0 && c % 8 == 0 && rows_out % hw == 0 &&
+                    src_rows % hw == 0 && rows_out < (1LL << 31),
+                "rows_add_emb: bad argument (channels must be a multiple of 8, row counts multiples of hw)");
+  STEDM_REQUIRE(out_dtype == DT_BF16 || out_dtype == DT_F32, "rows_add_emb: bad output dtype");
+  STEDM_REQUIRE(stats_out == nullptr || hw % TC_BM == 0, "rows_add_emb: tile statistics need hw %% 128 == 0");
+  TcParams p = {};
+  p.ws = const_cast<float*>(src); p.ws_rows = static_cast<int>(src_rows); p.ksplit = 1; p.m_pad = 0;
+  p.bias = nullptr; p.emb = emb; p.emb_stride = emb_stride; p.residual = nullptr; p.out = out;
+  p.M = static_cast<int>(rows_out); p.HW = hw; p.H = 1; p.W = hw; p.cout = c; p.cout_store = c;
+  p.out_dtype = out_dtype; p.res_dtype = DT_F32; p.stats_out = stats_out;
+  const int m_tiles = static_cast<int>((rows_out + TC_BM - 1) / TC_BM);
+  splitk_finish_kernel<<<dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((c + SKF_CH - 1) / SKF_CH)), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("rows_add_emb");
+}
+
 extern "C" int stedm_conv_tc_plan(const stedm_conv_desc* d, int32_t* out8) {
   STEDM_REQUIRE(out8 != nullptr, "conv_tc_plan: null output");
   TcLaunch L;
@@ -1408,7 +1431,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d->cout % bn == 0 || (d->cout % 32 == 0 && d->out_nchw == 0),
                 "conv_tc: cout %d with a partial last channel tile needs cout %% 32 == 0 and NHWC output", d->cout);
   p.ksplit = plan.ksplit; p.kb_per_split = plan.kb_per_split; p.m_pad = plan.m_pad;
-  p.ws = static_cast<float*>(d->workspace);
+  p.ws = static_cast<float*>(d->workspace); p.ws_rows = 0;
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;

@@ -230,6 +230,22 @@ def conv(x0, weight, bias, cout, ksize, *, x1=None, emb=None, residual=None, out
     return out
 
 
+def rows_add_emb(src, emb, groups, out_dtype=torch.bfloat16, want_stats=True):
+    """[B, H, W, C] fp32 ``src`` -> [groups * B, H, W, C]: sample b of the output = src[b % B] + emb[b] (per channel), with
+    the per-tile GroupNorm statistics of the result (``out._gn_tiles`` as conv(..., stats_out=...) leaves them)."""
+    _cuda(src, emb)
+    b, h, w, c = src.shape
+    assert src.dtype == torch.float32 and emb.dtype == torch.float32 and emb.shape == (groups * b, c) and emb.stride(1) == 1
+    out = torch.empty((groups * b, h, w, c), device=src.device, dtype=out_dtype)
+    tiles = None
+    if want_stats and (h * w) % 128 == 0:
+        tiles = torch.empty((groups * b * h * w // 128, c, 2), device=src.device, dtype=torch.float32)
+    _call("stedm_rows_add_emb", _ptr(src), b * h * w, _ptr(emb), emb.stride(0), _ptr(out), _DT[out_dtype], groups * b * h * w,
+          h * w, c, _ptr(tiles), _stream())
+    out._gn_tiles = None if tiles is None else (tiles, c, 1, tiles.shape[0], h * w // 128, groups * b)
+    return out
+
+
 _SPLITK_WS = {}
 
 

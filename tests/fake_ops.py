@@ -50,6 +50,12 @@ def gn_stats(x0, x1, stats=None):
     return None
 
 
+def rows_add_emb(src, emb, groups, out_dtype=torch.bfloat16, want_stats=True):
+    out = (src.float().repeat(groups, 1, 1, 1) + emb[:, None, None, :]).to(out_dtype)
+    out._gn_tiles = None
+    return out
+
+
 GN_FUSION = [True]
 
 

@@ -358,21 +358,59 @@ def test_shared_trunk_is_bit_identical(precision):
         return s.p_sample_ddim(x_T.cuda(), cond, ts, index=24, unconditional_guidance_scale=1.5,
                                unconditional_conditioning=unc)
 
-    saved = engine.SPLIT_CONCAT[0]
+    saved, saved_style = engine.SPLIT_CONCAT[0], engine.SHARE_STYLE_CONV[0]
     from stedm_b200 import ops as _ops
     saved_k, _ops.SPLIT_K[0] = _ops.SPLIT_K[0], False      # the trunk runs at B, the two-pass reference at 2B
     try:
-        engine.SPLIT_CONCAT[0] = False
+        engine.SPLIT_CONCAT[0] = engine.SHARE_STYLE_CONV[0] = False
         two_pass, shared = step(False), step(True)
         assert torch.equal(two_pass[0], shared[0]) and torch.equal(two_pass[1], shared[1])
         engine.SPLIT_CONCAT[0] = True
         split = step(True)
+        # ResBlockStyle's first convolution once per distinct input (conv + bias in fp32, the style embedding added by
+        # rows_add_emb): (acc + bias) + emb instead of acc + (bias + emb) — one fp32 rounding apart
+        engine.SPLIT_CONCAT[0], engine.SHARE_STYLE_CONV[0] = False, True
+        style = step(True)
     finally:
-        engine.SPLIT_CONCAT[0] = saved
+        engine.SPLIT_CONCAT[0], engine.SHARE_STYLE_CONV[0] = saved, saved_style
         _ops.SPLIT_K[0] = saved_k
     r = rel_err(split[0], two_pass[0])
     print(f"{precision} split-concat guided step vs unsplit rel err {r:.3e}")
     assert r < (1e-5 if precision == "fp32" else 5e-3)
+    r2 = rel_err(style[0], two_pass[0])
+    print(f"{precision} shared style-block convolution vs two passes rel err {r2:.3e}")
+    assert r2 < (1e-5 if precision == "fp32" else 5e-3)
+
+
+def test_shared_style_block_convolution_at_latent64():
+    """Guided step at latent 64 (16 x 16 middle maps: whole 128-pixel tiles per sample) with ResBlockStyle's first
+    convolution evaluated once per distinct input (engine.SHARE_STYLE_CONV: conv + bias in fp32, rows_add_emb adds the
+    cond / uncond style embeddings) against the step that convolves both halves: one fp32 rounding apart before the bf16
+    store, and both inside the bf16 bar of the reference's golden x_after_1 (tests/golden/c1_b4_l64.npz)."""
+    from stedm_b200 import engine
+    from stedm_b200.ldm.models.diffusion.ddim import DDIMSampler
+    g = load_golden("c1_b4_l64")
+    _, _, x4 = O.synthetic_batch(4, 256, 1, 1)
+    m = build_model(64, n_style=1, precision="bf16")
+    cond = {"c_concat": [torch.from_numpy(g["c_concat"]).cuda()], "c_crossattn": [torch.from_numpy(g["c_crossattn"]).cuda()]}
+    unc = {"c_concat": [torch.from_numpy(g["c_concat"]).cuda()], "c_crossattn": [torch.from_numpy(g["uc_crossattn"]).cuda()]}
+    ts = torch.full((4,), 981, dtype=torch.long, device="cuda")
+
+    def step(flag):
+        saved = engine.SHARE_STYLE_CONV[0]
+        engine.SHARE_STYLE_CONV[0] = flag
+        try:
+            s = DDIMSampler(m._model, use_cuda_graph=False)
+            s.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+            return s.p_sample_ddim(x4.cuda(), cond, ts, index=49, unconditional_guidance_scale=1.5, unconditional_conditioning=unc)
+        finally:
+            engine.SHARE_STYLE_CONV[0] = saved
+
+    (xa, _), (xb, _) = step(True), step(False)
+    r = rel_err(xa, xb)
+    print(f"shared style-block convolution vs both halves convolved, guided step at latent 64: rel err {r:.3e}")
+    assert r < 5e-3
+    assert rel_err(xa, g["x_after_1"]) < BF16_EPS_BAR and rel_err(xb, g["x_after_1"]) < BF16_EPS_BAR
 
 
 def test_latent128_eps_and_decode_vs_oracle():

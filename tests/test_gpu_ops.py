@@ -281,3 +281,22 @@ def test_attention_tc_cross_attention(T, N, heads, d):
     s = ops.attention_simt(q.float().cuda(), kv.float().cuda(), kv.float().cuda(), heads, d, T, 0, 0, inner, inner, d,
                            scale, torch.float32, tokens_kv=N, kv_token_stride=2 * inner)
     assert float((s.cpu() - want).abs().max()) < 1e-4
+
+
+def test_rows_add_emb_broadcast_and_statistics(ops):
+    """out[b] = src[b % B] + emb[b] with the per-tile GroupNorm statistics of the (bf16-rounded) result: the expansion of
+    ResBlockStyle's shared first convolution to the cond / uncond halves of a guided batch."""
+    g = _gen(41)
+    B, G, H, W, C = 3, 2, 16, 16, 256
+    src = torch.randn(B, H, W, C, generator=g) * 2
+    emb = torch.randn(G * B, C, generator=g)
+    out = ops.rows_add_emb(src.cuda(), emb.cuda(), G)
+    want = (src.repeat(G, 1, 1, 1) + emb[:, None, None, :]).to(torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (G * B, H, W, C)
+    assert torch.equal(out.cpu(), want)
+    tiles, c, reps, m_tiles, tps, nb = out._gn_tiles
+    assert (c, reps, m_tiles, tps, nb) == (C, 1, G * B * H * W // 128, H * W // 128, G * B)
+    t = want.float().reshape(m_tiles, 128, C)
+    assert max_abs(tiles[..., 0].cpu(), t.sum(1)) < 2e-3 and max_abs(tiles[..., 1].cpu(), (t * t).sum(1)) < 2e-2
+    out32 = ops.rows_add_emb(src.cuda(), emb.cuda(), G, out_dtype=torch.float32, want_stats=False)
+    assert torch.equal(out32.cpu(), src.repeat(G, 1, 1, 1) + emb[:, None, None, :]) and out32._gn_tiles is None
