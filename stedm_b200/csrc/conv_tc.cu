@@ -96,7 +96,6 @@ struct TcParams {
   int ksplit;           // split-K factor (1 = off): work item = (tile, K range); partials go to `ws`
   int kb_per_split;     // K slabs per split
   float* ws;            // split-K workspace: fp32 [ksplit][m_pad][cout]
-  int ws_rows;          // > 0 (stedm_rows_add_emb): the source has ws_rows rows, output row m reads row m % ws_rows
   int m_pad;            // rows of one workspace slice (all tiles, including the out-of-bounds one)
   int emb_stride, res_dtype, out_dtype;
   int out_nchw, cout_store;
@@ -125,7 +124,6 @@ struct TcParams {
   int nb;                // weight ring depth (XF: what fits beside the 6 boxes; otherwise Cfg::STAGES)
   int a_pool_bytes;      // XF: 6 * a_buf_bytes
   int log2w;             // XF: W is a power of two
-  int xf_debug;          // timing experiments only (STEDM_XF_DEBUG): 1 = no math, 2 = no outer-box stores, 4 = no work at all
   float* stats_out;      // optional [tile entries][cout][2]: per-(pixel tile, channel) sum / sum of squares of the output
   int stats_tile_base;   // first tile entry of this launch (phase * m_tiles for the sub-pixel phases)
 };
@@ -596,7 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t a0 = smem_base + (is * 3) * box + (static_cast<uint32_t>(j ^ ((pl + 1) & 7)) << 4);
           const uint32_t a2 = smem_base + (is * 3 + 2) * box + (static_cast<uint32_t>(j ^ ((pl - 1) & 7)) << 4);
 #pragma unroll 2
-          for (int it = 0; it < ((p.xf_debug & 4) ? 0 : n_it); ++it) {
+          for (int it = 0; it < n_it; ++it) {
             const int px = pl + 16 * it;
             const int r = px >> log2w, x = px & wmask;
             const bool row_ok = static_cast<unsigned>(y0 - 1 + r) < static_cast<unsigned>(H);
@@ -608,21 +606,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
             f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
 #pragma unroll
-            if (!(p.xf_debug & 1)) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float h = fmaf(v[i], ca[i], cs[i]);
-                float t;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-                v[i] = silu ? fmaf(h, t, h) : h + h;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float h = fmaf(v[i], ca[i], cs[i]);
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+              v[i] = silu ? fmaf(h, t, h) : h + h;
             }
             uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                  pack_bf16x2(v[6], v[7]));
             if (!row_ok) o = zero;    // rows outside the image are the convolution's padding
             sts128(a1 + it * 2048u, o);
             // dx = -1 box: operand pixel (r, x') = source pixel (r, x' - 1): this value lands at x + 1; column 0 is padding
-            if (p.xf_debug & 2) continue;
             sts128_or_zero(x != wmask, a0 + static_cast<uint32_t>(px + 1) * 128u, o, a0 + static_cast<uint32_t>(px - wmask) * 128u);
             // dx = +1 box: this value lands at x - 1; column W - 1 is padding
             sts128_or_zero(x != 0, a2 + static_cast<uint32_t>(px - 1) * 128u, o, a2 + static_cast<uint32_t>(px + wmask) * 128u);
@@ -960,7 +954,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const TcParams p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
   if (live) {
-    const float* wp = p.ws + static_cast<size_t>(p.ws_rows > 0 ? m % p.ws_rows : m) * p.cout + n;
+    const float* wp = p.ws + static_cast<size_t>(m) * p.cout + n;
     const size_t ss = static_cast<size_t>(p.m_pad) * p.cout;
     int s = 0;
     for (; s + 4 <= p.ksplit; s += 4) {   // fixed order: deterministic; 8 independent 16-byte loads in flight
@@ -1302,24 +1296,87 @@ int tc_prepare(const stedm_conv_desc* d, TcLaunch* L) {
 }  // namespace
 
 // out[m][n] = round(src[m % src_rows][n] + emb[(m / hw) * emb_stride + n]) (+ the per-(128-row tile, channel) statistics
-// a GroupNorm consumer folds): the split-K finish pass with one "partial" and a row broadcast.  Used where a convolution's
-// input is shared by the G halves of a guided batch and only the per-sample embedding differs (ResBlockStyle's first
-// convolution, openaimodel.py:291-297 after :278-287): the convolution runs once per distinct input, this pass expands it.
+// a GroupNorm consumer folds).  Used where a convolution's input is shared by the G halves of a guided batch and only the
+// per-sample embedding differs (ResBlockStyle's first convolution, openaimodel.py:291-297 after :277-286): the convolution
+// runs once per distinct input, this pass expands it.  A streaming pass (HBM / L2 bound): block = one 128-row tile x 256
+// channels, thread = (8-channel octet, row group) so that a warp reads 1 KB of one row; the statistics describe the STORED
+// values (bf16-rounded when the output is bf16, as in the convolution's epilogue) and are summed in a fixed order.
+namespace {
+constexpr int RAE_CH = 256, RAE_GROUPS = 8;
+__global__ void __launch_bounds__(256) rows_add_emb_kernel(const float* __restrict__ src, int src_rows,
+                                                           const float* __restrict__ emb, int emb_stride,
+                                                           void* __restrict__ out, int out_bf16, int M, int hw, int C,
+                                                           float* __restrict__ stats) {
+  __shared__ float s_red[RAE_GROUPS][RAE_CH][2];
+  const int tile = blockIdx.x, oct = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.y * RAE_CH + oct * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (n < C) {
+#pragma unroll 4
+    for (int i = 0; i < TC_BM / RAE_GROUPS; ++i) {
+      const int m = tile * TC_BM + rg + i * RAE_GROUPS;
+      if (m >= M) break;
+      const float* sp = src + static_cast<size_t>(m % src_rows) * C + n;
+      const float* ep = emb + static_cast<size_t>(m / hw) * emb_stride + n;
+      const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+      const float4 ea = *reinterpret_cast<const float4*>(ep), eb = *reinterpret_cast<const float4*>(ep + 4);
+      float v[8] = {a.x + ea.x, a.y + ea.y, a.z + ea.z, a.w + ea.w, b.x + eb.x, b.y + eb.y, b.z + eb.z, b.w + eb.w};
+      const size_t o = static_cast<size_t>(m) * C + n;
+      if (out_bf16) {
+        const uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                   pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + o) = u;
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+      } else {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(out) + o);
+        op[0] = make_float4(v[0], v[1], v[2], v[3]);
+        op[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] = fmaf(v[j], v[j], q[j]);
+      }
+    }
+  }
+  if (stats == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_red[rg][oct * 8 + j][0] = s[j];
+    s_red[rg][oct * 8 + j][1] = q[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.y * RAE_CH + threadIdx.x;
+  if (c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int g = 0; g < RAE_GROUPS; ++g) {
+      a += s_red[g][threadIdx.x][0];
+      b += s_red[g][threadIdx.x][1];
+    }
+    *reinterpret_cast<float2*>(stats + (static_cast<size_t>(tile) * C + c) * 2) = make_float2(a, b);
+  }
+}
+}  // namespace
+
 extern "C" int stedm_rows_add_emb(const float* src, long long src_rows, const float* emb, int emb_stride, void* out,
                                   int out_dtype, long long rows_out, int hw, int c, float* stats_out, void* stream) {
   STEDM_REQUIRE(src && emb && out && src_rows > 0 && rows_out > 0 && hw > 0 && c > 0 && c % 8 == 0 && rows_out % hw == 0 &&
-                    src_rows % hw == 0 && rows_out < (1LL << 31),
-                "rows_add_emb: bad argument (channels must be a multiple of 8, row counts multiples of hw)");
+                    src_rows % hw == 0 && rows_out < (1LL << 31) && src_rows < (1LL << 31) && emb_stride % 4 == 0,
+                "rows_add_emb: bad argument (channels must be a multiple of 8, row counts multiples of hw, emb rows 16-byte "
+                "aligned)");
   STEDM_REQUIRE(out_dtype == DT_BF16 || out_dtype == DT_F32, "rows_add_emb: bad output dtype");
   STEDM_REQUIRE(stats_out == nullptr || hw % TC_BM == 0, "rows_add_emb: tile statistics need hw %% 128 == 0");
-  TcParams p = {};
-  p.ws = const_cast<float*>(src); p.ws_rows = static_cast<int>(src_rows); p.ksplit = 1; p.m_pad = 0;
-  p.bias = nullptr; p.emb = emb; p.emb_stride = emb_stride; p.residual = nullptr; p.out = out;
-  p.M = static_cast<int>(rows_out); p.HW = hw; p.H = 1; p.W = hw; p.cout = c; p.cout_store = c;
-  p.out_dtype = out_dtype; p.res_dtype = DT_F32; p.stats_out = stats_out;
   const int m_tiles = static_cast<int>((rows_out + TC_BM - 1) / TC_BM);
-  splitk_finish_kernel<<<dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((c + SKF_CH - 1) / SKF_CH)), 256, 0,
-                         static_cast<cudaStream_t>(stream)>>>(p);
+  rows_add_emb_kernel<<<dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((c + RAE_CH - 1) / RAE_CH)), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(src, static_cast<int>(src_rows), emb, emb_stride, out,
+                                                             out_dtype == DT_BF16, static_cast<int>(rows_out), hw, c, stats_out);
   return check_launch("rows_add_emb");
 }
 
@@ -1431,7 +1488,7 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   STEDM_REQUIRE(d->cout % bn == 0 || (d->cout % 32 == 0 && d->out_nchw == 0),
                 "conv_tc: cout %d with a partial last channel tile needs cout %% 32 == 0 and NHWC output", d->cout);
   p.ksplit = plan.ksplit; p.kb_per_split = plan.kb_per_split; p.m_pad = plan.m_pad;
-  p.ws = static_cast<float*>(d->workspace); p.ws_rows = 0;
+  p.ws = static_cast<float*>(d->workspace);
   p.emb_stride = d->emb_stride; p.res_dtype = d->res_dtype; p.out_dtype = d->out_dtype;
   p.out_nchw = d->out_nchw; p.cout_store = d->cout_store > 0 ? d->cout_store : d->cout;
   p.tap_mode = d->tap_mode; p.py = d->phase >> 1; p.px = d->phase & 1;
@@ -1448,8 +1505,6 @@ extern "C" int stedm_conv_tc(const stedm_conv_desc* d, void* stream) {
   }
   p.gn_coef = d->gn_coef; p.gn_cstride = d->gn_cstride; p.gn_c_off = d->gn_c_off; p.gn_silu = d->gn_silu;
   p.nb = 0; p.a_pool_bytes = 0; p.log2w = 0;
-  static const int xf_debug = [] { const char* e = getenv("STEDM_XF_DEBUG"); return e ? atoi(e) : 0; }();
-  p.xf_debug = xf_debug;
   while ((1 << p.log2w) < W) ++p.log2w;
   p.stats_out = nullptr; p.stats_tile_base = 0;
   if (d->stats_out != nullptr) {

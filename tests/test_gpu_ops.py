@@ -300,3 +300,10 @@ def test_rows_add_emb_broadcast_and_statistics(ops):
     assert max_abs(tiles[..., 0].cpu(), t.sum(1)) < 2e-3 and max_abs(tiles[..., 1].cpu(), (t * t).sum(1)) < 2e-2
     out32 = ops.rows_add_emb(src.cuda(), emb.cuda(), G, out_dtype=torch.float32, want_stats=False)
     assert torch.equal(out32.cpu(), src.repeat(G, 1, 1, 1) + emb[:, None, None, :]) and out32._gn_tiles is None
+    # ragged: 320 channels (a partial second channel block), 8 x 8 maps (tiles straddle samples, no statistics),
+    # 3 x 64 = 192 rows (a partial last tile)
+    src = torch.randn(1, 8, 8, 320, generator=g)
+    emb = torch.randn(3, 320, generator=g)
+    out = ops.rows_add_emb(src.cuda(), emb.cuda(), 3)
+    assert out._gn_tiles is None
+    assert torch.equal(out.cpu(), (src.repeat(3, 1, 1, 1) + emb[:, None, None, :]).to(torch.bfloat16))
