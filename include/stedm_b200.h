@@ -72,6 +72,15 @@ int stedm_gn_stats(const void* x0, const void* x1, int in_dtype, int batch, int 
 int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int batch, int x1_batch, int hw, int c0, int c1,
                    const double* partials, int n_chunks, const float* gamma, const float* beta, float eps,
                    int apply_silu, void* out, int out_dtype, void* stream);
+/* stedm_gn_apply for a concat whose second source is shared by the cond / uncond halves of a guided batch (x1 has
+ * x1_batch < batch samples, broadcast as b % x1_batch; bf16 in, bf16 out).  Channels [split_c, c0 + c1) must lie in groups
+ * made of x1 channels only: their normalised values repeat with period x1_batch and are written once per distinct sample
+ * to out_hi [x1_batch][hw][c0 + c1 - split_c]; channels [0, split_c) go to out_lo [batch][hw][split_c].  The consumer
+ * convolution takes (out_lo, out_hi) as its two sources, the second one broadcast (stedm_conv_desc.x1_batch).  Element
+ * for element the values stedm_gn_apply writes (openaimodel.py:800 th.cat + util.py:199-216). */
+int stedm_gn_apply_split(const void* x0, const void* x1, int batch, int x1_batch, int hw, int c0, int c1,
+                         const double* partials, int n_chunks, const float* gamma, const float* beta, float eps,
+                         int apply_silu, int split_c, void* out_lo, void* out_hi, void* stream);
 /* Statistics pass folded into the producing convolutions: reduce the per-(128-pixel tile, channel) sums written by
  * stedm_conv_tc (stedm_conv_desc.stats_out) for the one or two producers of a GroupNorm input into
  * out = double [batch][1][32][2].  Source s: fp32 [reps_s][rep_stride_s tiles][c_s][2]; sample b owns tile rows

@@ -37,6 +37,7 @@ SIGNATURES = {
     "stedm_gn_num_chunks": [i32, i32],
     "stedm_gn_stats": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "stedm_gn_apply": [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, i32, vp, i32, vp],
+    "stedm_gn_apply_split": [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, i32, i32, vp, vp, vp],
     "stedm_gn_fold_tiles": [vp, i32, i32, i64, i32, i32, vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, f32, i32, vp, vp],
     "stedm_rows_add_emb": [vp, i64, vp, i32, vp, i32, i64, i32, i32, vp, vp],
     "stedm_conv_tc": [C.POINTER(ConvDesc), vp],

@@ -138,17 +138,31 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
 }
 
 template <typename TI, typename TO, bool kPrecise>
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restrict__ x0, const TI* __restrict__ x1,
+__global__ void __launch_bounds__(GN_THREADS, kPrecise ? 1 : 6) gn_apply_kernel(const TI* __restrict__ x0, const TI* __restrict__ x1,
                                                               int x1_batch, int hw, int c0, int c1, int pix_per_block,
                                                               const double* __restrict__ partials, int n_chunks,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int apply_silu,
-                                                              TO* __restrict__ out) {
+                                                              TO* __restrict__ out, int tpi_lo, int split_c,
+                                                              int batch_lo, TO* __restrict__ out_hi, int tpi_hi) {
   extern __shared__ float s_ab[];  // scale[C], shift[C]
   __shared__ double s_tot[2 * GN_GROUPS];
   __shared__ float s_mr[2 * GN_GROUPS];  // per group: mean, rstd
-  const int C = c0 + c1, items = C / 8, cpg = C / GN_GROUPS;
-  const int b = blockIdx.y, b1 = (x1_batch > 0) ? (b % x1_batch) : b;
+  const int C = c0 + c1, cpg = C / GN_GROUPS;
+  // split mode (stedm_gn_apply_split): rows y < batch_lo of the grid write channels [0, split_c) of sample y to `out`,
+  // rows above write channels [split_c, C) of sample y - batch_lo to `out_hi`; both outputs are dense
+  int b = blockIdx.y, c_begin = 0, c_end = C;
+  if (split_c > 0) {
+    if (b < batch_lo) {
+      c_end = split_c;
+    } else {
+      b -= batch_lo;
+      c_begin = split_c;
+      out = out_hi;
+    }
+  }
+  const int items = (c_end - c_begin) / 8, item_base = c_begin / 8, c_out = c_end - c_begin;
+  const int b1 = (x1_batch > 0) ? (b % x1_batch) : b;
   {
     // fold the per-chunk partials: 64 outputs x 4 threads, fixed strided partition + fixed shuffle tree
     // (deterministic); the loads of one thread are independent, so they are issued in batches
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
     s_mr[threadIdx.x * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+  for (int c = c_begin + threadIdx.x; c < c_end; c += GN_THREADS) {
     const int g = c / cpg;
     const float a = s_mr[g * 2 + 1] * gamma[c];
     s_ab[c] = a;
@@ -181,19 +195,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
   // thread -> (pixel lane, channel item): no integer division in the streaming loop, the item's scale/shift
   // live in registers, and the unrolled pixel loop keeps several independent 16 B loads in flight per thread
   const int p_begin = blockIdx.x * pix_per_block, p_end = min(hw, p_begin + pix_per_block);
-  const int tpi = min(items, GN_THREADS), lanes = GN_THREADS / tpi;
+  const int tpi = (split_c > 0 && c_begin > 0) ? tpi_hi : tpi_lo;   // threads along the item axis (apply_threads_per_item)
+  const int lanes = GN_THREADS / tpi;
   const int lane = threadIdx.x / tpi, it0 = threadIdx.x % tpi;
   if (lane >= lanes) return;
   for (int item = it0; item < items; item += tpi) {
+    const int gi = item_base + item;          // item of the concat's channel axis
     float a[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = s_ab[item * 8 + j];
-      sh[j] = s_ab[C + item * 8 + j];
+      a[j] = s_ab[gi * 8 + j];
+      sh[j] = s_ab[C + gi * 8 + j];
     }
-    const TI* src = item_ptr<TI>(x0, x1, b, b1, 0, hw, c0, c1, item);
-    const size_t src_stride = (item * 8 < c0) ? c0 : c1;
-    TO* dst = out + static_cast<size_t>(b) * hw * C + item * 8;
+    const TI* src = item_ptr<TI>(x0, x1, b, b1, 0, hw, c0, c1, gi);
+    const size_t src_stride = (gi * 8 < c0) ? c0 : c1;
+    TO* dst = out + static_cast<size_t>(b) * hw * c_out + item * 8;
     int p = p_begin + lane;
     for (; p + (GN_MLP - 1) * lanes < p_end; p += GN_MLP * lanes) {
       float v[GN_MLP][8];
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
           if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
           v[u][j] = y;
         }
-        store8<TO>(dst + static_cast<size_t>(p + u * lanes) * C, v[u]);
+        store8<TO>(dst + static_cast<size_t>(p + u * lanes) * c_out, v[u]);
       }
     }
     for (; p < p_end; p += lanes) {
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restri
         if (apply_silu) y = kPrecise ? silu_precise(y) : silu_f(y);
         v[j] = y;
       }
-      store8<TO>(dst + static_cast<size_t>(p) * C, v);
+      store8<TO>(dst + static_cast<size_t>(p) * c_out, v);
     }
   }
 }
@@ -417,6 +433,22 @@ __global__ void __launch_bounds__(FOLD_THREADS) gn_fold_tiles_kernel(FoldSrc s0,
   }
 }
 
+// Threads along the item (8-channel) axis of an apply block; the other GN_THREADS / tpi are pixel lanes and a thread loops
+// over items it0, it0 + tpi, ...  The split that keeps the most threads busy: e.g. 192 items -> 64 threads x 4 lanes x 3
+// items each instead of 192 threads x 1 lane with a quarter of the block idle — as long as every lane keeps GN_MLP pixels
+// for the unrolled loop.
+int apply_threads_per_item(int items, int pix_per_block) {
+  int tpi = items < GN_THREADS ? items : GN_THREADS, best = 0;
+  const int max_lanes = max(GN_THREADS / tpi, pix_per_block / GN_MLP);
+  for (int k = 1; k <= 8; ++k) {
+    const int t = (items + k - 1) / k;
+    if (t > GN_THREADS || GN_THREADS / t > max_lanes) continue;
+    const int score = items * (GN_THREADS / t) / k;   // busy thread-iterations per unit of block time
+    if (score > best) { best = score; tpi = t; }
+  }
+  return tpi;
+}
+
 int apply_pix_per_block(int batch, int hw, int C) {
   // >= 64 KB of input per block (amortises the per-block scale/shift prologue) unless that leaves the GPU short of
   // ~4 blocks per SM, then smaller down to 8 KB
@@ -488,11 +520,12 @@ extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int 
   const int ppb = apply_pix_per_block(batch, hw, C);
   dim3 grid((hw + ppb - 1) / ppb, batch);
   const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+  const int tpi = apply_threads_per_item(C / 8, ppb < hw ? ppb : hw);
   auto s = static_cast<cudaStream_t>(stream);
 #define LAUNCH(TI, TO, PREC)                                                                                       \
   gn_apply_kernel<TI, TO, PREC><<<grid, GN_THREADS, smem, s>>>(static_cast<const TI*>(x0), static_cast<const TI*>(x1), \
                                                               x1_batch, hw, c0, c1, ppb, partials, n_chunks, gamma, \
-                                                              beta, eps, apply_silu, static_cast<TO*>(out))
+                                                              beta, eps, apply_silu, static_cast<TO*>(out), tpi, 0, 0, nullptr, 0)
   static const bool kBulk = [] { const char* e = getenv("STEDM_GN_BULK"); return !(e && e[0] == '0'); }();
   if (in_dtype == DT_BF16 && out_dtype == DT_BF16 && kBulk && c0 <= 2048 && c1 == 0) {  // measured: +10-17 % for one source, slower for a concat (two short pipelines)
     // throughput path: TMA-bulk staged input (needs 16-byte items per pixel <= 256 per source)
@@ -521,4 +554,35 @@ extern "C" int stedm_gn_apply(const void* x0, const void* x1, int in_dtype, int 
   }
 #undef LAUNCH
   return check_launch("gn_apply");
+}
+
+// GroupNorm (+ SiLU) of [x0 | x1] where x1 holds `x1_batch` < `batch` DISTINCT samples broadcast as b % x1_batch (guided
+// sampling: the encoder skips are shared by the cond / uncond halves).  Channels [split_c, C) lie in groups made of x1
+// channels only, so their normalised values repeat with period x1_batch: they are written ONCE per distinct sample to
+// `out_hi` [x1_batch][hw][C - split_c]; channels [0, split_c) go to `out_lo` [batch][hw][split_c].  Same arithmetic per
+// element as stedm_gn_apply (whose output is [out_lo | out_hi broadcast]); one launch.
+extern "C" int stedm_gn_apply_split(const void* x0, const void* x1, int batch, int x1_batch, int hw, int c0, int c1,
+                                    const double* partials, int n_chunks_in, const float* gamma, const float* beta,
+                                    float eps, int apply_silu, int split_c, void* out_lo, void* out_hi, void* stream) {
+  const int C = c0 + c1;
+  STEDM_REQUIRE(x0 && x1 && partials && gamma && beta && out_lo && out_hi, "gn_apply_split: null pointer");
+  STEDM_REQUIRE(batch > 0 && hw > 0 && c0 > 0 && c1 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GN_GROUPS == 0 && C <= 4096,
+                "gn_apply_split: bad channel counts (%d + %d)", c0, c1);
+  STEDM_REQUIRE(x1_batch > 0 && x1_batch < batch && batch % x1_batch == 0, "gn_apply_split: x1_batch %d must divide batch %d",
+                x1_batch, batch);
+  const int cpg = C / GN_GROUPS;
+  STEDM_REQUIRE(split_c % 8 == 0 && split_c < C && split_c >= (c0 + cpg - 1) / cpg * cpg,
+                "gn_apply_split: channels from %d on must lie in groups without x0 channels (c0 %d, %d per group)", split_c,
+                c0, cpg);
+  const int sppb = stats_pix_per_block(hw, C);
+  const int n_chunks = n_chunks_in > 0 ? n_chunks_in : (hw + sppb - 1) / sppb;
+  const int ppb = apply_pix_per_block(batch, hw, split_c);   // sized by the bytes a block of the wide part streams
+  dim3 grid((hw + ppb - 1) / ppb, batch + x1_batch);
+  gn_apply_kernel<__nv_bfloat16, __nv_bfloat16, false><<<grid, GN_THREADS, static_cast<size_t>(2) * C * sizeof(float),
+                                                         static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), x1_batch, hw, c0, c1, ppb, partials,
+      n_chunks, gamma, beta, eps, apply_silu, static_cast<__nv_bfloat16*>(out_lo),
+      apply_threads_per_item(split_c / 8, ppb < hw ? ppb : hw), split_c, batch, static_cast<__nv_bfloat16*>(out_hi),
+      apply_threads_per_item((C - split_c) / 8, ppb < hw ? ppb : hw));
+  return check_launch("gn_apply_split");
 }

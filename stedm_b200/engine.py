@@ -10,6 +10,7 @@ Weights stay visible as nn.Parameters under the reference's names; the packed co
 and rebuilt whenever the owner invalidates them (load_state_dict / .to()).
 """
 import math
+import os
 
 import torch
 
@@ -20,6 +21,7 @@ FUSE_SKIP = [True]   # fold ResBlock 1x1 skip convolutions into the second 3x3 c
 SPLIT_CONCAT = [True]  # decoder conv1([h | skip]): the skip channels shared by cond / uncond convolved once per distinct sample
 SHARE_STYLE_CONV = [True]  # ResBlockStyle under guidance: its first convolution once per distinct input, the style embeddings added after
 SPLIT_MIN_SHARED = 384  # ... when at least this many input channels are shared (PackedResBlock._split_point)
+SPLIT_GN = [os.environ.get("STEDM_SPLIT_GN", "1") != "0"]  # ... and their GroupNorm + SiLU written once per distinct sample (ops.gn_apply_split), whatever their number
 PAD_SIMT = 4
 
 
@@ -262,6 +264,17 @@ class PackedNorm:
             return None
         return ops.gn_fold_tiles(t0, t1, x0.shape[0], coef_for=(self.gamma, self.beta, self.eps, x0.shape[1] * x0.shape[2]))
 
+    def split(self, x0, x1, sp, silu, stats):
+        """__call__ for a concat whose skip half x1 is shared by the halves of a guided batch: (a[..., :sp] for every
+        sample, a[..., sp:] once per distinct skip sample), see ops.gn_apply_split."""
+        t0 = getattr(x0, "_gn_tiles", None)
+        t1 = getattr(x1, "_gn_tiles", None)
+        if t0 is not None and t1 is not None:
+            folded = ops.gn_fold_tiles(t0, t1, x0.shape[0])
+            return ops.gn_apply_split(x0, x1, folded, self.gamma, self.beta, self.eps, silu, sp, n_chunks=1)
+        stats = ops.gn_stats(x0, x1, stats)
+        return ops.gn_apply_split(x0, x1, stats, self.gamma, self.beta, self.eps, silu, sp)
+
     def __call__(self, x0, x1, silu, out_dtype, stats):
         t0 = getattr(x0, "_gn_tiles", None)
         t1 = getattr(x1, "_gn_tiles", None) if x1 is not None else None
@@ -306,14 +319,20 @@ class PackedResBlock:
         the h | skip boundary (= c0 when no group straddles).  Returns 0 when not applicable or not worth it: the saved
         FLOPs (9 * shared * 2 per output) must outweigh writing and twice re-reading the fp32 partial (12 B per
         output) at ~200 FLOP per HBM byte, with margin."""
-        if not (SPLIT_CONCAT[0] and self.c1.tc and x1 is not None and x1.shape[0] < x0.shape[0]):
+        sp = self._shared_from(x0, x1)
+        return sp if SPLIT_CONCAT[0] and sp and x0.shape[-1] + x1.shape[-1] - sp >= SPLIT_MIN_SHARED else 0
+
+    def _shared_from(self, x0, x1):
+        """First channel (a K-slab boundary) from which the normalised concat [x0 | x1] depends on x1 alone, for an x1 that
+        holds fewer distinct samples than x0; 0 when there is no such channel or the tensor-core path does not run."""
+        if not (self.c1.tc and x1 is not None and x1.shape[0] < x0.shape[0]):
             return 0
         c0, c1 = x0.shape[-1], x1.shape[-1]
-        if c0 % PAD_TC or c1 % PAD_TC or (c0 + c1) % 32 or not self.c1.tc_ok(x0):
+        if c0 % PAD_TC or c1 % PAD_TC or (c0 + c1) % 32 or not self.c1.tc_ok(x0, x1):
             return 0
         cpg = (c0 + c1) // 32
         sp = _round_up(_round_up(c0, cpg), PAD_TC)
-        return sp if c0 + c1 - sp >= SPLIT_MIN_SHARED else 0
+        return sp if sp < c0 + c1 else 0
 
     def _conv1(self, x0, x1, emb, pool):
         """conv1(SiLU(GN([x0 | x1]))) + emb, with the fold / split / fusion choices of the tensor-core path."""
@@ -342,19 +361,29 @@ class PackedResBlock:
                          residual=part, out_dtype=self.prec.act, tensor_core=True, stats_out=tiles, gn_coef=coef)
             h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
             return h
-        a = self.n1(x0, x1, True, self.prec.act, pool.next())
-        if sp:
-            bs = x1.shape[0]
-            w_lo, w_hi = self.c1.split_weights(sp)
-            # shared channels: one pass over the bs distinct samples (fp32 partial sums, no bias) ...
-            part = ops.conv(a[:bs, :, :, sp:], w_hi, None, self.c1.cout, 3, out_dtype=torch.float32, tensor_core=True)
-            # ... the rest: + bias + embedding + the partial broadcast as b % bs, statistics of the sum for the next GN
-            tiles, meta = self.c1._tile_stats(x0, True)
-            h = ops.conv(a[..., :sp], w_lo, self.c1.bias, self.c1.cout, 3, emb=emb, residual=part,
-                         out_dtype=self.prec.act, tensor_core=True, stats_out=tiles)
-            h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
-            return h
-        return self.c1(a, emb=emb, want_stats=True)
+        sg = self._shared_from(x0, x1) if SPLIT_GN[0] and x0.dtype == torch.bfloat16 and self.prec.act == torch.bfloat16 else 0
+        if sg and not sp and (x0.shape[-1] + x1.shape[-1] - sg) * 4 < x0.shape[-1] + x1.shape[-1]:
+            sg = 0    # under a quarter of the channels shared (640 = 512 + 128 at 64 x 64: 64 of them): measured no gain
+        if sg:
+            # the normalised skip-only channels [sg, C) once per distinct skip sample, the rest per sample (sg == sp when
+            # the convolution is split too)
+            a_lo, a_hi = self.n1.split(x0, x1, sg, True, pool.next())
+            if not sp:
+                return self.c1(a_lo, a_hi, emb=emb, want_stats=True)
+        else:
+            a = self.n1(x0, x1, True, self.prec.act, pool.next())
+            if not sp:
+                return self.c1(a, emb=emb, want_stats=True)
+            a_lo, a_hi = a[..., :sp], a[:x1.shape[0], :, :, sp:]
+        w_lo, w_hi = self.c1.split_weights(sp)
+        # shared channels: one pass over the distinct skip samples (fp32 partial sums, no bias) ...
+        part = ops.conv(a_hi, w_hi, None, self.c1.cout, 3, out_dtype=torch.float32, tensor_core=True)
+        # ... the rest: + bias + embedding + the partial broadcast as b % bs, statistics of the sum for the next GN
+        tiles, meta = self.c1._tile_stats(x0, True)
+        h = ops.conv(a_lo, w_lo, self.c1.bias, self.c1.cout, 3, emb=emb, residual=part,
+                     out_dtype=self.prec.act, tensor_core=True, stats_out=tiles)
+        h._gn_tiles = meta if getattr(h, "_stats_written", False) else None
+        return h
 
     def call_shared_input(self, x0, emb, pool, groups):
         """The block on ``groups`` copies of the SAME input x0 [B] that differ only in their embedding rows emb [groups*B]

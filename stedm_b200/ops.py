@@ -140,6 +140,21 @@ def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
     return out
 
 
+def gn_apply_split(x0, x1, stats, gamma, beta, eps, silu, split_c, n_chunks=0):
+    """gn_apply for a concat whose second source x1 holds fewer (distinct) samples than x0: returns (lo, hi) with
+    lo = channels [0, split_c) for every sample and hi = channels [split_c, C) once per DISTINCT x1 sample — the channels
+    from split_c on lie in groups of x1 channels only, so they do not depend on x0.  [lo | hi broadcast] == gn_apply(...)."""
+    _cuda(x0, x1, stats, gamma, beta)
+    b, h, w, c0 = x0.shape
+    bs, c1 = x1.shape[0], x1.shape[-1]
+    assert x0.dtype == torch.bfloat16 and x1.dtype == torch.bfloat16 and bs < b
+    lo = torch.empty((b, h, w, split_c), device=x0.device, dtype=torch.bfloat16)
+    hi = torch.empty((bs, h, w, c0 + c1 - split_c), device=x0.device, dtype=torch.bfloat16)
+    _call("stedm_gn_apply_split", _ptr(x0), _ptr(x1), b, bs, h * w, c0, c1, _ptr(stats), n_chunks, _ptr(gamma), _ptr(beta),
+          float(eps), 1 if silu else 0, split_c, _ptr(lo), _ptr(hi), _stream())
+    return lo, hi
+
+
 def group_norm(x0, x1, gamma, beta, eps, silu, out_dtype, stats=None):
     """GroupNorm(32) (+SiLU) of the channel concat [x0 | x1]; returns the normalised NHWC tensor."""
     stats = gn_stats(x0, x1, stats)

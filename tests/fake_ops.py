@@ -93,6 +93,11 @@ def gn_apply(x0, x1, stats, gamma, beta, eps, silu, out_dtype, n_chunks=0):
     return _nhwc(F.silu(y) if silu else y).to(out_dtype)
 
 
+def gn_apply_split(x0, x1, stats, gamma, beta, eps, silu, split_c, n_chunks=0):
+    full = gn_apply(x0, x1, stats, gamma, beta, eps, silu, x0.dtype, n_chunks)
+    return full[..., :split_c].contiguous(), full[:x1.shape[0], :, :, split_c:].contiguous()
+
+
 def upsample_nearest2x(x):
     return _nhwc(F.interpolate(_nchw(x.float()), scale_factor=2, mode="nearest")).to(x.dtype)
 

@@ -151,10 +151,13 @@ def test_split_point_of_concat_conv(patched, c0, c1, want):
     """PackedResBlock._split_point: the channels of the normalised [h | skip] concat above the split must belong to
     GroupNorm groups that lie wholly inside the skip half (their values are then shared by cond / uncond)."""
     blk = patched.PackedResBlock.__new__(patched.PackedResBlock)
-    blk.c1 = type("C", (), {"tc": True, "tc_ok": staticmethod(lambda x: True)})()
+    blk.c1 = type("C", (), {"tc": True, "tc_ok": staticmethod(lambda x0, x1=None: True)})()
     x0, x1 = torch.empty(4, 16, 16, c0), torch.empty(2, 16, 16, c1)
     sp = blk._split_point(x0, x1)
     assert sp == want
+    # the GroupNorm of the skip-only channels is shared whatever their number (engine.SPLIT_GN)
+    cpg_, sg = (c0 + c1) // 32, blk._shared_from(x0, x1)
+    assert sg == -(-(-(-c0 // cpg_) * cpg_) // 64) * 64 and (not sp or sg == sp)
     if sp:
         cpg = (c0 + c1) // 32
         assert sp % 64 == 0 and sp >= c0 and (sp // cpg) * cpg >= c0 and all((g * cpg >= c0) for g in range(-(-sp // cpg), 32))

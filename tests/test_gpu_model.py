@@ -413,6 +413,29 @@ def test_shared_style_block_convolution_at_latent64():
     assert rel_err(xa, g["x_after_1"]) < BF16_EPS_BAR and rel_err(xb, g["x_after_1"]) < BF16_EPS_BAR
 
 
+def test_split_groupnorm_of_shared_skips_is_bit_identical():
+    """engine.SPLIT_GN: decoder ResBlocks normalise the skip-only channels of [h | skip] once per distinct skip sample
+    (ops.gn_apply_split) and feed the convolution two sources — same values, same K order: the guided eps must not move
+    by a bit (latent 64: all nine concat sites, with and without the split convolution)."""
+    from stedm_b200 import engine
+    g = load_golden("c1_b4_l64")
+    _, _, x4 = O.synthetic_batch(4, 256, 1, 1)
+    m = build_model(64, n_style=1, precision="bf16")
+    unet = m._model.model.diffusion_model
+    cc = torch.from_numpy(g["c_concat"]).cuda()
+    ctx = torch.cat([torch.from_numpy(g["uc_crossattn"]), torch.from_numpy(g["c_crossattn"])]).cuda()
+    ts = torch.full((4,), 481, dtype=torch.long, device="cuda")
+    outs = {}
+    for flag in (True, False):
+        saved = engine.SPLIT_GN[0]
+        engine.SPLIT_GN[0] = flag
+        try:
+            outs[flag] = unet.forward_split(x4.cuda(), cc, ts, ctx).clone()
+        finally:
+            engine.SPLIT_GN[0] = saved
+    assert outs[True].shape[0] == 8 and torch.equal(outs[True], outs[False])
+
+
 def test_latent128_eps_and_decode_vs_oracle():
     """BASELINE configs[3] geometry (512^2 image, latent 128: full-row 128-pixel tiles, 16 384-token decoder
     attention) against the CPU oracle run live on the same fixture weights: batch 1, and the same sample as row 0 of a

@@ -92,6 +92,26 @@ def test_group_norm_broadcast_skip(ops):
     assert max_abs(nchw(got.cpu()), want) < 5e-5
 
 
+@pytest.mark.parametrize("c0,c1,hw,split_c", [(128, 128, 16, 128), (512, 128, 8, 576), (1024, 512, 8, 1088),
+                                               (64, 192, 12, 64), (512, 256, 8, 576)])
+def test_group_norm_split_for_shared_skip(ops, c0, c1, hw, split_c):
+    """gn_apply_split: the skip-only channels of the normalised concat once per distinct skip sample, the rest per
+    sample — bit for bit the slices of the one-tensor apply (ragged channel counts: 17 / 46 / 80 items per pixel)."""
+    g = _gen(40)
+    B, bs = 4, 2
+    x0 = nhwc(torch.randn(B, c0, hw, hw, generator=g) * 2 + 0.5).to(torch.bfloat16).cuda()
+    x1 = nhwc(torch.randn(bs, c1, hw, hw, generator=g) - 1).to(torch.bfloat16).cuda()
+    gamma, beta = torch.randn(c0 + c1, generator=g).cuda(), torch.randn(c0 + c1, generator=g).cuda()
+    stats = ops.gn_stats(x0, x1, None)
+    full = ops.gn_apply(x0, x1, stats, gamma, beta, 1e-5, True, torch.bfloat16)
+    lo, hi = ops.gn_apply_split(x0, x1, stats, gamma, beta, 1e-5, True, split_c)
+    assert tuple(lo.shape) == (B, hw, hw, split_c) and tuple(hi.shape) == (bs, hw, hw, c0 + c1 - split_c)
+    assert torch.equal(lo, full[..., :split_c])
+    assert torch.equal(hi, full[:bs, :, :, split_c:]) and torch.equal(hi, full[bs:, :, :, split_c:])
+    with pytest.raises(RuntimeError, match="groups without x0 channels"):
+        ops.gn_apply_split(x0, x1, stats, gamma, beta, 1e-5, True, c0 - 8)     # channel c0 - 8 shares a group with x0
+
+
 # ---------------------------------------------------------------------------------------------- SIMT conv
 def _simt_w(w):
     co = w.shape[0]
