@@ -352,7 +352,6 @@ class PackedResBlock:
         if coef is not None:
             if not sp:
                 return self.c1(x0, x1, emb=emb, want_stats=True, gn=(coef, True))
-            bs = x1.shape[0]
             w_lo, w_hi = self.c1.split_weights(sp)
             part = ops.conv(x1[:, :, :, sp - c0:], w_hi, None, self.c1.cout, 3, out_dtype=torch.float32,
                             tensor_core=True, gn_coef=coef, gn_c_off=sp)
