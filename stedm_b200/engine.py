@@ -20,7 +20,7 @@ PAD_TC = 64   # channel padding granularity of the tensor-core path (one 128-byt
 FUSE_SKIP = [True]   # fold ResBlock 1x1 skip convolutions into the second 3x3 conv (A/B switch for measurements)
 SPLIT_CONCAT = [True]  # decoder conv1([h | skip]): the skip channels shared by cond / uncond convolved once per distinct sample
 SHARE_STYLE_CONV = [True]  # ResBlockStyle under guidance: its first convolution once per distinct input, the style embeddings added after
-SPLIT_MIN_SHARED = 384  # ... when at least this many input channels are shared (PackedResBlock._split_point)
+SPLIT_MIN_SHARED = 384  # ... when at least this many input channels are shared (PackedResBlock._split_point); 128 measured: -1.3 % images/s
 SPLIT_GN = [os.environ.get("STEDM_SPLIT_GN", "1") != "0"]  # ... and their GroupNorm + SiLU written once per distinct sample (ops.gn_apply_split), whatever their number
 PAD_SIMT = 4
 
